@@ -1,0 +1,196 @@
+"""Pin oracle/ against vectors recorded from the reference's own code (tests/golden/make_golden.py)."""
+import hashlib
+
+import numpy as np
+import torch
+
+from oracle import ddim, hmc as ohmc, operators as oops, schedule as osch, unet as ounet
+from oracle.tinynet import TinyEpsNet
+
+T = torch.from_numpy
+
+
+def test_alpha_table_and_sequence(golden):
+    g = golden("schedule.npz")
+    betas = osch.beta_schedule("linear", 1e-4, 0.02, 1000)
+    assert np.array_equal(betas, g["betas"])
+    tab = osch.alpha_bar_table(betas)
+    assert np.array_equal(tab.numpy(), g["alpha_table"])          # bit-exact fp32
+    assert tab[0] == 1.0
+    np.testing.assert_allclose(tab[[251, 501, 751]].numpy(), [0.52142, 0.077797, 0.0033002], rtol=2e-5)
+    seq, seq_next = osch.timestep_sequence(1000, 3)
+    assert seq == list(g["seq"]) and seq_next == list(g["seq_next"])
+    a = osch.compute_alpha(betas, [750, -1])
+    assert a.shape == (2, 1, 1, 1) and a[1].item() == 1.0
+
+
+def test_inpaint_mask_pins(golden):
+    g = golden("inpaint_mask.npz")
+    torch.manual_seed(5678)
+    miss = osch and oops.random_inpaint_missing_pixels(256)
+    torch.manual_seed(5678)
+    perm = torch.randperm(256 ** 2)
+    assert np.array_equal(perm[:8].numpy(), g["perm_head"])
+    assert perm[:8].tolist() == [34932, 31276, 34720, 52821, 59459, 18816, 31389, 3592]
+    op = oops.Inpainting(3, 256, miss)
+    kept = op.kept_pix.numpy()
+    assert len(kept) == int(g["kept_count"]) == 5243
+    assert np.array_equal(kept[:10], g["kept_head"])
+    assert hashlib.sha1(kept.astype(np.int64).tobytes()).digest() == bytes(g["sha1"])
+    # small case built by the reference's own constructor: kept_indices = 3*pix + c ascending
+    op2 = oops.Inpainting.from_missing_indices(3, 32, g["small_missing"])
+    ki = (3 * op2.kept_pix[:, None] + torch.arange(3)[None]).reshape(-1)
+    assert np.array_equal(ki.numpy(), g["small_kept_indices"])
+
+
+def _make_ops(g):
+    D = 32
+    ops = {
+        "inp": oops.Inpainting.from_missing_indices(3, D, g["inp_missing"]),
+        "sr4": oops.SuperResolution(3, D, 4),
+        "sr16": oops.SuperResolution(3, D, 16),
+        "sr2": oops.SuperResolution(3, D, 2),
+        "hdr": oops.HDR(),
+        "deblur": oops.Deblurring2D(3, D, T(g["deblur_tab_U_small1"]), T(g["deblur_tab_V_small1"]),
+                                    T(g["deblur_tab_U_small2"]), T(g["deblur_tab_V_small2"]),
+                                    T(g["deblur_tab_singulars"]), T(g["deblur_tab_perm"])),
+        "phase": oops.PhaseRetrieval(2.0),
+    }
+    return ops
+
+
+def test_operators_match_reference(golden):
+    g = golden("operators.npz")
+    for name, op in _make_ops(g).items():
+        x, y = T(g[name + "_x"]), T(g[name + "_y"])
+        Hx = op.H(x.clamp(-1, 1))
+        np.testing.assert_allclose(Hx.numpy(), g[name + "_Hx"], atol=2e-5, rtol=1e-5, err_msg=name)
+        r, loss = op.residual(x, y)
+        np.testing.assert_allclose(loss.sum().item(), float(g[name + "_loss"]), rtol=2e-5, err_msg=name)
+        grad = op.grad(x, y)
+        scale = np.abs(g[name + "_grad"]).max()
+        np.testing.assert_allclose(grad.numpy(), g[name + "_grad"], atol=2e-5 * max(1.0, scale), err_msg=name)
+        pinv = op.H_pinv(y)
+        np.testing.assert_allclose(pinv.reshape(g[name + "_pinv"].shape).numpy(), g[name + "_pinv"],
+                                   atol=5e-4 if name == "deblur" else 2e-5, rtol=1e-4, err_msg=name)
+
+
+def test_deblur_tables_rebuild(golden):
+    """Our restatement of the band matrix + SVD table construction reproduces the reference's tables."""
+    g = golden("operators.npz")
+    U1, V1, U2, V2, s, perm = oops.deblur2d_tables(T(g["deblur_kernel1"]), T(g["deblur_kernel2"]), 32)
+    assert np.array_equal(s.numpy(), g["deblur_tab_singulars"])
+    assert np.array_equal(perm.numpy(), g["deblur_tab_perm"])
+    assert np.array_equal(U1.numpy(), g["deblur_tab_U_small1"])
+    k1 = oops.gaussian_taps(1.0); k2 = oops.gaussian_taps(20.0)
+    assert np.array_equal(k1.numpy(), g["deblur_kernel1"]) and np.array_equal(k2.numpy(), g["deblur_kernel2"])
+    st = golden("deblur256_stats.npz")
+    assert int(st["nz1"]) == 218 and int(st["nz2"]) == 227 and int(st["nnz"]) == 49486
+
+
+def test_ddim_epilogue_matches_reference(golden):
+    g = golden("ddim.npz")
+    net = TinyEpsNet()
+    tab = osch.alpha_bar_table(osch.beta_schedule("linear", 1e-4, 0.02, 1000))
+    x = T(g["x"])
+    eps_net = ohmc.module_eps_net(net)
+    # single step t=750 -> 500
+    eps, _ = eps_net(x, 750)
+    np.testing.assert_allclose(eps.numpy(), g["step_eps"], atol=1e-6)
+    xt1, mask = ddim.epilogue_fwd(x, T(g["step_eps"]), tab[751], tab[501])
+    assert np.array_equal(xt1.numpy(), g["step_xt"])               # bit-exact given the same eps
+    # full 3-step map and its VJP
+    x_hat, tape = ddim.ddim_map(x, eps_net, tab, [250, 500, 750], [-1, 250, 500])
+    np.testing.assert_allclose(x_hat.numpy(), g["x_hat"], atol=2e-6)
+    gx = ddim.ddim_map_vjp(T(g["w"]), tape)
+    np.testing.assert_allclose(gx.numpy(), g["grad_x"], atol=2e-5 * np.abs(g["grad_x"]).max())
+
+
+def test_unet_matches_reference(golden):
+    g = golden("unet_small.npz")
+    kw = dict(image_size=64, num_channels=32, num_res_blocks=1, channel_mult="", learn_sigma=True,
+              attention_resolutions=16, num_heads=4, num_head_channels=16, use_scale_shift_norm=True,
+              resblock_updown=True)
+    cfg = ounet.resolve_config(**kw)
+    sd = ounet.seeded_state_dict(cfg, seed=1234)
+    x = T(g["x"]).requires_grad_(True)
+    out = ounet.unet_forward(sd, cfg, x, T(g["t"]))
+    np.testing.assert_allclose(out.detach().numpy(), g["out"], atol=2e-5, rtol=1e-4)
+    (gx,) = torch.autograd.grad((out * T(g["w"])).sum(), x)
+    np.testing.assert_allclose(gx.numpy(), g["grad_x"], atol=2e-5 * max(1.0, np.abs(g["grad_x"]).max()), rtol=1e-4)
+
+
+def test_unet_ffhq10m_shapes(golden):
+    g = golden("unet_ffhq10m_meta.npz")
+    cfg = ounet.resolve_config(image_size=256, num_channels=128, num_res_blocks=1, channel_mult="",
+                               learn_sigma=True, attention_resolutions=16, num_heads=4, num_head_channels=64,
+                               use_scale_shift_norm=True, resblock_updown=True)
+    shapes = ounet.param_shapes(cfg)
+    assert sum(int(np.prod(s)) for s in shapes.values()) == int(g["nparam"]) == 93563910
+    sha = hashlib.sha1("\n".join(f"{k}:{tuple(v)}" for k, v in shapes.items()).encode()).digest()
+    assert sha == bytes(g["names_sha1"])
+
+
+def _trace_setup(g):
+    D = 32
+    op = oops.Inpainting.from_missing_indices(3, D, g["missing"])
+    tab = osch.alpha_bar_table(osch.beta_schedule("linear", 1e-4, 0.02, 1000))
+    eps_net = ohmc.module_eps_net(TinyEpsNet())
+    return op, tab, eps_net
+
+
+def test_hmc_teacher_forced_iterations(golden):
+    """First 32 iterations of the real hmc(): same state, same draws -> same prob/accept/sample.
+
+    A trajectory is 20 leapfrog steps through 3 hard clips each; one element landing on the other
+    side of a clip boundary by rounding changes the gradient discontinuously, so a rare iteration
+    (about 1 in 30 here, in fp32 and in fp64 alike) legitimately lands on a different dH.  Those are
+    counted and bounded instead of hidden.
+    """
+    g = golden("hmc_trace.npz")
+    op, tab, eps_net = _trace_setup(g)
+    y = T(g["y_0"]); sigma_0 = float(g["sigma_0"])
+    seq, seq_next = [250, 500, 750], [-1, 250, 500]
+    sch = osch.PixelSchedule(1.0, 0.05, sigma_0)
+    torch.manual_seed(int(g["seed"]))
+    n_saved = n_img_ok = outliers = 0
+    eval_fn = lambda x_: ohmc.grad_eval(x_, eps_net, tab, seq, seq_next, op, y)
+    for it in range(32):
+        x = T(g["x_start"][it:it + 1])
+        p = torch.randn_like(x)
+        sig, eps_now = sch.begin_iteration()
+        out = ohmc.hmc_iteration(x, p, None, sig, eps_now, sch.L, 1.0, eval_fn)
+        u = torch.rand(1)
+        assert abs(float(u) - g["u"][it]) < 1e-7
+        prob_ref = min(1.0, float(g["prob"][it]))
+        prob = float(out["prob"])
+        acc = bool(g["accept"][it])
+        band = 0.02 * max(prob_ref, 1e-3) + 1e-6       # dH is a difference of fp32 totals ~1e3
+        if abs(prob - prob_ref) > band:
+            outliers += 1
+        else:
+            if abs(float(u) - prob_ref) > band:
+                assert (float(u) < prob) == acc, it
+            if acc:
+                img = ((out["x_hat"][0] + 1) / 2).clamp(0, 1)
+                np.testing.assert_allclose(img.numpy(), g["saved"][n_saved], atol=1e-3)
+                n_img_ok += 1
+        n_saved += acc
+        sch.end_iteration(acc)
+    assert outliers <= 2, outliers
+    assert n_img_ok >= 5
+
+
+def test_hmc_schedule_replay(golden):
+    """Driving PixelSchedule with the recorded accept sequence ends after exactly the recorded iterations."""
+    g = golden("hmc_trace.npz")
+    sch = osch.PixelSchedule(1.0, 0.05, float(g["sigma_0"]))
+    n = 0
+    collected = 0
+    for acc in g["accept"]:
+        assert not sch.done()
+        sch.begin_iteration()
+        collected += bool(sch.end_iteration(bool(acc)))
+        n += 1
+    assert sch.done() and n == len(g["accept"]) and sch.accepted == 100 and collected == 20
+    assert abs(sch.sigma_y - float(g["sigma_0"])) < 1e-12
