@@ -1,0 +1,234 @@
+/*
+ * nhmc.h -- C ABI of the B200 (sm_100a) noise-space HMC kernels.
+ *
+ * The reference (Sunsett5/Noise-space-HMC) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b); every entry point below replaces a group of implicit ATen launches
+ * on the `--algo hmc` / `--algo hmc_latent` path, cited per function as file:line of the
+ * upstream tree.  INTEGRATION.md shows the ctypes stub a maintainer of the reference adds.
+ *
+ * Conventions
+ *  - every tensor argument is a raw DEVICE pointer plus explicit sizes; `stream` is a
+ *    cudaStream_t (pass torch's current stream); nothing synchronises the device;
+ *  - the caller owns every buffer, the library allocates nothing;
+ *  - return value: 0 = OK, otherwise an NHMC_ERR_* code; nhmc_last_error() gives the text
+ *    (thread-local); no C++ exception crosses the boundary;
+ *  - per-chain scalars live in a device array of `nhmc_chain` (one entry per chain) so that
+ *    chains of one batch can sit at different epochs / step sizes / noise levels;
+ *  - images are fp32, contiguous [B, C, H, W]; N = C*H*W elements per chain;
+ *  - "workspace": device scratch, size from the matching *_workspace_bytes(); it must be
+ *    zero-filled ONCE after allocation (reduction tickets live there and reset themselves).
+ *  - sm_100a only; there is no CPU or other-arch fallback.
+ */
+#ifndef NHMC_H
+#define NHMC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NHMC_OK 0
+#define NHMC_ERR_ARG 1
+#define NHMC_ERR_CUDA 2
+#define NHMC_ERR_UNSUPPORTED 3
+
+typedef void* nhmc_stream_t; /* cudaStream_t */
+
+/* element types of the score-network output / its cotangent */
+#define NHMC_F32 0
+#define NHMC_BF16 1
+#define NHMC_F16 2
+
+int nhmc_version(void);
+const char* nhmc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-chain sampler state (device array, one per chain).  Mirrors the python locals of
+ * hmc() (main_sampling.py:660-689) and hmc_latent() (main_sampling_latent.py:623-646).
+ * Doubles first, then 4-byte fields: identical layout for C, ctypes and numpy.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct nhmc_chain {
+  double epsilon;      /* current step size (python float in the reference)            */
+  double tau;          /* current trajectory length                                     */
+  double sigma_y;      /* noise level used by the running iteration                     */
+  double sigma_0;      /* measurement noise, already doubled (main_sampling.py:348)     */
+  double sigma_y_init; /* latent path: opt.sigma_y (main_sampling_latent.py:625)        */
+  double sum_x2[2];    /* sum x^2 : [0] current state, [1] proposal (fp64 accumulate)   */
+  double sum_p2[2];    /* sum p^2 : [0] at the momentum draw, [1] end of trajectory     */
+  double loss[2];      /* sum r^2 : [0] at the current state, [1] at the proposal       */
+  float H[2];          /* fp32 totals, reference order prior + data + kinetic           */
+  float prob;          /* min(1, exp(-(H[1]-H[0])))                                     */
+  float u;             /* uniform draw consumed by the last decision                    */
+  int32_t epoch;
+  int32_t accepted;
+  int32_t rejected;
+  int32_t n_collected; /* samples stored so far                                         */
+  int32_t iters;       /* HMC iterations run                                            */
+  int32_t accept;      /* decision of the last iteration (0/1)                          */
+  int32_t collect;     /* 1 if the last iteration stored a sample                       */
+  int32_t slot;        /* ring-buffer slot written by the last iteration, or -1         */
+  int32_t active;      /* 0 once the chain's schedule is complete                       */
+  int32_t reserved;
+} nhmc_chain;
+
+size_t nhmc_sizeof_chain(void);
+
+#define NHMC_SCHED_PIXEL 0  /* main_sampling.py:681-749        */
+#define NHMC_SCHED_LATENT 1 /* main_sampling_latent.py:646-733 */
+
+/* Top of an iteration: sigma_y / tau / epsilon for this epoch.
+ * Replaces main_sampling.py:683-689 (pixel).  The latent schedule sets sigma_y on accept
+ * (done by nhmc_accept), so this is a no-op for NHMC_SCHED_LATENT except iters bookkeeping. */
+int nhmc_begin_iteration(nhmc_chain* chains, int n_chains, int sched, nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1/K6 fused leapfrog (main_sampling.py:697,702,706-707,713,715,717)
+ *   force F = x + g/(2 sigma_y^2),  g = g_a (+ g_b if non-NULL)
+ *   NHMC_LF_FIRST : energies of (x_in, p) -> sum_x2[0], sum_p2[0], loss[0] = loss_in;
+ *                   p -= (eps/2) F ; x_out = x_in + eps/m * p
+ *   NHMC_LF_MIDDLE: p -= eps F     ; x_out = x_in + eps/m * p        (x_out may alias x_in)
+ *   NHMC_LF_LAST  : p -= eps F ; p += (eps/2) F ; energies of (x_in, p) -> [1], loss[1] = loss_in
+ * fp32 arithmetic in the reference's operation order with no FMA contraction; energy sums
+ * are accumulated in fp64 in-register and reduced warp-shuffle + one block reduce + a
+ * deterministic last-block pass.  loss_in: device double[B] (may be NULL for MIDDLE).
+ * ---------------------------------------------------------------------------------------- */
+#define NHMC_LF_FIRST 0
+#define NHMC_LF_MIDDLE 1
+#define NHMC_LF_LAST 2
+size_t nhmc_leapfrog_workspace_bytes(int n_chains);
+int nhmc_leapfrog(int mode, const float* x_in, float* x_out, float* p, const float* g_a,
+                  const float* g_b, const double* loss_in, nhmc_chain* chains, double mass,
+                  int n_chains, int64_t n_per_chain, void* workspace, nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 DDIM epilogue forward (algos/unconditional.py:17-28; formula of functions/denoising.py:62)
+ *   x0raw = (xt - c1*eps)/sa ; mask = (-1 <= x0raw <= 1) ; xt' = ss*clamp(x0raw,-1,1) + c2*eps
+ * with c1 = sqrt(1-abar_t), sa = sqrt(abar_t), c2 = sqrt(1-abar_next), ss = sqrt(abar_next),
+ * computed by the caller in fp32 exactly as the reference does.  eps is the network output
+ * [B, eps_channels, H, W] of which the first C channels are used (unconditional.py:17-18):
+ * eps_chain_stride = eps_channels*H*W elements.  mask_out: 1 bit per element, packed per
+ * 128-element group as 4 uint32 (word j, bit l <-> element 4*l + j); (N+127)/128*16 bytes
+ * per chain; may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+size_t nhmc_ddim_mask_bytes(int64_t n_per_chain);
+int nhmc_ddim_fwd(const float* xt, const void* eps, int eps_dtype, int64_t eps_chain_stride,
+                  float* xt_next, uint32_t* mask_out, float c1, float sa, float c2, float ss,
+                  int n_chains, int64_t n_per_chain, nhmc_stream_t stream);
+
+/* K3 DDIM epilogue backward (autograd of the above), g' = g_a (+ g_b):
+ *   g_xt = ss*g'*mask/sa ; g_eps = c2*g' - c1*g_xt
+ * g_eps_out: [B, eps_channels, H, W] cotangent for the network VJP (channels >= C are never
+ * written: zero them once); may be NULL (latent path: eps carries no gradient). */
+int nhmc_ddim_bwd(const float* g_a, const float* g_b, const uint32_t* mask, float* g_xt,
+                  void* g_eps_out, int eps_dtype, int64_t eps_chain_stride, float c1, float sa,
+                  float c2, float ss, int n_chains, int64_t n_per_chain, nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4/K5 measurement operators (obs_functions/Hfuncs.py).  All table pointers are DEVICE
+ * pointers owned by the caller.
+ * ---------------------------------------------------------------------------------------- */
+#define NHMC_OP_INPAINT 0  /* Hfuncs.py:119-154  */
+#define NHMC_OP_SR 1       /* Hfuncs.py:180-234  */
+#define NHMC_OP_HDR 2      /* Hfuncs.py:406-445  */
+#define NHMC_OP_DEBLUR2D 3 /* Hfuncs.py:448-523  */
+#define NHMC_OP_PHASE 4    /* Hfuncs.py:318-366 + fastmri_utils.py:67-114 */
+
+typedef struct nhmc_op {
+  int32_t kind;
+  int32_t channels;
+  int32_t img_dim;
+  int32_t ratio;              /* SR: block size                                              */
+  int32_t n_kept;             /* inpaint: kept pixels                                        */
+  int32_t pad;                /* phase: zero padding per side (64)                           */
+  int32_t no_clamp;           /* 1: loss_grad skips clamp(x_hat,-1,1) and its mask (latent   */
+                              /*    path: the decoded image is not clipped,                  */
+                              /*    main_sampling_latent.py:651)                             */
+  int32_t reserved;
+  const int32_t* kept_pix;    /* inpaint: [n_kept] ascending pixel indices                   */
+  const int32_t* pix_to_kept; /* inpaint: [D*D] rank among kept pixels, -1 if dropped        */
+  const float* U1;            /* deblur2d: [D,D] row-major, as Hfuncs.Deblurring2D.U_small1  */
+  const float* V1;
+  const float* U2;
+  const float* V2;
+  const float* gain;          /* deblur2d: [C,D,D] spectral gain D_c (SURVEY.md headline 6)  */
+  const float* gain_pinv;     /* deblur2d: [C,D,D] 1/D_c where non-zero else 0               */
+} nhmc_op;
+
+/* measurement elements per chain (M) for this operator */
+int64_t nhmc_op_meas_size(const nhmc_op* op);
+size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains);
+
+/* y = H(x) in the reference's layout (no clamp). Replaces H_functions.H (Hfuncs.py:65-71). */
+int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* workspace,
+                    nhmc_stream_t stream);
+/* out = H^T(r) for the linear operators (Hfuncs.py:73-79). */
+int nhmc_op_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* workspace,
+                    nhmc_stream_t stream);
+/* out = H^+(y) (Hfuncs.py:81-91; hdr: identity; phase: |ifft2c| cropped). */
+int nhmc_op_pinv(const nhmc_op* op, const float* y, float* out, int n_chains, void* workspace,
+                 nhmc_stream_t stream);
+/* Fused loss + gradient of main_sampling.py:709-711 w.r.t. x_hat (the DDIM output):
+ *   xc = clamp(x_hat,-1,1); r = y - H(xc); loss[b] = sum r^2 (fp64);
+ *   g = dloss/dx_hat = -2 J_H(xc)^T r * 1[-1 <= x_hat <= 1].
+ * xc_out (nullable) receives the clamped image (the sample the reference keeps). */
+int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g,
+                      float* xc_out, double* loss, int n_chains, void* workspace,
+                      nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K7 Metropolis decision + schedule update, on device (main_sampling.py:697,717-731,743-749;
+ * latent main_sampling_latent.py:676-733).  u: device float[B] uniform draws.
+ * Writes H[], prob, accept, collect, slot and advances epoch/rejected/epsilon/tau/sigma_y.
+ * n_slots = capacity of the per-chain sample ring buffer (pixel 20, latent 10).
+ * ---------------------------------------------------------------------------------------- */
+int nhmc_accept(nhmc_chain* chains, const float* u, double mass, int sched, int n_slots,
+                int n_chains, nhmc_stream_t stream);
+/* Apply the decision: x <- x_prop where accepted; store the sample.
+ * pixel : accepted & collect -> samples[b][slot] = x_hat[b]
+ * latent: collect -> samples[b][slot] = x_keep[b] (previous accepted x_hat, one accept
+ *         behind, main_sampling_latent.py:705-713); accepted -> x_keep[b] = x_hat[b].
+ * samples: [B, n_slots, N]; x_keep may be NULL for the pixel schedule. */
+int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const float* x_hat,
+                float* x_keep, float* samples, int sched, int n_slots, int n_chains,
+                int64_t n_per_chain, nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9 U-Net epilogues: GroupNorm(32 groups, eps 1e-5, fp32 statistics) fused with its
+ * follow-up (nn.py:17-19; unet_ffhq.py:253-257,277-280,319-323,356,683-685).
+ *   NHMC_GN_PLAIN : y = gn(x)                          (attention norm)
+ *   NHMC_GN_SILU  : y = silu(gn(x))                    (in_layers / out)
+ *   NHMC_GN_FILM_SILU : y = silu(gn(x)*(1+scale)+shift) (out_layers, use_scale_shift_norm)
+ * x, y: [B, C, HW] contiguous (NCHW) or channels-last [B, HW, C] (layout flag), dtype
+ * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32-or-dtype [B, C] (FiLM only).
+ * stats_out: fp32 [B, G, 2] (mean, rstd) saved for the backward.
+ * ---------------------------------------------------------------------------------------- */
+#define NHMC_GN_PLAIN 0
+#define NHMC_GN_SILU 1
+#define NHMC_GN_FILM_SILU 2
+#define NHMC_LAYOUT_NCHW 0
+#define NHMC_LAYOUT_NHWC 1
+int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
+                const float* beta, const float* scale, const float* shift, float* stats_out,
+                int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream);
+/* dx (and optionally dscale/dshift [B,C] fp32) given dy; weights are frozen on this path, so
+ * no dgamma/dbeta. */
+int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
+                const float* gamma, const float* beta, const float* scale, const float* shift,
+                const float* stats, float* dscale, float* dshift, int batch, int channels,
+                int64_t hw, int groups, nhmc_stream_t stream);
+
+/* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of
+ * logits [rows, T] (dtype f32/bf16/f16), computed in fp32; logits are multiplied by
+ * `scale` first (the reference pre-scales q and k by ch^-1/4 each). */
+int nhmc_softmax_fwd(int dtype, const void* logits, void* probs, float scale, int64_t rows,
+                     int cols, nhmc_stream_t stream);
+/* dlogits = scale * probs * (dprobs - sum(dprobs*probs)) */
+int nhmc_softmax_bwd(int dtype, const void* probs, const void* dprobs, void* dlogits, float scale,
+                     int64_t rows, int cols, nhmc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NHMC_H */

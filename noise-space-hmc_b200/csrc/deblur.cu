@@ -1,0 +1,203 @@
+// Anisotropic deblurring operator in its spectral form (Hfuncs.py:448-523):
+//   Y_c = U1 (G_c .* (V1^T X_c V2)) U2^T ,  G_c[j] = s_sorted[(3*rank(j)+c) mod D^2]  (SURVEY.md headline 6)
+// and the fused loss/gradient of main_sampling.py:709-711 through it:
+//   R = y - Y(clamp(x_hat)) ; loss = sum R^2 ; g = -2 V1 (G_c .* (U1^T R U2)) V2^T .* 1[-1<=x_hat<=1]
+//
+// Eight D x D x D products per (chain, channel) (D = 256: 0.27 GFLOP), true fp32 FFMA (max-abs 1e-3
+// parity rules out single-pass TF32/bf16), each a 64x64-tile SIMT GEMM whose epilogue carries the
+// elementwise work (spectral gain, residual + loss reduction, final clip mask) so no extra pass over
+// the images is made.  The SVD factor tables are inputs: torch.svd signs / tie order are
+// implementation-defined, so they are built once by the caller and shared with the checker.
+#include "common.cuh"
+
+namespace nhmc {
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+enum { EPI_NONE = 0, EPI_GAIN = 1, EPI_RESID = 2, EPI_GRAD = 3 };
+
+struct GemmArgs {
+  const float* A; int64_t sA; int lda_m, lda_k;   // A(m,k) = A[mat*sA + m*lda_m + k*lda_k]
+  const float* B; int64_t sB; int ldb_k, ldb_n;   // B(k,n) = B[mat*sB + k*ldb_k + n*ldb_n]
+  float* C; int64_t sC;                           // C(m,n) = C[mat*sC + m*D + n]
+  int D, channels;
+  const float* gain;   // [channels][D][D]             (EPI_GAIN)
+  const float* y;      // [mats][D][D] measurement      (EPI_RESID)
+  const float* xhat;   // [mats][D][D] unclamped image  (EPI_GRAD)
+  double* loss;        // [chains]                      (EPI_RESID)
+  int no_clamp;        // skip the final clip and its mask (latent path)
+  RedWs ws;
+};
+
+template <int EPI, bool CLAMP_B>
+__global__ void __launch_bounds__(256)
+gemm_kernel(GemmArgs a) {
+  __shared__ __align__(16) float As[TK][TM + 4];
+  __shared__ __align__(16) float Bs[TK][TN + 4];
+  const int D = a.D;
+  const int mat = blockIdx.z;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float* Ab = a.A + (int64_t)mat * a.sA;
+  const float* Bb = a.B + (int64_t)mat * a.sB;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < D; k0 += TK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      int m, k;
+      if (a.lda_k == 1) { k = idx & (TK - 1); m = idx >> 4; } else { m = idx & (TM - 1); k = idx >> 6; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < D && gk < D) ? __ldg(Ab + (int64_t)gm * a.lda_m + (int64_t)gk * a.lda_k) : 0.f;
+      int n, kb;
+      if (a.ldb_n == 1) { n = idx & (TN - 1); kb = idx >> 6; } else { kb = idx & (TK - 1); n = idx >> 4; }
+      const int gn = n0 + n, gkb = k0 + kb;
+      float v = (gn < D && gkb < D) ? __ldg(Bb + (int64_t)gkb * a.ldb_k + (int64_t)gn * a.ldb_n) : 0.f;
+      if (CLAMP_B && !a.no_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+      Bs[kb][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int c = mat % a.channels, chain = mat / a.channels;
+  double lsum = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gm < D && gn < D) {
+        const int64_t off = (int64_t)gm * D + gn;
+        float v = acc[i][j];
+        if (EPI == EPI_GAIN) v *= __ldg(a.gain + (int64_t)c * D * D + off);
+        if (EPI == EPI_RESID) {
+          v = __fsub_rn(__ldg(a.y + (int64_t)mat * D * D + off), v);
+          lsum += (double)v * (double)v;
+        }
+        if (EPI == EPI_GRAD) {
+          const float xh = __ldg(a.xhat + (int64_t)mat * D * D + off);
+          v = -(2.0f * v) * ((a.no_clamp || (xh >= -1.0f && xh <= 1.0f)) ? 1.0f : 0.0f);
+        }
+        a.C[(int64_t)mat * a.sC + off] = v;
+      }
+    }
+  }
+  if (EPI == EPI_RESID) {
+    __shared__ double red[32];
+    double vsum[1] = {lsum};
+    block_sum<double, 1>(vsum, red);
+    const int tiles = gridDim.x * gridDim.y;
+    const int blk = (c * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (grid_finish<1>(vsum, a.ws.partials + (int64_t)chain * kMaxBlocksPerChain, a.ws.tickets + chain, blk,
+                       tiles * a.channels))
+      a.loss[chain] = vsum[0];
+  }
+}
+
+struct Mats { const float *U1, *V1, *U2, *V2; };
+
+// out = L' * X * R' with elementwise epilogue; L', R' given by (pointer, transposed?)
+template <int EPI, bool CLAMP>
+static void launch(GemmArgs a, int mats, cudaStream_t st) {
+  const int t = (a.D + TM - 1) / TM;
+  gemm_kernel<EPI, CLAMP><<<dim3(t, t, mats), 256, 0, st>>>(a);
+}
+
+static GemmArgs left(const float* M, bool trans, const float* X, float* out, int D, int C) {
+  GemmArgs a{};
+  a.A = M; a.sA = 0; a.lda_m = trans ? 1 : D; a.lda_k = trans ? D : 1;
+  a.B = X; a.sB = (int64_t)D * D; a.ldb_k = D; a.ldb_n = 1;
+  a.C = out; a.sC = (int64_t)D * D; a.D = D; a.channels = C;
+  return a;
+}
+static GemmArgs right(const float* X, const float* M, bool trans, float* out, int D, int C) {
+  GemmArgs a{};
+  a.A = X; a.sA = (int64_t)D * D; a.lda_m = D; a.lda_k = 1;
+  a.B = M; a.sB = 0; a.ldb_k = trans ? 1 : D; a.ldb_n = trans ? D : 1;
+  a.C = out; a.sC = (int64_t)D * D; a.D = D; a.channels = C;
+  return a;
+}
+
+size_t deblur_workspace_bytes(const nhmc_op* op, int n_chains) {
+  return (size_t)3 * n_chains * op->channels * op->img_dim * op->img_dim * sizeof(float) + 256;
+}
+
+// y = U1 (gain .* (V1^T x V2)) U2^T       (Hfuncs.py:65-71 with Vt :493-499, U :501-509)
+int deblur_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
+  const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  float* t0 = reinterpret_cast<float*>(ws);
+  float* t1 = t0 + (size_t)mats * D * D;
+  launch<EPI_NONE, false>(left(op->V1, true, x, t0, D, C), mats, st);
+  GemmArgs g2 = right(t0, op->V2, false, t1, D, C); g2.gain = op->gain;
+  launch<EPI_GAIN, false>(g2, mats, st);
+  launch<EPI_NONE, false>(left(op->U1, false, t1, t0, D, C), mats, st);
+  launch<EPI_NONE, false>(right(t0, op->U2, true, y, D, C), mats, st);
+  return NHMC_LAUNCH_CHECK();
+}
+
+// out = V1 (gain' .* (U1^T r U2)) V2^T   with gain' = gain (H^T, Hfuncs.py:73-79) or 1/gain (H^+, :81-91)
+int deblur_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
+  const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  float* t0 = reinterpret_cast<float*>(ws);
+  float* t1 = t0 + (size_t)mats * D * D;
+  launch<EPI_NONE, false>(left(op->U1, true, r, t0, D, C), mats, st);
+  GemmArgs g2 = right(t0, op->U2, false, t1, D, C); g2.gain = pinv ? op->gain_pinv : op->gain;
+  launch<EPI_GAIN, false>(g2, mats, st);
+  launch<EPI_NONE, false>(left(op->V1, false, t1, t0, D, C), mats, st);
+  launch<EPI_NONE, false>(right(t0, op->V2, true, out, D, C), mats, st);
+  return NHMC_LAUNCH_CHECK();
+}
+
+__global__ void clamp_copy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total, int nc) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    y[e] = nc ? x[e] : fminf(fmaxf(x[e], -1.0f), 1.0f);
+}
+
+int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
+                     int n_chains, void* workspace, cudaStream_t st) {
+  const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  NHMC_CHECK_ARG(((D + TM - 1) / TM) * ((D + TN - 1) / TN) * C <= kMaxBlocksPerChain, "image too large for the deblur loss reduction");
+  const RedWs rw = red_ws(workspace, n_chains);
+  float* t0 = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
+  float* t1 = t0 + (size_t)mats * D * D;
+  float* rr = t1 + (size_t)mats * D * D;
+  // forward through clamp(x_hat)
+  GemmArgs g1 = left(op->V1, true, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
+  launch<EPI_NONE, true>(g1, mats, st);
+  GemmArgs g2 = right(t0, op->V2, false, t1, D, C); g2.gain = op->gain;
+  launch<EPI_GAIN, false>(g2, mats, st);
+  launch<EPI_NONE, false>(left(op->U1, false, t1, t0, D, C), mats, st);
+  GemmArgs g4 = right(t0, op->U2, true, rr, D, C); g4.y = y; g4.loss = loss; g4.ws = rw;
+  launch<EPI_RESID, false>(g4, mats, st);
+  // adjoint of the residual
+  launch<EPI_NONE, false>(left(op->U1, true, rr, t0, D, C), mats, st);
+  GemmArgs g6 = right(t0, op->U2, false, t1, D, C); g6.gain = op->gain;
+  launch<EPI_GAIN, false>(g6, mats, st);
+  launch<EPI_NONE, false>(left(op->V1, false, t1, t0, D, C), mats, st);
+  GemmArgs g8 = right(t0, op->V2, true, g, D, C); g8.xhat = x_hat; g8.no_clamp = op->no_clamp;
+  launch<EPI_GRAD, false>(g8, mats, st);
+  if (xc_out) {
+    const int64_t total = (int64_t)mats * D * D;
+    clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
+}  // namespace nhmc

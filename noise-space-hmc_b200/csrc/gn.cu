@@ -1,0 +1,447 @@
+// K9: GroupNorm(32) fused with its follow-up (SiLU / FiLM + SiLU), forward and input-backward.
+// Replaces GroupNorm32 + SiLU (+ `h*(1+scale)+shift`) of the ADM U-Net
+// (guided_diffusion/nn.py:17-19; unet_ffhq.py:253-257,277-280,319-323,356,683-685): fp32 statistics,
+// activations in the network dtype, one statistics pass + one apply pass instead of
+// cast -> native_group_norm -> cast -> mul/add -> silu (5+ full passes in the reference).
+//
+// HBM-bound.  Layouts: channels-last [B, HW, C] (what the bf16 convolutions want on sm_100) and
+// NCHW [B, C, HW].  Channels-last mapping: a thread owns VEC consecutive channels (16 B) of a pixel and
+// walks down the pixels of its CTA's chunk, so every access is a full 16-byte vector and the
+// per-channel affine (rstd*gamma*(1+scale), ...) is computed once per thread.  Statistics: fp32
+// per-thread partials -> shared-memory ordered reduce -> fp64 per-(sample, group) finish by the last CTA
+// (deterministic).  Weights are frozen on this path (sampling), so backward produces dx only.
+#include "common.cuh"
+
+namespace nhmc {
+
+constexpr int kGnMaxBlocks = 256;  // CTAs per sample in the statistics kernels
+
+template <typename T> struct VecOf { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T, int N> struct Pack { float v[N]; };
+
+template <typename T> __device__ __forceinline__ void load_vec(const T* p, float (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void load_vec<float>(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void load_vec<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <> __device__ __forceinline__ void load_vec<__half>(const __half* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+template <typename T> __device__ __forceinline__ void store_vec(T* p, const float (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void store_vec<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 t;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = t;
+}
+template <> __device__ __forceinline__ void store_vec<__half>(__half* p, const float (&v)[8]) {
+  uint4 t;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+
+struct GnArgs {
+  const void* x; const void* dy; void* out;
+  const float* gamma; const float* beta; const float* scale; const float* shift;  // scale/shift: [B,C] fp32 or null
+  float* stats;      // [B][G][2]: fwd (mean, rstd)
+  float* bstats;     // [B][G][2]: bwd (sum du / n, sum du*u / n)
+  double* partials;  // [B][kGnMaxBlocks][G][2]
+  unsigned int* tickets;  // [B]
+  int C, G; int64_t HW; float eps;
+  int rows_per_cta_iter;  // pixel rows covered by one CTA pass (channels-last)
+  int64_t rows_per_cta;   // pixel rows owned by a CTA (channels-last)
+};
+
+// per-element pieces --------------------------------------------------------------------------
+template <int MODE> __device__ __forceinline__ float gn_act(float z) {
+  return MODE == NHMC_GN_PLAIN ? z : z * sigmoidf_fast(z);
+}
+template <int MODE> __device__ __forceinline__ float gn_dact(float z) {  // d act / dz
+  if (MODE == NHMC_GN_PLAIN) return 1.0f;
+  const float s = sigmoidf_fast(z);
+  return s * (1.0f + z * (1.0f - s));
+}
+
+// ============================== channels-last ==============================================
+// PHASE 0: forward statistics (sum x, sum x^2)            -> stats  = (mean, rstd)
+// PHASE 1: backward statistics (sum du, sum du*u)          -> bstats = (S1/n, S2/n)
+template <typename T, int MODE, int PHASE>
+__global__ void __launch_bounds__(256)
+gn_nhwc_stats_kernel(GnArgs a) {
+  constexpr int V = VecOf<T>::N;
+  extern __shared__ float sm[];  // [rows][C][2]
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int cvec = a.C / V;
+  const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
+  const int c0 = cv * V;
+  const int Cg = a.C / a.G;
+  const T* xb = reinterpret_cast<const T*>(a.x) + (int64_t)b * a.HW * a.C;
+  const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + (int64_t)b * a.HW * a.C : nullptr;
+  float s0[V], s1[V], ca[V], cb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; ca[i] = 0.f; cb[i] = 0.f; }
+  if (PHASE == 1) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+      ca[i] = rstd * gam * sc;                       // z = ca*x + cb
+      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+    }
+  }
+  const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
+  int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+  // PHASE 1 accumulates t0 = sum dy*act'(z), t1 = sum dy*act'(z)*x per channel; the per-channel
+  // affine (gamma(1+s), mean, rstd) is applied once after the loop.
+#pragma unroll 4
+  for (int64_t r = r_begin + prow; r < r_end; r += rows) {
+    float xv[V];
+    load_vec<T>(xb + r * a.C + c0, xv);
+    if (PHASE == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+    } else {
+      float dv[V];
+      load_vec<T>(dyb + r * a.C + c0, dv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+        s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
+      }
+    }
+  }
+  if (PHASE == 1) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
+      const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
+      const float t0 = s0[i], t1 = s1[i];
+      s0[i] = cgm * t0;
+      s1[i] = cgm * rstd * (t1 - mean * t0);
+    }
+  }
+  // ordered reduce over the CTA's pixel rows, then over the channels of each group
+  float* sm0 = sm; float* sm1 = sm + (size_t)rows * a.C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sm0[(size_t)prow * a.C + c0 + i] = s0[i]; sm1[(size_t)prow * a.C + c0 + i] = s1[i]; }
+  __syncthreads();
+  double* part = a.partials + ((int64_t)b * kGnMaxBlocks + blk) * a.G * 2;
+  for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int c = g * Cg; c < (g + 1) * Cg; ++c)
+      for (int r = 0; r < rows; ++r) { t0 += (double)sm0[(size_t)r * a.C + c]; t1 += (double)sm1[(size_t)r * a.C + c]; }
+    part[g * 2] = t0; part[g * 2 + 1] = t1;
+  }
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicInc(a.tickets + b, (unsigned int)(nblk - 1)) == (unsigned int)(nblk - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double n = (double)Cg * (double)a.HW;
+  for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int k = 0; k < nblk; ++k) {
+      const double* p = a.partials + ((int64_t)b * kGnMaxBlocks + k) * a.G * 2 + g * 2;
+      t0 += __ldcg(p); t1 += __ldcg(p + 1);
+    }
+    if (PHASE == 0) {
+      const double mean = t0 / n;
+      double var = t1 / n - mean * mean; if (var < 0.0) var = 0.0;
+      a.stats[((int64_t)b * a.G + g) * 2] = (float)mean;
+      a.stats[((int64_t)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+    } else {
+      a.bstats[((int64_t)b * a.G + g) * 2] = (float)(t0 / n);
+      a.bstats[((int64_t)b * a.G + g) * 2 + 1] = (float)(t1 / n);
+    }
+  }
+}
+
+// PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
+template <typename T, int MODE, int PHASE>
+__global__ void __launch_bounds__(256)
+gn_nhwc_apply_kernel(GnArgs a) {
+  constexpr int V = VecOf<T>::N;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  const int cvec = a.C / V;
+  const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
+  const int c0 = cv * V;
+  const int Cg = a.C / a.G;
+  const T* xb = reinterpret_cast<const T*>(a.x) + (int64_t)b * a.HW * a.C;
+  const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + (int64_t)b * a.HW * a.C : nullptr;
+  T* ob = reinterpret_cast<T*>(a.out) + (int64_t)b * a.HW * a.C;
+  float ca[V], cb[V], k1[V], k2[V], k3[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = c0 + i, g = c / Cg;
+    const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+    const float gam = a.gamma[c], bet = a.beta[c];
+    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
+    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+    ca[i] = rstd * gam * sc;
+    cb[i] = (bet - mean * rstd * gam) * sc + sh;
+    k1[i] = k2[i] = k3[i] = 0.f;
+    if (PHASE == 1) {
+      // dx = rstd*(du - m1 - u*m2), du = dy*act'(z)*gamma*(1+s), u = (x-mean)*rstd
+      //    = k1*dy*act'(z) + k2*x + k3
+      const float m1 = a.bstats[((int64_t)b * a.G + g) * 2], m2 = a.bstats[((int64_t)b * a.G + g) * 2 + 1];
+      k1[i] = rstd * gam * sc;
+      k2[i] = -rstd * rstd * m2;
+      k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
+    }
+  }
+  const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
+  int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+#pragma unroll 4
+  for (int64_t r = r_begin + prow; r < r_end; r += rows) {
+    float xv[V], ov[V];
+    load_vec<T>(xb + r * a.C + c0, xv);
+    if (PHASE == 0) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
+    } else {
+      float dv[V];
+      load_vec<T>(dyb + r * a.C + c0, dv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+        ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
+      }
+    }
+    store_vec<T>(ob + r * a.C + c0, ov);
+  }
+}
+
+// ============================== NCHW =========================================================
+// One CTA per (sample, group): the group is a contiguous slab of Cg*HW elements (<= 1 MB at FFHQ-256),
+// read twice by the same CTA so the second read is an L2 hit.
+template <typename T, int MODE, int PHASE>
+__global__ void __launch_bounds__(256)
+gn_nchw_kernel(GnArgs a) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int Cg = a.C / a.G;
+  const int64_t n = (int64_t)Cg * a.HW;
+  const int64_t base = ((int64_t)b * a.C + (int64_t)g * Cg) * a.HW;
+  const T* xb = reinterpret_cast<const T*>(a.x) + base;
+  const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + base : nullptr;
+  T* ob = reinterpret_cast<T*>(a.out) + base;
+  __shared__ double red[2 * 32];
+  __shared__ float bc[2];
+  float mean, rstd;
+  if (PHASE == 0) {
+    double s[2] = {0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = Elem<T>::to_f(xb[i]);
+      s[0] += v; s[1] += (double)v * v;
+    }
+    block_sum<double, 2>(s, red);
+    if (threadIdx.x == 0) {
+      const double m = s[0] / (double)n;
+      double var = s[1] / (double)n - m * m; if (var < 0.0) var = 0.0;
+      bc[0] = (float)m; bc[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+      a.stats[((int64_t)b * a.G + g) * 2] = bc[0];
+      a.stats[((int64_t)b * a.G + g) * 2 + 1] = bc[1];
+    }
+    __syncthreads();
+    mean = bc[0]; rstd = bc[1];
+  } else {
+    mean = a.stats[((int64_t)b * a.G + g) * 2]; rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+  }
+  auto coef = [&](int c, float& ca, float& cb, float& cgm) {
+    const float gam = a.gamma[c], bet = a.beta[c];
+    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
+    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+    ca = rstd * gam * sc; cb = (bet - mean * rstd * gam) * sc + sh; cgm = gam * sc;
+  };
+  if (PHASE == 0) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
+      ob[i] = Elem<T>::from_f(gn_act<MODE>(fmaf(ca, Elem<T>::to_f(xb[i]), cb)));
+    }
+  } else {
+    double s[2] = {0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
+      const float xv = Elem<T>::to_f(xb[i]);
+      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE>(fmaf(ca, xv, cb)) * cgm;
+      s[0] += du; s[1] += (double)du * (double)((xv - mean) * rstd);
+    }
+    block_sum<double, 2>(s, red);
+    if (threadIdx.x == 0) { bc[0] = (float)(s[0] / (double)n); bc[1] = (float)(s[1] / (double)n); }
+    __syncthreads();
+    const float m1 = bc[0], m2 = bc[1];
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
+      const float xv = Elem<T>::to_f(xb[i]);
+      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE>(fmaf(ca, xv, cb)) * cgm;
+      const float u = (xv - mean) * rstd;
+      ob[i] = Elem<T>::from_f(rstd * (du - m1 - u * m2));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GN scratch (partials + tickets) lives in a library-static device buffer per device: it is tiny,
+// self-resetting, and keeping it here spares every caller a workspace argument on the hottest
+// U-Net path.  (The header's "library allocates nothing" covers tensors; this is documented there.)
+struct GnScratch { double* partials; unsigned int* tickets; float* bstats; int batch; };
+static GnScratch g_scratch[16] = {};
+
+static int get_scratch(int batch, int G, GnScratch& out) {
+  int dev = 0;
+  if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+  if (dev < 0 || dev >= 16) { set_error("device index %d out of range", dev); return NHMC_ERR_ARG; }
+  GnScratch& s = g_scratch[dev];
+  if (s.batch < batch || !s.partials) {
+    // grow-only; allocation happens outside any stream capture (first call) -- warm up before capturing
+    if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); }
+    const int nb = batch < 64 ? 64 : batch;
+    if (int e = cuda_status(cudaMalloc(&s.partials, (size_t)nb * kGnMaxBlocks * 64 * 2 * sizeof(double)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMalloc(&s.tickets, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMalloc(&s.bstats, (size_t)nb * 64 * 2 * sizeof(float)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMemset(s.tickets, 0, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
+    s.batch = nb;
+  }
+  (void)G;
+  out = s;
+  return NHMC_OK;
+}
+
+template <typename T, int MODE, int PHASE>
+static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
+  constexpr int V = VecOf<T>::N;
+  const int cvec = a.C / V;
+  int rows = 256 / cvec; if (rows < 1) rows = 1;
+  const int threads = cvec * rows;
+  NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
+  // chunking: ~64 KiB of input per CTA, at most kGnMaxBlocks CTAs per sample
+  const int64_t bytes_per_row = (int64_t)a.C * sizeof(T);
+  int64_t rows_per_cta = (65536 + bytes_per_row - 1) / bytes_per_row;
+  rows_per_cta = ((rows_per_cta + rows - 1) / rows) * rows;
+  int64_t nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
+  if (nblk > kGnMaxBlocks) {
+    nblk = kGnMaxBlocks;
+    rows_per_cta = (a.HW + nblk - 1) / nblk;
+    rows_per_cta = ((rows_per_cta + rows - 1) / rows) * rows;
+    nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
+  }
+  a.rows_per_cta = rows_per_cta;
+  a.rows_per_cta_iter = rows;
+  const dim3 grid((unsigned)nblk, batch);
+  const size_t smem = (size_t)rows * a.C * 2 * sizeof(float);
+  gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, smem, st>>>(a);
+  gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, 0, st>>>(a);
+  return NHMC_LAUNCH_CHECK();
+}
+
+template <typename T, int MODE, int PHASE>
+static int run_any(int layout, GnArgs a, int batch, cudaStream_t st) {
+  if (layout == NHMC_LAYOUT_NHWC) return run_nhwc<T, MODE, PHASE>(a, batch, st);
+  gn_nchw_kernel<T, MODE, PHASE><<<dim3(a.G, batch), 256, 0, st>>>(a);
+  return NHMC_LAUNCH_CHECK();
+}
+
+template <int PHASE>
+static int dispatch(int mode, int layout, int dtype, GnArgs a, int batch, cudaStream_t st) {
+#define GN_CASE(T)                                                                      \
+  switch (mode) {                                                                       \
+    case NHMC_GN_PLAIN: return run_any<T, NHMC_GN_PLAIN, PHASE>(layout, a, batch, st);   \
+    case NHMC_GN_SILU: return run_any<T, NHMC_GN_SILU, PHASE>(layout, a, batch, st);     \
+    case NHMC_GN_FILM_SILU: return run_any<T, NHMC_GN_FILM_SILU, PHASE>(layout, a, batch, st); \
+  }
+  switch (dtype) {
+    case NHMC_F32: GN_CASE(float) break;
+    case NHMC_BF16: GN_CASE(__nv_bfloat16) break;
+    case NHMC_F16: GN_CASE(__half) break;
+  }
+#undef GN_CASE
+  set_error("gn: unknown mode %d / dtype %d", mode, dtype);
+  return NHMC_ERR_ARG;
+}
+
+static int check_common(int mode, int layout, int dtype, const void* x, const void* out, const float* gamma,
+                        const float* beta, const float* scale, const float* shift, int batch, int channels,
+                        int64_t hw, int groups) {
+  NHMC_CHECK_ARG(x && out && gamma && beta, "null pointer");
+  NHMC_CHECK_ARG(batch > 0 && channels > 0 && hw > 0 && groups > 0 && groups <= 64 && channels % groups == 0, "bad geometry");
+  NHMC_CHECK_ARG(mode != NHMC_GN_FILM_SILU || (scale && shift), "FiLM needs scale and shift");
+  NHMC_CHECK_ARG(layout == NHMC_LAYOUT_NCHW || layout == NHMC_LAYOUT_NHWC, "unknown layout");
+  if (layout == NHMC_LAYOUT_NHWC) {
+    const int V = dtype == NHMC_F32 ? 4 : 8;
+    NHMC_CHECK_ARG(channels % V == 0 && aligned16(x) && aligned16(out), "channels-last needs C % (16B/elem) == 0 and 16-byte alignment");
+  }
+  return NHMC_OK;
+}
+
+}  // namespace nhmc
+
+using namespace nhmc;
+
+extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
+                           const float* beta, const float* scale, const float* shift, float* stats_out, int batch,
+                           int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
+  if (int e = check_common(mode, layout, dtype, x, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
+  NHMC_CHECK_ARG(stats_out, "stats_out required");
+  GnScratch s;
+  if (int e = get_scratch(batch, groups, s)) return e;
+  GnArgs a{};
+  a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = stats_out;
+  a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
+  return dispatch<0>(mode, layout, dtype, a, batch, (cudaStream_t)stream);
+}
+
+extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
+                           const float* gamma, const float* beta, const float* scale, const float* shift,
+                           const float* stats, float* dscale, float* dshift, int batch, int channels, int64_t hw,
+                           int groups, nhmc_stream_t stream) {
+  if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
+  NHMC_CHECK_ARG(dy && stats, "dy and stats required");
+  NHMC_CHECK_ARG(!dscale && !dshift, "dscale/dshift are not produced on the sampling path (timestep embedding carries no gradient)");
+  NHMC_CHECK_ARG(layout != NHMC_LAYOUT_NHWC || aligned16(dy), "dy must be 16-byte aligned");
+  GnScratch s;
+  if (int e = get_scratch(batch, groups, s)) return e;
+  GnArgs a{};
+  a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift;
+  a.stats = const_cast<float*>(stats);
+  a.bstats = s.bstats;
+  a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;
+  return dispatch<1>(mode, layout, dtype, a, batch, (cudaStream_t)stream);
+}

@@ -1,0 +1,409 @@
+// K4/K5: measurement operators fused with residual, loss reduction and adjoint.
+// Replaces obs_functions/Hfuncs.py {Inpainting :119-154, SuperResolution :180-234, HDR :406-445}
+// plus `loss = sum((y_0 - H(xt.clip(-1,1)))**2)` and its autograd (main_sampling.py:709-711).
+// Deblurring2D and PhaseRetrieval live in deblur.cu / phase.cu and are dispatched from here.
+//
+// One pass per gradient evaluation: read x_hat (N) + y (M), write g (N) [+ clamped image];
+// loss accumulated in fp64 in-register, warp-shuffle + one block reduce + deterministic
+// last-block finish (common.cuh).
+#include "common.cuh"
+
+namespace nhmc {
+
+// defined in deblur.cu / phase.cu
+int deblur_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int deblur_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t, bool pinv);
+int deblur_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
+size_t deblur_workspace_bytes(const nhmc_op*, int);
+int phase_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int phase_pinv(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int phase_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
+size_t phase_workspace_bytes(const nhmc_op*, int);
+
+__device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
+__device__ __forceinline__ float inr(float v, float lo, float hi) { return (v >= lo && v <= hi) ? 1.0f : 0.0f; }
+// final clip of main_sampling.py:709 and its gradient mask; nc = 1 disables both (latent path)
+__device__ __forceinline__ float clampx(float v, int nc) { return nc ? v : clamp1(v); }
+__device__ __forceinline__ float maskx(float v, int nc) { return nc ? 1.0f : inr(v, -1.0f, 1.0f); }
+
+// =====================================================================================
+// Inpainting
+// =====================================================================================
+// y[b, 3k+c] = x[b, c, kept[k]]
+__global__ void inpaint_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, const int32_t* __restrict__ kept,
+                                   int n_kept, int C, int64_t P) {
+  const int b = blockIdx.y;
+  const int64_t M = (int64_t)n_kept * C;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(j / C), c = (int)(j - (int64_t)k * C);
+    y[(int64_t)b * M + j] = x[((int64_t)b * C + c) * P + kept[k]];
+  }
+}
+
+// out[b, c, pix] = r[b, 3*rank(pix)+c] if kept else 0   (H^T = H^+ for a row-selection matrix)
+__global__ void inpaint_adj_kernel(const float* __restrict__ r, float* __restrict__ out, const int32_t* __restrict__ p2k,
+                                   int n_kept, int C, int64_t P) {
+  const int b = blockIdx.y;
+  const int64_t N = (int64_t)C * P, M = (int64_t)n_kept * C;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / P);
+    const int64_t pix = e - (int64_t)c * P;
+    const int k = p2k[pix];
+    out[(int64_t)b * N + e] = k >= 0 ? r[(int64_t)b * M + (int64_t)k * C + c] : 0.0f;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+inpaint_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                         float* __restrict__ xc_out, const int32_t* __restrict__ p2k, int n_kept, int C, int64_t P,
+                         double* loss, RedWs ws, int nc) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t N = (int64_t)C * P, M = (int64_t)n_kept * C;
+  const int64_t n_vec = N / 4;  // P % 4 == 0 is checked by the host, so a float4 never straddles channels
+  const float* xb = xh + (int64_t)b * N;
+  const float* yb = y + (int64_t)b * M;
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
+    const int64_t e0 = v * 4;
+    const int c = (int)(e0 / P);
+    const int64_t pix0 = e0 - (int64_t)c * P;
+    const float4 xv = ld_ro(reinterpret_cast<const float4*>(xb + e0));
+    const int4 kv = __ldg(reinterpret_cast<const int4*>(p2k + pix0));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const int ks[4] = {kv.x, kv.y, kv.z, kv.w};
+    float gs[4], cs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cs[j] = clampx(xs[j], nc);
+      gs[j] = 0.0f;
+      if (ks[j] >= 0) {
+        const float r = __fsub_rn(__ldg(yb + (int64_t)ks[j] * C + c), cs[j]);
+        acc += (double)r * (double)r;
+        gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+      }
+    }
+    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N + e0), make_float4(gs[0], gs[1], gs[2], gs[3]));
+    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N + e0), make_float4(cs[0], cs[1], cs[2], cs[3]));
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+}
+
+// =====================================================================================
+// Super-resolution (r x r block average)
+// =====================================================================================
+__global__ void sr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int D, int r) {
+  const int b = blockIdx.y, yd = D / r;
+  const int64_t M = (int64_t)C * yd * yd;
+  const float inv = 1.0f / (float)(r * r);
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(j / ((int64_t)yd * yd));
+    const int rem = (int)(j - (int64_t)c * yd * yd);
+    const int ci = rem / yd, cj = rem - ci * yd;
+    const float* src = x + (((int64_t)b * C + c) * D + (int64_t)ci * r) * D + (int64_t)cj * r;
+    float s = 0.f;
+    for (int u = 0; u < r; ++u) {
+      float rs = 0.f;
+      for (int w = 0; w < r; ++w) rs += src[(int64_t)u * D + w];
+      s += rs;
+    }
+    y[(int64_t)b * M + j] = s * inv;
+  }
+}
+
+// out = upsample(r) * mul   (mul = 1/r^2 for H^T, 1 for H^+)
+__global__ void sr_up_kernel(const float* __restrict__ rr, float* __restrict__ out, int C, int D, int r, float mul) {
+  const int b = blockIdx.y, yd = D / r;
+  const int64_t N = (int64_t)C * D * D, M = (int64_t)C * yd * yd;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < N; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e / ((int64_t)D * D));
+    const int rem = (int)(e - (int64_t)c * D * D);
+    const int i = rem / D, j = rem - i * D;
+    out[(int64_t)b * N + e] = rr[(int64_t)b * M + ((int64_t)c * yd + i / r) * yd + j / r] * mul;
+  }
+}
+
+// One CTA owns a strip of TR rows x D columns of one (chain, channel): stage raw x in shared memory,
+// reduce r x r cells in a fixed order, then write the gradient of every pixel of the strip.
+__global__ void __launch_bounds__(kThreads)
+sr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                    float* __restrict__ xc_out, int C, int D, int r, int TR, double* loss, RedWs ws, int nc) {
+  extern __shared__ float smem[];
+  float* tile = smem;                    // [TR][D] raw x_hat
+  float* rowsum = tile + (size_t)TR * D; // [TR][D/r]
+  float* cellres = rowsum + (size_t)TR * (D / r);  // [TR/r][D/r] residual per cell
+  const int b = blockIdx.y, strip = blockIdx.x, nstrips = gridDim.x;
+  const int strips_per_ch = D / TR;
+  const int c = strip / strips_per_ch, row0 = (strip - c * strips_per_ch) * TR;
+  const int yd = D / r, cpr = D / r;  // cells per row
+  const int64_t N = (int64_t)C * D * D, M = (int64_t)C * yd * yd;
+  const float* src = xh + (int64_t)b * N + ((int64_t)c * D + row0) * D;
+  const int n_vec = TR * D / 4;
+  for (int v = threadIdx.x; v < n_vec; v += kThreads)
+    reinterpret_cast<float4*>(tile)[v] = ld_ro(reinterpret_cast<const float4*>(src) + v);
+  __syncthreads();
+  for (int i = threadIdx.x; i < TR * cpr; i += kThreads) {
+    const int row = i / cpr, cc = i - row * cpr;
+    const float* p = tile + (size_t)row * D + (size_t)cc * r;
+    float s = 0.f;
+    for (int w = 0; w < r; ++w) s += clampx(p[w], nc);
+    rowsum[i] = s;
+  }
+  __syncthreads();
+  double acc = 0.0;
+  const float inv = 1.0f / (float)(r * r);
+  for (int i = threadIdx.x; i < (TR / r) * cpr; i += kThreads) {
+    const int cr = i / cpr, cc = i - cr * cpr;
+    float s = 0.f;
+    for (int u = 0; u < r; ++u) s += rowsum[(cr * r + u) * cpr + cc];
+    const float res = __fsub_rn(__ldg(y + (int64_t)b * M + ((int64_t)c * yd + (row0 / r + cr)) * yd + cc), s * inv);
+    cellres[i] = res;
+    acc += (double)res * (double)res;
+  }
+  __syncthreads();
+  float* gdst = g + (int64_t)b * N + ((int64_t)c * D + row0) * D;
+  float* cdst = xc_out ? xc_out + (int64_t)b * N + ((int64_t)c * D + row0) * D : nullptr;
+  for (int v = threadIdx.x; v < n_vec; v += kThreads) {
+    const int e = v * 4, row = e / D, col = e - row * D;
+    const float4 xv = reinterpret_cast<const float4*>(tile)[v];
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    float gs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float res = cellres[(row / r) * cpr + (col + j) / r];
+      gs[j] = -(2.0f * res) * inv * maskx(xs[j], nc);
+    }
+    st_stream(reinterpret_cast<float4*>(gdst) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+    if (cdst) st_stream(reinterpret_cast<float4*>(cdst) + v, make_float4(clampx(xs[0], nc), clampx(xs[1], nc), clampx(xs[2], nc), clampx(xs[3], nc)));
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, strip, nstrips)) loss[b] = vsum[0];
+}
+
+// =====================================================================================
+// HDR
+// =====================================================================================
+__global__ void hdr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    y[e] = clamp1(__fdiv_rn(x[e], 0.5f));
+}
+__global__ void copy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) y[e] = x[e];
+}
+
+__global__ void __launch_bounds__(kThreads)
+hdr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                     float* __restrict__ xc_out, int64_t N, double* loss, RedWs ws, int nc) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t n_vec = N / 4;
+  const float4* xb = reinterpret_cast<const float4*>(xh + (int64_t)b * N);
+  const float4* yb = reinterpret_cast<const float4*>(y + (int64_t)b * N);
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
+    const float4 xv = ld_ro(xb + v), yv = ld_ro(yb + v);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+    float gs[4], cs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cs[j] = clampx(xs[j], nc);
+      const float h = __fdiv_rn(cs[j], 0.5f);
+      const float r = __fsub_rn(ys[j], clamp1(h));
+      acc += (double)r * (double)r;
+      // -2 r * d clip(h)/dh * dh/dx * d clamp(x)/dx
+      gs[j] = -(2.0f * r) * inr(h, -1.0f, 1.0f) * 2.0f * maskx(xs[j], nc);
+    }
+    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+}
+
+static inline int sr_tile_rows(int D, int r) {
+  int TR = r;
+  while (TR < 16 && TR * 2 <= D) TR *= 2;  // ~1024 float4 per CTA at D = 256
+  return TR;
+}
+
+static int check_op(const nhmc_op* op) {
+  NHMC_CHECK_ARG(op, "null operator");
+  NHMC_CHECK_ARG(op->channels > 0 && op->img_dim > 0, "bad operator geometry");
+  switch (op->kind) {
+    case NHMC_OP_INPAINT:
+      NHMC_CHECK_ARG(op->kept_pix && op->pix_to_kept && op->n_kept >= 0, "inpaint tables missing");
+      break;
+    case NHMC_OP_SR:
+      NHMC_CHECK_ARG(op->ratio > 0 && op->img_dim % op->ratio == 0, "ratio must divide img_dim");
+      break;
+    case NHMC_OP_HDR:
+      break;
+    case NHMC_OP_DEBLUR2D:
+      NHMC_CHECK_ARG(op->U1 && op->V1 && op->U2 && op->V2 && op->gain, "deblur tables missing");
+      break;
+    case NHMC_OP_PHASE:
+      NHMC_CHECK_ARG(op->pad >= 0, "bad pad");
+      break;
+    default:
+      set_error("unknown operator kind %d", op->kind);
+      return NHMC_ERR_ARG;
+  }
+  return NHMC_OK;
+}
+
+}  // namespace nhmc
+
+using namespace nhmc;
+
+extern "C" int64_t nhmc_op_meas_size(const nhmc_op* op) {
+  if (!op) return -1;
+  const int64_t C = op->channels, D = op->img_dim;
+  switch (op->kind) {
+    case NHMC_OP_INPAINT: return (int64_t)op->n_kept * C;
+    case NHMC_OP_SR: return op->ratio > 0 ? C * (D / op->ratio) * (D / op->ratio) : -1;
+    case NHMC_OP_HDR: return C * D * D;
+    case NHMC_OP_DEBLUR2D: return C * D * D;
+    case NHMC_OP_PHASE: return C * (D + 2 * op->pad) * (D + 2 * op->pad);
+    default: return -1;
+  }
+}
+
+extern "C" size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains) {
+  if (!op || n_chains < 1) return 0;
+  size_t base = red_ws_bytes(n_chains);
+  base = (base + 255) & ~(size_t)255;
+  if (op->kind == NHMC_OP_DEBLUR2D) return base + deblur_workspace_bytes(op, n_chains);
+  if (op->kind == NHMC_OP_PHASE) return base + phase_workspace_bytes(op, n_chains);
+  return base;
+}
+
+extern "C" int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* workspace,
+                               nhmc_stream_t stream) {
+  if (int e = check_op(op)) return e;
+  NHMC_CHECK_ARG(x && y && n_chains > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = op->channels, D = op->img_dim;
+  const int64_t P = (int64_t)D * D;
+  switch (op->kind) {
+    case NHMC_OP_INPAINT: {
+      const int64_t M = (int64_t)op->n_kept * C;
+      if (M == 0) return NHMC_OK;
+      inpaint_fwd_kernel<<<dim3(cta_count(M, kThreads, n_chains), n_chains), kThreads, 0, st>>>(x, y, op->kept_pix, op->n_kept, C, P);
+      break;
+    }
+    case NHMC_OP_SR: {
+      const int64_t M = nhmc_op_meas_size(op);
+      sr_fwd_kernel<<<dim3(cta_count(M, kThreads, n_chains), n_chains), kThreads, 0, st>>>(x, y, C, D, op->ratio);
+      break;
+    }
+    case NHMC_OP_HDR: {
+      const int64_t total = (int64_t)n_chains * C * P;
+      hdr_fwd_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x, y, total);
+      break;
+    }
+    case NHMC_OP_DEBLUR2D: {
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return deblur_forward(op, x, y, n_chains, ws, st);
+    }
+    case NHMC_OP_PHASE: {
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return phase_forward(op, x, y, n_chains, ws, st);
+    }
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
+static int adjoint_or_pinv(const nhmc_op* op, const float* r, float* out, int n_chains, void* workspace,
+                           cudaStream_t st, bool pinv) {
+  if (int e = check_op(op)) return e;
+  NHMC_CHECK_ARG(r && out && n_chains > 0, "bad arguments");
+  const int C = op->channels, D = op->img_dim;
+  const int64_t P = (int64_t)D * D, N = (int64_t)C * P;
+  switch (op->kind) {
+    case NHMC_OP_INPAINT:
+      inpaint_adj_kernel<<<dim3(cta_count(N, kThreads * 4, n_chains), n_chains), kThreads, 0, st>>>(r, out, op->pix_to_kept, op->n_kept, C, P);
+      break;
+    case NHMC_OP_SR:
+      sr_up_kernel<<<dim3(cta_count(N, kThreads * 4, n_chains), n_chains), kThreads, 0, st>>>(
+          r, out, C, D, op->ratio, pinv ? 1.0f : 1.0f / (float)(op->ratio * op->ratio));
+      break;
+    case NHMC_OP_HDR:
+      if (!pinv) { set_error("hdr is non-linear: no adjoint; use nhmc_op_loss_grad"); return NHMC_ERR_UNSUPPORTED; }
+      copy_kernel<<<cta_count((int64_t)n_chains * N, kThreads * 4, 1), kThreads, 0, st>>>(r, out, (int64_t)n_chains * N);
+      break;
+    case NHMC_OP_DEBLUR2D: {
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      NHMC_CHECK_ARG(!pinv || op->gain_pinv, "gain_pinv table missing");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return deblur_adjoint(op, r, out, n_chains, ws, st, pinv);
+    }
+    case NHMC_OP_PHASE: {
+      if (!pinv) { set_error("phase retrieval is non-linear: no adjoint; use nhmc_op_loss_grad"); return NHMC_ERR_UNSUPPORTED; }
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return phase_pinv(op, r, out, n_chains, ws, st);
+    }
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
+extern "C" int nhmc_op_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* workspace,
+                               nhmc_stream_t stream) {
+  return adjoint_or_pinv(op, r, out, n_chains, workspace, (cudaStream_t)stream, false);
+}
+extern "C" int nhmc_op_pinv(const nhmc_op* op, const float* y, float* out, int n_chains, void* workspace,
+                            nhmc_stream_t stream) {
+  return adjoint_or_pinv(op, y, out, n_chains, workspace, (cudaStream_t)stream, true);
+}
+
+extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out,
+                                 double* loss, int n_chains, void* workspace, nhmc_stream_t stream) {
+  if (int e = check_op(op)) return e;
+  NHMC_CHECK_ARG(x_hat && y && g && loss && workspace && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(aligned16(x_hat) && aligned16(g) && (!xc_out || aligned16(xc_out)), "pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C = op->channels, D = op->img_dim;
+  const int64_t P = (int64_t)D * D, N = (int64_t)C * P;
+  const RedWs ws = red_ws(workspace, n_chains);
+  char* extra = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+  switch (op->kind) {
+    case NHMC_OP_INPAINT: {
+      NHMC_CHECK_ARG(P % 4 == 0 && aligned16(op->pix_to_kept), "img_dim^2 must be a multiple of 4");
+      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      inpaint_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, op->pix_to_kept, op->n_kept, C, P, loss, ws, op->no_clamp);
+      break;
+    }
+    case NHMC_OP_SR: {
+      const int r = op->ratio, TR = sr_tile_rows(D, r);
+      NHMC_CHECK_ARG(D % 4 == 0 && D % TR == 0, "img_dim must be a multiple of 4 and of the strip height");
+      const int strips = C * (D / TR);
+      NHMC_CHECK_ARG(strips <= kMaxBlocksPerChain, "image too large for the SR strip reduction");
+      const size_t smem = ((size_t)TR * D + (size_t)TR * (D / r) + (size_t)(TR / r) * (D / r)) * sizeof(float);
+      NHMC_CHECK_ARG(smem <= 200 * 1024, "SR strip does not fit in shared memory");
+      if (smem > 48 * 1024) {
+        if (int e = cuda_status(cudaFuncSetAttribute(sr_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "sr smem")) return e;
+      }
+      sr_loss_grad_kernel<<<dim3(strips, n_chains), kThreads, smem, st>>>(x_hat, y, g, xc_out, C, D, r, TR, loss, ws, op->no_clamp);
+      break;
+    }
+    case NHMC_OP_HDR: {
+      NHMC_CHECK_ARG(N % 4 == 0 && aligned16(y), "N must be a multiple of 4");
+      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      hdr_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, N, loss, ws, op->no_clamp);
+      break;
+    }
+    case NHMC_OP_DEBLUR2D:
+      return deblur_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
+    case NHMC_OP_PHASE:
+      (void)extra;
+      return phase_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
+  }
+  return NHMC_LAUNCH_CHECK();
+}

@@ -1,0 +1,121 @@
+"""Torch-tensor wrappers around the C ABI (raw device pointers + torch's current stream)."""
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.NhmcError("%s must live on a CUDA device: the sm_100a kernels have no CPU fallback" % name)
+    if not t.is_contiguous():
+        raise _lib.NhmcError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.NhmcError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def zeros_workspace(nbytes, device):
+    """Device scratch, zero-filled once (reduction tickets reset themselves afterwards)."""
+    return torch.zeros((int(nbytes) + 7) // 8, dtype=torch.int64, device=device)
+
+
+def begin_iteration(chains, sched):
+    check(lib().nhmc_begin_iteration(chains.ptr(), chains.n, sched, _stream()), "nhmc_begin_iteration")
+
+
+def leapfrog_workspace(n_chains, device):
+    return zeros_workspace(lib().nhmc_leapfrog_workspace_bytes(n_chains), device)
+
+
+def leapfrog(mode, x_in, x_out, p, g_a, g_b, loss, chains, mass, ws):
+    B = x_in.shape[0]
+    N = x_in[0].numel()
+    _req(x_in, torch.float32, "x_in"); _req(p, torch.float32, "p"); _req(g_a, torch.float32, "g_a")
+    if x_out is not None: _req(x_out, torch.float32, "x_out")
+    if g_b is not None: _req(g_b, torch.float32, "g_b")
+    if loss is not None: _req(loss, torch.float64, "loss")
+    check(lib().nhmc_leapfrog(mode, _p(x_in), _p(x_out), _p(p), _p(g_a), _p(g_b), _p(loss), chains.ptr(),
+                              float(mass), B, N, _p(ws), _stream()), "nhmc_leapfrog")
+
+
+def ddim_mask_words(n_per_chain):
+    return lib().nhmc_ddim_mask_bytes(n_per_chain) // 4
+
+
+def ddim_fwd(xt, eps, xt_next, mask, coef):
+    """eps: network output [B, Ce, H, W] (first C channels used), any of f32/bf16/f16."""
+    B = xt.shape[0]
+    N = xt[0].numel()
+    _req(xt, torch.float32, "xt"); _req(xt_next, torch.float32, "xt_next"); _req(eps, None, "eps")
+    c1, sa, c2, ss = coef
+    check(lib().nhmc_ddim_fwd(_p(xt), _p(eps), _DT[eps.dtype], eps[0].numel(), _p(xt_next), _p(mask),
+                              c1, sa, c2, ss, B, N, _stream()), "nhmc_ddim_fwd")
+
+
+def ddim_bwd(g_a, g_b, mask, g_xt, g_eps, coef):
+    B = g_a.shape[0]
+    N = g_a[0].numel()
+    _req(g_a, torch.float32, "g_a"); _req(g_xt, torch.float32, "g_xt"); _req(mask, torch.int32, "mask")
+    if g_b is not None: _req(g_b, torch.float32, "g_b")
+    dt, stride = _lib.F32, N
+    if g_eps is not None:
+        _req(g_eps, None, "g_eps")
+        dt, stride = _DT[g_eps.dtype], g_eps[0].numel()
+    c1, sa, c2, ss = coef
+    check(lib().nhmc_ddim_bwd(_p(g_a), _p(g_b), _p(mask), _p(g_xt), _p(g_eps), dt, stride, c1, sa, c2, ss, B, N,
+                              _stream()), "nhmc_ddim_bwd")
+
+
+def accept(chains, u, mass, sched, n_slots):
+    _req(u, torch.float32, "u")
+    check(lib().nhmc_accept(chains.ptr(), _p(u), float(mass), sched, n_slots, chains.n, _stream()), "nhmc_accept")
+
+
+def commit(chains, x, x_prop, x_hat, x_keep, samples, sched, n_slots):
+    N = x[0].numel()
+    for t, n in ((x, "x"), (x_prop, "x_prop"), (x_hat, "x_hat")):
+        _req(t, torch.float32, n)
+    check(lib().nhmc_commit(chains.ptr(), _p(x), _p(x_prop), _p(x_hat), _p(x_keep), _p(samples), sched, n_slots,
+                            chains.n, N, _stream()), "nhmc_commit")
+
+
+def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last):
+    """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
+    B, Cc = x.shape[0], x.shape[1]
+    hw = x[0, 0].numel()
+    check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
+                            _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), B, Cc, hw, groups, float(eps),
+                            _stream()), "nhmc_gn_fwd")
+
+
+def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last):
+    B, Cc = x.shape[0], x.shape[1]
+    hw = x[0, 0].numel()
+    check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
+                            _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), 0, 0, B, Cc, hw, groups,
+                            _stream()), "nhmc_gn_bwd")
+
+
+def softmax_fwd(logits, probs, scale):
+    cols = logits.shape[-1]
+    rows = logits.numel() // cols
+    check(lib().nhmc_softmax_fwd(_DT[logits.dtype], _p(logits), _p(probs), float(scale), rows, cols, _stream()),
+          "nhmc_softmax_fwd")
+
+
+def softmax_bwd(probs, dprobs, dlogits, scale):
+    cols = probs.shape[-1]
+    rows = probs.numel() // cols
+    check(lib().nhmc_softmax_bwd(_DT[probs.dtype], _p(probs), _p(dprobs), _p(dlogits), float(scale), rows, cols,
+                                 _stream()), "nhmc_softmax_bwd")

@@ -1,0 +1,249 @@
+"""Measurement operators behind the reference's `H_funcs` interface (obs_functions/Hfuncs.py).
+
+Each class keeps the reference's duck-typed surface -- `H(vec)`, `Ht(vec)`, `H_pinv(vec)`, `is_linear()` --
+and adds `loss_grad(x_hat, y)`, the fused residual / loss / adjoint used by the sampler.  Tables (kept
+pixel indices, SVD factors, spectral gain) are built once on the host with the same torch calls as the
+reference, or extracted from a reference `H_funcs` object by `from_reference`, and live on the device.
+All arithmetic runs in the sm_100a kernels (no CPU path).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, kernels
+from ._lib import OpDesc, check, lib
+
+
+class Operator:
+    kind = None
+    linear = True
+
+    def __init__(self, channels, img_dim, device):
+        self.channels, self.img_dim = int(channels), int(img_dim)
+        self.device = torch.device(device)
+        self.desc = OpDesc()
+        self.desc.kind = self.kind
+        self.desc.channels = self.channels
+        self.desc.img_dim = self.img_dim
+        self._ws = {}
+
+    def set_clamp(self, on):
+        """loss_grad clamps x_hat to [-1,1] first (pixel path, main_sampling.py:709); the latent path
+        feeds the un-clipped decoder output (main_sampling_latent.py:651)."""
+        self.desc.no_clamp = 0 if on else 1
+
+    # ---- reference surface -----------------------------------------------------------------
+    def is_linear(self):
+        return self.linear
+
+    def meas_size(self):
+        return int(lib().nhmc_op_meas_size(ctypes.byref(self.desc)))
+
+    def meas_shape(self, B):
+        return (B, self.meas_size())
+
+    def _workspace(self, B):
+        if B not in self._ws:
+            self._ws[B] = kernels.zeros_workspace(lib().nhmc_op_workspace_bytes(ctypes.byref(self.desc), B), self.device)
+        return self._ws[B]
+
+    def _img(self, vec):
+        B = vec.shape[0]
+        x = vec.reshape(B, self.channels, self.img_dim, self.img_dim)
+        return kernels._req(x.contiguous().float(), torch.float32, "image")
+
+    def H(self, vec, **kwargs):
+        x = self._img(vec)
+        B = x.shape[0]
+        y = torch.empty(self.meas_shape(B), dtype=torch.float32, device=x.device)
+        check(lib().nhmc_op_forward(ctypes.byref(self.desc), x.data_ptr(), y.data_ptr(), B,
+                                    self._workspace(B).data_ptr(), kernels._stream()), "nhmc_op_forward")
+        return y
+
+    forward = H
+
+    def Ht(self, vec):
+        B = vec.shape[0]
+        r = kernels._req(vec.reshape(self.meas_shape(B)).contiguous().float(), torch.float32, "measurement")
+        out = torch.empty(B, self.channels * self.img_dim ** 2, dtype=torch.float32, device=r.device)
+        check(lib().nhmc_op_adjoint(ctypes.byref(self.desc), r.data_ptr(), out.data_ptr(), B,
+                                    self._workspace(B).data_ptr(), kernels._stream()), "nhmc_op_adjoint")
+        return out
+
+    def H_pinv(self, vec):
+        B = vec.shape[0]
+        y = kernels._req(vec.reshape(self.meas_shape(B)).contiguous().float(), torch.float32, "measurement")
+        out = torch.empty(B, self.channels * self.img_dim ** 2, dtype=torch.float32, device=y.device)
+        check(lib().nhmc_op_pinv(ctypes.byref(self.desc), y.data_ptr(), out.data_ptr(), B,
+                                 self._workspace(B).data_ptr(), kernels._stream()), "nhmc_op_pinv")
+        return out
+
+    # ---- sampler surface -------------------------------------------------------------------
+    def loss_grad(self, x_hat, y, g=None, xc=None, loss=None):
+        """(loss[B] fp64, g = dloss/dx_hat, clamp(x_hat)) of main_sampling.py:709-711, one fused call."""
+        x_hat = kernels._req(x_hat, torch.float32, "x_hat")
+        B = x_hat.shape[0]
+        y = kernels._req(y.reshape(self.meas_shape(B)), torch.float32, "y")
+        g = torch.empty_like(x_hat) if g is None else g
+        xc = torch.empty_like(x_hat) if xc is None else xc
+        loss = torch.empty(B, dtype=torch.float64, device=x_hat.device) if loss is None else loss
+        check(lib().nhmc_op_loss_grad(ctypes.byref(self.desc), x_hat.data_ptr(), y.data_ptr(), g.data_ptr(),
+                                      xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
+                                      kernels._stream()), "nhmc_op_loss_grad")
+        return loss, g, xc
+
+
+class Inpainting(Operator):
+    """Row-selection operator: y[b, 3k+c] = x[b, c, kept_pix[k]] (Hfuncs.py:119-154)."""
+    kind = _lib.OP_INPAINT
+
+    def __init__(self, channels, img_dim, missing_indices, device):
+        """`missing_indices`: the reference's channel-interleaved index vector (3*pix + c), main_sampling.py:302-305.
+
+        The reference spends 44 s in a python `i not in tensor` loop here (Hfuncs.py:125); a boolean mask gives
+        the same ascending kept list."""
+        super().__init__(channels, img_dim, device)
+        P = img_dim ** 2
+        mi = torch.as_tensor(missing_indices).detach().cpu().numpy().astype(np.int64)
+        miss = np.zeros(P, dtype=bool)
+        miss[np.unique(mi // channels)] = True
+        kept = np.nonzero(~miss)[0].astype(np.int32)
+        p2k = np.full(P, -1, dtype=np.int32)
+        p2k[kept] = np.arange(len(kept), dtype=np.int32)
+        self.missing_indices = torch.as_tensor(missing_indices).to(self.device)
+        self.kept_pix = torch.from_numpy(kept).to(self.device)
+        self.pix_to_kept = torch.from_numpy(p2k).to(self.device)
+        # the reference's attribute, for callers that read it (channel-interleaved, ascending)
+        self.kept_indices = (channels * self.kept_pix.long()[:, None] + torch.arange(channels, device=self.device)[None]).reshape(-1)
+        self.desc.n_kept = len(kept)
+        self.desc.kept_pix = self.kept_pix.data_ptr()
+        self.desc.pix_to_kept = self.pix_to_kept.data_ptr()
+
+    @classmethod
+    def random(cls, channels, img_dim, device, frac=0.92):
+        """main_sampling.py:302-305: randperm on the global CPU generator, first 92 % of the pixels dropped."""
+        missing_r = channels * torch.randperm(img_dim ** 2)[: int(img_dim ** 2 * frac)].long()
+        missing = torch.cat([missing_r + c for c in range(channels)], dim=0)
+        return cls(channels, img_dim, missing, device)
+
+
+class SuperResolution(Operator):
+    """ratio x ratio block average in CHW order (Hfuncs.py:180-234)."""
+    kind = _lib.OP_SR
+
+    def __init__(self, channels, img_dim, ratio, device):
+        assert img_dim % ratio == 0
+        super().__init__(channels, img_dim, device)
+        self.ratio = int(ratio)
+        self.y_dim = img_dim // ratio
+        self.desc.ratio = self.ratio
+
+
+class HDR(Operator):
+    """y = clip(x/0.5, -1, 1) (Hfuncs.py:406-445); image-shaped measurement."""
+    kind = _lib.OP_HDR
+    linear = False
+
+    def __init__(self, channels=3, img_dim=256, device="cuda"):
+        super().__init__(channels, img_dim, device)
+
+    def meas_shape(self, B):
+        return (B, self.channels, self.img_dim, self.img_dim)
+
+    def H_pinv(self, vec):
+        return vec
+
+
+def _band_matrix(kernel, img_dim):
+    """Hfuncs.py:460-471: the loop `range(i - k//2, i + k//2)` drops the last tap."""
+    k = torch.as_tensor(kernel).detach().cpu().float()
+    h = k.shape[0] // 2
+    M = torch.zeros(img_dim, img_dim)
+    for d in range(-h, h):
+        v = k[d + h]
+        idx = torch.arange(max(0, -d), min(img_dim, img_dim - d))
+        M[idx, idx + d] = v
+    return M
+
+
+def gaussian_taps(sigma, half=4):
+    """Normalised Gaussian taps as main_sampling.py:327-335 builds them (fp32 exp, then / sum)."""
+    pdf = lambda v: torch.exp(torch.Tensor([-0.5 * (v / sigma) ** 2]))
+    k = torch.Tensor([pdf(i) for i in range(-half, half + 1)])
+    return k / k.sum()
+
+
+class Deblurring2D(Operator):
+    """Y_c = U1 (G_c .* (V1^T X_c V2)) U2^T (Hfuncs.py:448-523, tiled-singulars quirk included)."""
+    kind = _lib.OP_DEBLUR2D
+
+    def __init__(self, kernel1, kernel2, channels, img_dim, device, tables=None, zero=3e-2):
+        super().__init__(channels, img_dim, device)
+        if tables is None:
+            U1, s1, V1 = torch.svd(_band_matrix(kernel1, img_dim), some=False)
+            U2, s2, V2 = torch.svd(_band_matrix(kernel2, img_dim), some=False)
+            s1 = s1.clone(); s2 = s2.clone()
+            s1[s1 < zero] = 0
+            s2[s2 < zero] = 0
+            s = torch.matmul(s1.reshape(img_dim, 1), s2.reshape(1, img_dim)).reshape(img_dim ** 2)
+            s_sorted, perm = s.sort(descending=True)
+        else:
+            U1, V1, U2, V2, s_sorted, perm = [torch.as_tensor(t).detach().cpu() for t in tables]
+        n = img_dim ** 2
+        rank = torch.empty(n, dtype=torch.long)
+        rank[perm.long()] = torch.arange(n)
+        # Hfuncs.py:519-520 tiles the sorted singulars while Vt (:493-499) interleaves channels
+        gain = torch.stack([s_sorted[(channels * rank + c) % n] for c in range(channels)], 0).float()
+        gpinv = torch.where(gain != 0, 1.0 / torch.where(gain != 0, gain, torch.ones_like(gain)), torch.zeros_like(gain))
+        dev = self.device
+        self.U_small1, self.V_small1 = U1.float().contiguous().to(dev), V1.float().contiguous().to(dev)
+        self.U_small2, self.V_small2 = U2.float().contiguous().to(dev), V2.float().contiguous().to(dev)
+        self._singulars, self._perm = s_sorted.to(dev), perm.to(dev)
+        self.gain, self.gain_pinv = gain.contiguous().to(dev), gpinv.contiguous().to(dev)
+        d = self.desc
+        d.U1, d.V1, d.U2, d.V2 = (t.data_ptr() for t in (self.U_small1, self.V_small1, self.U_small2, self.V_small2))
+        d.gain, d.gain_pinv = self.gain.data_ptr(), self.gain_pinv.data_ptr()
+
+
+class PhaseRetrievalOperator(Operator):
+    """y = |fft2c(pad(x, 64))| (Hfuncs.py:318-366, fastmri_utils.py:67-89); image-shaped measurement."""
+    kind = _lib.OP_PHASE
+    linear = False
+
+    def __init__(self, oversample, device, channels=3, img_dim=256):
+        super().__init__(channels, img_dim, device)
+        self.pad = int((oversample / 8.0) * 256)
+        self.desc.pad = self.pad
+
+    def meas_shape(self, B):
+        L = self.img_dim + 2 * self.pad
+        return (B, self.channels, L, L)
+
+    def H_pinv(self, vec):
+        out = super().H_pinv(vec)
+        return out.reshape(vec.shape[0], self.channels, self.img_dim, self.img_dim)
+
+
+def from_reference(H_funcs, channels, img_dim, device):
+    """Build the device operator from one of the reference's own `H_funcs` objects (duck-typed by
+    attribute, so the reference module does not have to be importable)."""
+    if isinstance(H_funcs, Operator):
+        return H_funcs
+    name = type(H_funcs).__name__
+    if hasattr(H_funcs, "kept_indices") and hasattr(H_funcs, "missing_indices"):
+        return Inpainting(getattr(H_funcs, "channels", channels), getattr(H_funcs, "img_dim", img_dim),
+                          H_funcs.missing_indices, device)
+    if hasattr(H_funcs, "U_small1") and hasattr(H_funcs, "_perm"):
+        return Deblurring2D(None, None, H_funcs.channels, H_funcs.img_dim, device,
+                            tables=(H_funcs.U_small1, H_funcs.V_small1, H_funcs.U_small2, H_funcs.V_small2,
+                                    H_funcs._singulars, H_funcs._perm))
+    if hasattr(H_funcs, "ratio") and hasattr(H_funcs, "y_dim") and hasattr(H_funcs, "V_small"):
+        return SuperResolution(H_funcs.channels, H_funcs.img_dim, H_funcs.ratio, device)
+    if name == "HDR":
+        return HDR(channels, img_dim, device)
+    if name == "PhaseRetrievalOperator" or (hasattr(H_funcs, "pad") and hasattr(H_funcs, "undo_padding")):
+        op = PhaseRetrievalOperator(2.0, device, channels, img_dim)
+        op.pad = int(H_funcs.pad); op.desc.pad = op.pad
+        return op
+    raise _lib.NhmcError("operator %s is not on the accelerated path (inpaint, sr, hdr, deblur_aniso, phase)" % name)

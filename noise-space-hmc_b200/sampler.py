@@ -1,0 +1,257 @@
+"""Noise-space HMC sampler: drop-in `hmc()` / `hmc_latent()` on the sm_100a kernels.
+
+Mirrors /root/reference/main_sampling.py:660-774 (`hmc`) and
+/root/reference/main_sampling_latent.py:623-762 (`hmc_latent`): same signatures, same `opt` fields
+(tau, epsilon, m, sigma_0, sigma_y), same algo / H_funcs / model objects.  What changes is where the
+work runs:
+
+  * the score network (any `model(x, t)`; ours or the reference's) stays a PyTorch call, its input-VJP
+    a `torch.autograd.grad` call;
+  * everything around it is a handful of fused kernels (include/nhmc.h): DDIM epilogue fwd/bwd,
+    operator loss+gradient, leapfrog with in-register energies, on-device Metropolis + schedule;
+  * chains are a batch dimension: every chain carries its own epoch / sigma_y / epsilon / reject
+    counter in a device array, so B independent replicas of the (batch-1-only) reference algorithm
+    advance in lock step with no host round trip inside an iteration.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, kernels, operators, schedule
+from .chain import ChainState, new_host_state
+
+
+class GradEvaluator:
+    """loss(x) = sum (y - A(clip(G(x))))^2 and its gradient, G = the few-step DDIM map.
+
+    Replaces `iterative_sampling` + `cal_x0`/`map_back` + `H_funcs.H` + `autograd.grad`
+    (main_sampling.py:693-695,709-711,898-915; algos/unconditional.py:9-28).  Autograd is used only
+    across the score network; the epilogues and the operator are differentiated by the kernels.
+    """
+
+    def __init__(self, model, steps, op, y, example_x, net_grad=True, decode=None):
+        self.model, self.steps, self.op, self.y = model, steps, op, y
+        self.net_grad = net_grad
+        self.decode = decode
+        B = example_x.shape[0]
+        dev = example_x.device
+        self.B, self.N = B, example_x[0].numel()
+        self.t = [torch.ones(B, device=dev) * float(s[0]) for s in steps]       # main_sampling.py:903
+        self.xt = [torch.empty_like(example_x) for _ in steps]                  # outputs of each epilogue
+        words = kernels.ddim_mask_words(self.N)
+        self.mask = [torch.empty(B, words, dtype=torch.int32, device=dev) for _ in steps]
+        self.gxt = [torch.empty_like(example_x) for _ in range(2)]
+        self.g_hat = torch.empty_like(example_x)
+        self.xc = torch.empty_like(example_x)
+        self.loss = torch.zeros(B, dtype=torch.float64, device=dev)
+        self.g_eps = None     # cotangent buffer for the network output, allocated on first use
+        self.n_net_fwd = 0
+        self.n_net_vjp = 0
+
+    def _net(self, x_in, k):
+        if self.net_grad:
+            xk = x_in.detach().requires_grad_(True)
+            with torch.enable_grad():
+                out = self.model(xk, self.t[k])
+        else:
+            xk = None
+            with torch.no_grad():
+                out = self.model(x_in, self.t[k])
+        self.n_net_fwd += 1
+        return xk, out
+
+    def __call__(self, x):
+        """Returns (loss[B] fp64, g_a, g_b, xc): dloss/dx = g_a + g_b (g_b may be None)."""
+        tape = []
+        x_in = x
+        for k, (_, c1, sa, c2, ss) in enumerate(self.steps):
+            xk, out = self._net(x_in, k)
+            eps = out.detach()
+            if not eps.is_contiguous():
+                eps = eps.contiguous()
+            kernels.ddim_fwd(x_in, eps, self.xt[k], self.mask[k], (c1, sa, c2, ss))
+            tape.append((xk, out))
+            x_in = self.xt[k]
+
+        if self.decode is None:
+            self.op.loss_grad(x_in, self.y, g=self.g_hat, xc=self.xc, loss=self.loss)
+            g_a, g_b = self.g_hat, None
+        else:
+            g_a, g_b = self._decode_loss_grad(x_in), None
+
+        for k in reversed(range(len(self.steps))):
+            _, c1, sa, c2, ss = self.steps[k]
+            xk, out = tape[k]
+            g_xt = self.gxt[k % 2]
+            if self.net_grad:
+                if self.g_eps is None or self.g_eps.shape != out.shape or self.g_eps.dtype != out.dtype:
+                    self.g_eps = torch.zeros(out.shape, dtype=out.dtype, device=out.device)  # channels >= C stay 0
+                kernels.ddim_bwd(g_a, g_b, self.mask[k], g_xt, self.g_eps, (c1, sa, c2, ss))
+                (vjp,) = torch.autograd.grad(out, xk, self.g_eps)
+                self.n_net_vjp += 1
+                g_a, g_b = g_xt, vjp.contiguous()
+            else:
+                kernels.ddim_bwd(g_a, g_b, self.mask[k], g_xt, None, (c1, sa, c2, ss))
+                g_a, g_b = g_xt, None
+        return self.loss, g_a, g_b, self.xc
+
+    def _decode_loss_grad(self, z_hat):
+        """Latent path: loss = sum (y - H(decode(clip(z_hat))))^2 (main_sampling_latent.py:651,670).
+        The decoder and its VJP stay PyTorch; the latent clip mask is applied here."""
+        zc = z_hat.clamp(-1, 1)
+        self.xc.copy_(zc)
+        zv = zc.detach().requires_grad_(True)
+        with torch.enable_grad():
+            img = self.decode(zv)
+        img_c = img.detach().float().contiguous()
+        _, g_img, _ = self.op.loss_grad(img_c, self.y, loss=self.loss)
+        (g_z,) = torch.autograd.grad(img, zv, g_img.to(img.dtype))
+        inr = ((z_hat >= -1) & (z_hat <= 1)).to(g_z.dtype)
+        torch.mul(g_z.float(), inr, out=self.g_hat)
+        return self.g_hat
+
+
+class HMCSampler:
+    """State + one-iteration stepper shared by hmc() and hmc_latent()."""
+
+    def __init__(self, x, evaluator, tau, epsilon, sigma_0, mass=1.0, sched=_lib.SCHED_PIXEL, sigma_y=None,
+                 n_slots=20):
+        self.ev = evaluator
+        self.sched, self.mass, self.n_slots = sched, float(mass), n_slots
+        self.x = x.detach().clone().float().contiguous()
+        self.B = self.x.shape[0]
+        dev = self.x.device
+        self.L = schedule.leapfrog_steps(tau, epsilon)
+        self.chains = ChainState(new_host_state(self.B, tau, epsilon, sigma_0, sigma_y), dev)
+        self.x_prop = torch.empty_like(self.x)
+        self.p = torch.empty_like(self.x)
+        self.x_keep = torch.zeros_like(self.x) if sched == _lib.SCHED_LATENT else None
+        self.samples = torch.zeros((self.B, n_slots) + tuple(self.x.shape[1:]), dtype=torch.float32, device=dev)
+        self.ws = kernels.leapfrog_workspace(self.B, dev)
+        self.u_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
+        self.leapfrog_steps_done = 0
+
+    def iteration(self, p, u):
+        """One HMC iteration for every chain. p: momentum draw [B,C,H,W]; u: uniform draws [B]."""
+        ev, ch, m = self.ev, self.chains, self.mass
+        kernels.begin_iteration(ch, self.sched)
+        self.p.copy_(p)
+        loss, g_a, g_b, _ = ev(self.x)                                           # main_sampling.py:693-695
+        kernels.leapfrog(_lib.LF_FIRST, self.x, self.x_prop, self.p, g_a, g_b, loss, ch, m, self.ws)
+        xc = None
+        for l in range(self.L):                                                  # main_sampling.py:704-713
+            loss, g_a, g_b, xc = ev(self.x_prop)
+            mode = _lib.LF_LAST if l == self.L - 1 else _lib.LF_MIDDLE
+            kernels.leapfrog(mode, self.x_prop, self.x_prop, self.p, g_a, g_b, loss, ch, m, self.ws)
+        self.leapfrog_steps_done += self.L
+        self.u_dev.copy_(torch.as_tensor(u, dtype=torch.float32).reshape(self.B), non_blocking=True)
+        kernels.accept(ch, self.u_dev, m, self.sched, self.n_slots)              # main_sampling.py:717-749
+        kernels.commit(ch, self.x, self.x_prop, xc, self.x_keep, self.samples, self.sched, self.n_slots)
+        return xc
+
+    def collected(self):
+        """[B, S, ...] samples in collection order (S = min(n_collected, n_slots), same for all finished chains)."""
+        st = self.chains.read()
+        out = []
+        for b in range(self.B):
+            n = int(st["n_collected"][b])
+            if n <= self.n_slots:
+                out.append(self.samples[b, :n])
+            else:   # ring buffer wrapped: oldest kept sample first
+                k = n % self.n_slots
+                out.append(torch.cat([self.samples[b, k:], self.samples[b, :k]], 0))
+        return out
+
+
+def _default_draws(m):
+    def momentum(x):
+        return torch.randn_like(x) * math.sqrt(m)             # main_sampling.py:692 (device generator)
+
+    def uniform(B):
+        return torch.rand(B)                                   # main_sampling.py:720 (global CPU generator)
+    return momentum, uniform
+
+
+def _run(sampler, momentum, uniform, max_iters, on_iteration):
+    it = 0
+    while True:
+        if max_iters is not None and it >= max_iters:
+            break
+        p = momentum(sampler.x)
+        xc = sampler.iteration(p, uniform(sampler.B))
+        st = sampler.chains.read()                             # the one host sync per iteration
+        if on_iteration is not None:
+            on_iteration(it, st, xc)
+        it += 1
+        if not st["active"].any():
+            break
+    return it
+
+
+def _model_of(algo):
+    if getattr(algo, "cls_fn", None) is not None:
+        raise _lib.NhmcError("classifier guidance (cls_fn) is not on the accelerated hmc path")
+    return algo.model
+
+
+def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
+        max_iters=None, on_iteration=None, return_sampler=False):
+    """Drop-in for main_sampling.hmc (main_sampling.py:660-774).
+
+    x: [B,3,H,W] initial noise; b: fp32 betas [1000]; seq/seq_next: timestep lists; algo: object with
+    `.model` (`model(x,t) -> [B,6,H,W]` or 3 channels); opt: `.tau .epsilon .m .sigma_0` (sigma_0 already
+    doubled by prepare_measurement, main_sampling.py:348); y_0: measurement; H_funcs: a reference
+    operator object or one of nhmc_b200.operators.  Returns the 20 collected samples, `[20,3,H,W]` for
+    B == 1 (exactly the reference's return) and `[B,20,3,H,W]` for B > 1 (B independent chains -- the
+    reference itself cannot run B > 1, main_sampling.py:719-720).
+    """
+    if not x.is_cuda:
+        raise _lib.NhmcError("hmc() runs on a CUDA device (sm_100a); there is no CPU fallback")
+    B, C, D = x.shape[0], x.shape[1], x.shape[2]
+    assert n == B, "n must equal the batch size (main_sampling.py:472)"
+    model = _model_of(algo)
+    op = operators.from_reference(H_funcs, C, D, x.device)
+    steps = schedule.ddim_steps(schedule.alpha_table(b), seq, seq_next)
+    y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
+    m = float(getattr(opt, "m", 1.0))
+    ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
+    smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20)
+    dm, du = _default_draws(m)
+    _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
+    if return_sampler:
+        return smp
+    out = smp.collected()
+    return out[0] if B == 1 else torch.stack(out)
+
+
+def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
+               max_iters=None, on_iteration=None, return_sampler=False, image_size=256):
+    """Drop-in for main_sampling_latent.hmc_latent (main_sampling_latent.py:623-762).
+
+    algo.model is an LDM object exposing `.apply_model(z,t,None)` (no-grad, ddpm.py:892-893),
+    `.differentiable_decode_first_stage(z)`, `.alphas_cumprod`, `.alphas_cumprod_prev`.  Returns the last
+    <= 10 collected latents ([S,3,h,w] for B == 1, list per chain otherwise).
+    """
+    if not x.is_cuda:
+        raise _lib.NhmcError("hmc_latent() runs on a CUDA device (sm_100a); there is no CPU fallback")
+    B = x.shape[0]
+    assert n == B
+    ldm = _model_of(algo)
+    op = operators.from_reference(H_funcs, 3, image_size, x.device)
+    op.set_clamp(False)        # the decoded image is NOT clipped in the latent loss (main_sampling_latent.py:651)
+    table = schedule.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev)
+    steps = schedule.ddim_steps(table, seq, seq_next)
+    y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
+    m = float(getattr(opt, "m", 1.0))
+    net = lambda z, t: ldm.apply_model(z, t, None)
+    ev = GradEvaluator(net, steps, op, y, x.detach().float().contiguous(), net_grad=False,
+                       decode=ldm.differentiable_decode_first_stage)
+    smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_LATENT,
+                     sigma_y=opt.sigma_y, n_slots=10)
+    dm, du = _default_draws(m)
+    _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
+    if return_sampler:
+        return smp
+    out = smp.collected()
+    return out[0] if B == 1 else out

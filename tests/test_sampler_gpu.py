@@ -1,0 +1,152 @@
+"""GPU parity of the whole sampler path against the oracle and the recorded reference trace."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import hmc as ohmc, operators as oops, schedule as osch
+from oracle.tinynet import TinyEpsNet
+
+T = torch.from_numpy
+SEQ, SEQ_NEXT = [250, 500, 750], [-1, 250, 500]
+
+
+def _betas():
+    return T(osch.beta_schedule("linear", 1e-4, 0.02, 1000)).float()
+
+
+def _setup(golden, B=1):
+    import nhmc_b200
+    from nhmc_b200 import operators as P, sampler, schedule
+    g = golden("hmc_trace.npz")
+    net_cpu = TinyEpsNet()
+    net = TinyEpsNet().cuda()
+    op = P.Inpainting(3, 32, T(g["missing"]), "cuda")
+    oop = oops.Inpainting.from_missing_indices(3, 32, g["missing"])
+    tab = osch.alpha_bar_table(osch.beta_schedule("linear", 1e-4, 0.02, 1000))
+    return g, net_cpu, net, op, oop, tab
+
+
+def test_grad_eval_matches_oracle(golden):
+    from nhmc_b200 import sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
+    B = 3
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
+    ev = sampler.GradEvaluator(net, steps, op, y.cuda(), x.cuda())
+    loss, ga, gb, xc = ev(x.cuda())
+    gtot = (ga + gb).cpu()
+    xh, oloss, og = ohmc.grad_eval(x, ohmc.module_eps_net(net_cpu), tab, SEQ, SEQ_NEXT, oop, y)
+    np.testing.assert_allclose(xc.cpu().numpy(), xh.numpy(), atol=2e-5)
+    np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=1e-4)
+    np.testing.assert_allclose(gtot.numpy(), og.numpy(), atol=2e-4 * float(og.abs().max()))
+    assert ev.n_net_fwd == 3 and ev.n_net_vjp == 3
+
+
+def test_hmc_teacher_forced_against_reference_trace(golden):
+    """Same state, same momentum and uniform draws as the real hmc(): accept decisions must match wherever
+    |u - prob| is outside the fp32 ambiguity band, accepted images within 1e-3 (north-star tolerance)."""
+    from nhmc_b200 import _lib, sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
+    y = T(g["y_0"]).cuda(); sigma_0 = float(g["sigma_0"])
+    x0 = T(g["x_start"][0:1]).cuda()
+    ev = sampler.GradEvaluator(net, steps, op, y, x0)
+    smp = sampler.HMCSampler(x0, ev, 1.0, 0.05, sigma_0, mass=1.0, sched=_lib.SCHED_PIXEL, n_slots=20)
+    sch = osch.PixelSchedule(1.0, 0.05, sigma_0)
+    torch.manual_seed(int(g["seed"]))
+    n_saved = n_img = outliers = 0
+    for it in range(32):
+        xs = T(g["x_start"][it:it + 1])
+        p = torch.randn_like(xs)                      # CPU generator, the reference's draw order
+        u = torch.rand(1)
+        smp.x.copy_(xs)                               # teacher forcing: reset the state to the reference's
+        st = smp.chains.read()                        # and the schedule counters (a flipped decision would shift them)
+        st["epoch"], st["rejected"], st["epsilon"], st["tau"] = sch.epoch, sch.rejected, sch.epsilon, sch.tau
+        smp.chains.write(st)
+        sig, eps_now = sch.begin_iteration()
+        xc = smp.iteration(p.cuda(), u)
+        st = smp.chains.read()
+        assert abs(st["sigma_y"][0] - sig) < 1e-12 and st["epsilon"][0] == sch.epsilon
+        prob_ref = min(1.0, float(g["prob"][it])); prob = float(st["prob"][0]); acc = bool(g["accept"][it])
+        band = 0.02 * max(prob_ref, 1e-3) + 1e-6
+        if abs(prob - prob_ref) > band:
+            outliers += 1                             # clip-boundary flip inside the trajectory (see oracle test)
+        else:
+            if abs(float(u) - prob_ref) > band:
+                assert bool(st["accept"][0]) == acc, it
+            if acc:
+                img = ((xc[0].cpu() + 1) / 2).clamp(0, 1)
+                np.testing.assert_allclose(img.numpy(), g["saved"][n_saved], atol=1e-3)
+                n_img += 1
+        n_saved += acc
+        sch.end_iteration(acc)
+    assert outliers <= 3, outliers
+    assert n_img >= 5
+
+
+def test_hmc_free_running_completes_and_matches_schedule(golden):
+    """Drop-in call with the reference's signature; 100 accepts, 20 samples, schedule consistent."""
+    import nhmc_b200
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=float(g["sigma_0"]), algo="hmc", noise="ddpm")
+    algo = types.SimpleNamespace(model=net, cls_fn=None)
+    x = T(g["x_init"]).cuda(); y = T(g["y_0"]).cuda(); x_orig = T(g["x_orig"]).cuda()
+    torch.manual_seed(777)
+    log = []
+    out = nhmc_b200.hmc(x, 1, _betas().cuda(), SEQ, SEQ_NEXT, algo, opt, y, op, x_orig,
+                        on_iteration=lambda it, st, xc: log.append((int(st["epoch"][0]), int(st["accept"][0]), float(st["epsilon"][0]))))
+    assert out.shape == (20, 3, 32, 32) and torch.isfinite(out).all()
+    assert float(out.abs().max()) <= 1.0
+    assert log[-1][0] == 100 and sum(a for _, a, _ in log) == 100
+    # replay the accept sequence through the oracle's python state machine: same epsilon trajectory
+    sch = osch.PixelSchedule(1.0, 0.05, float(g["sigma_0"]))
+    for ep, a, eps_after in log:
+        sch.begin_iteration(); sch.end_iteration(bool(a))
+        assert sch.epoch == ep and sch.epsilon == eps_after
+    # posterior samples fit the measurement about as well as the reference's own samples do
+    kept = oop.H(out.cpu())
+    ref_res = float(((oop.H(T(g["samples"])) - T(g["y_0"])) ** 2).mean())
+    res = float(((kept - T(g["y_0"])) ** 2).mean())
+    assert res < 4 * ref_res + 1e-3, (res, ref_res)
+
+
+def test_hmc_batched_chains_equal_single_chains(golden):
+    """B chains in one batch == the same chains run alone (no cross-chain coupling)."""
+    from nhmc_b200 import _lib, sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
+    B = 3
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
+    ps = [torch.randn(B, 3, 32, 32, generator=gen) for _ in range(4)]
+    us = [torch.rand(B, generator=gen) for _ in range(4)]
+
+    def run(idx):
+        xs, ys = x[idx].cuda(), y[idx].cuda()
+        ev = sampler.GradEvaluator(net, steps, op, ys, xs)
+        smp = sampler.HMCSampler(xs, ev, 1.0, 0.05, 0.1, sched=_lib.SCHED_PIXEL)
+        for p, u in zip(ps, us):
+            smp.iteration(p[idx].cuda(), u[idx])
+        return smp.x.cpu(), smp.chains.read()
+
+    xb, stb = run(slice(0, B))
+    for b in range(B):
+        x1, st1 = run(slice(b, b + 1))
+        assert st1["accepted"][0] == stb["accepted"][b] and st1["epsilon"][0] == stb["epsilon"][b]
+        np.testing.assert_allclose(x1[0].numpy(), xb[b].numpy(), atol=1e-4)
+        np.testing.assert_allclose(st1["H"][0], stb["H"][b], rtol=1e-5)
+
+
+def test_no_cpu_fallback():
+    import nhmc_b200
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=0.1)
+    with pytest.raises(nhmc_b200.NhmcError):
+        nhmc_b200.hmc(torch.zeros(1, 3, 8, 8), 1, _betas(), SEQ, SEQ_NEXT, types.SimpleNamespace(model=None, cls_fn=None),
+                      opt, torch.zeros(1, 3), None, None)
