@@ -236,7 +236,7 @@ static int check_op(const nhmc_op* op) {
   NHMC_CHECK_ARG(op->channels > 0 && op->img_dim > 0, "bad operator geometry");
   switch (op->kind) {
     case NHMC_OP_INPAINT:
-      NHMC_CHECK_ARG(op->kept_pix && op->pix_to_kept && op->n_kept >= 0, "inpaint tables missing");
+      NHMC_CHECK_ARG(op->pix_to_kept && op->n_kept >= 0 && (op->n_kept == 0 || op->kept_pix), "inpaint tables missing");
       break;
     case NHMC_OP_SR:
       NHMC_CHECK_ARG(op->ratio > 0 && op->img_dim % op->ratio == 0, "ratio must divide img_dim");
@@ -285,7 +285,9 @@ extern "C" size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains) {
 extern "C" int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* workspace,
                                nhmc_stream_t stream) {
   if (int e = check_op(op)) return e;
-  NHMC_CHECK_ARG(x && y && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(x && n_chains > 0, "bad arguments");
+  if (nhmc_op_meas_size(op) == 0) return NHMC_OK;  // nothing is measured (all pixels dropped)
+  NHMC_CHECK_ARG(y, "null output");
   cudaStream_t st = (cudaStream_t)stream;
   const int C = op->channels, D = op->img_dim;
   const int64_t P = (int64_t)D * D;
@@ -366,7 +368,8 @@ extern "C" int nhmc_op_pinv(const nhmc_op* op, const float* y, float* out, int n
 extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out,
                                  double* loss, int n_chains, void* workspace, nhmc_stream_t stream) {
   if (int e = check_op(op)) return e;
-  NHMC_CHECK_ARG(x_hat && y && g && loss && workspace && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(x_hat && g && loss && workspace && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(y || nhmc_op_meas_size(op) == 0, "null measurement");
   NHMC_CHECK_ARG(aligned16(x_hat) && aligned16(g) && (!xc_out || aligned16(xc_out)), "pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const int C = op->channels, D = op->img_dim;
