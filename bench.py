@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- HMC leapfrog steps/s (chains x steps) at FFHQ-256, the metric of BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--deg sr4] [--chains 8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE leapfrog step for every chain resident on the GPU (main_sampling.py:706-713): position update,
+3-step DDIM map (3 U-Net forwards + fused epilogues), measurement loss + adjoint, full VJP (3 U-Net input-VJPs +
+fused epilogue backwards) and the momentum update.  Workload = BASELINE config[1]: FFHQ-256 sr4, 8 chains per
+GPU, random-init ffhq_10m-architecture U-Net (bf16, channels-last), synthetic measurements.  Chains are
+independent: at N GPUs every rank runs its own 8 chains (weak scaling), no collective in the timed loop.
+
+Rank 0 prints ONE JSON line (see DESIGN.md "Measurement" for every key).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "hmc_leapfrog_steps_per_sec"
+UNIT = "chain-steps/s"
+FFHQ = dict(image_size=256, num_channels=128, num_res_blocks=1, channel_mult="", learn_sigma=True, class_cond=False,
+            use_checkpoint=False, attention_resolutions=16, num_heads=4, num_head_channels=64, num_heads_upsample=-1,
+            use_scale_shift_norm=True, dropout=0.0, resblock_updown=True, use_fp16=False, use_new_attention_order=False)
+SEQ, SEQ_NEXT = [250, 500, 750], [-1, 250, 500]
+UNET_FWD_GFLOP = 387.9          # per 1x3x256x256 forward (SURVEY.md headline 4, FlopCounterMode on the reference)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | hdr | deblur_aniso | phase_retrieval")
+    ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", default=True)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), bf16=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
+    return dict(hbm=6650.0, bf16=1400.0, src="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# workload construction (synthetic FFHQ-256 measurements)
+# ----------------------------------------------------------------------------------------------------
+def make_operator(deg, device):
+    from nhmc_b200 import operators as P
+    if deg.startswith("sr"):
+        return P.SuperResolution(3, 256, int(deg[2:]), device)
+    if "inp" in deg:
+        torch.manual_seed(5678)
+        return P.Inpainting.random(3, 256, device)
+    if "hdr" in deg:
+        return P.HDR(3, 256, device)
+    if deg == "deblur_aniso":
+        return P.Deblurring2D(P.gaussian_taps(1.0), P.gaussian_taps(20.0), 3, 256, device)
+    if "phase" in deg:
+        return P.PhaseRetrievalOperator(2.0, device, 3, 256)
+    raise SystemExit("unknown --deg " + deg)
+
+
+def run_ours(args, rank, world, local_rank):
+    import nhmc_b200
+    from nhmc_b200 import _lib, kernels, sampler, schedule, unet
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    B, K, W = args.chains, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(1234)
+    model = unet.create_model(**FFHQ, dtype=dtype)
+    unet.randomize_zero_tensors(model, seed=1234)
+    model.prepare(dev)
+    op = make_operator(args.deg, dev)
+    gen = torch.Generator().manual_seed(5678 + rank)
+    x_orig = torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1
+    sigma_0 = 0.1                                                                 # --sigma_0 0.05, doubled
+    y = op.H(x_orig.to(dev))
+    y = y + sigma_0 * torch.randn(y.shape, generator=gen).to(dev)
+    x0 = torch.randn(B, 3, 256, 256, generator=gen)
+    betas = torch.from_numpy(schedule.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+    steps = schedule.ddim_steps(schedule.alpha_table(betas), SEQ, SEQ_NEXT)
+    ev = sampler.GradEvaluator(model, steps, op, y, x0.to(dev))
+    smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
+    kernels.begin_iteration(smp.chains, _lib.SCHED_PIXEL)                          # sigma_y for epoch 0
+    smp.p.copy_(torch.randn(B, 3, 256, 256, generator=gen).to(dev))
+    loss, ga, gb, _ = ev(smp.x)
+    kernels.leapfrog(_lib.LF_FIRST, smp.x, smp.x_prop, smp.p, ga, gb, loss, smp.chains, 1.0, smp.ws)
+
+    def step():
+        l_, a_, b_, _ = ev(smp.x_prop)
+        kernels.leapfrog(_lib.LF_MIDDLE, smp.x_prop, smp.x_prop, smp.p, a_, b_, l_, smp.chains, 1.0, smp.ws)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events, per-kernel events for our kernels ----
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.3)
+    launches0 = kernels.LAUNCHES
+    kernels.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = kernels.profile_stop()
+    launches = kernels.LAUNCHES - launches0
+    clk = clocks.stop()
+    finite = bool(torch.isfinite(smp.x_prop).all() and torch.isfinite(smp.p).all())
+
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+
+    # ---- end-to-end: the same step through the public API with HOST buffers ----
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(B, 3, 256, 256).pin_memory(); ph = torch.empty(B, 3, 256, 256).pin_memory()
+        xh.copy_(smp.x_prop); ph.copy_(smp.p)
+        for _ in range(2):
+            smp.leapfrog_step_host(xh, ph)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        Ke = max(2, min(K, 10))
+        t0.record()
+        for _ in range(Ke):
+            res = smp.leapfrog_step_host(xh, ph)
+        t1.record()
+        barrier()
+        ms_e = t0.elapsed_time(t1)
+        if dist is not None:
+            t = torch.tensor([ms_e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * B * Ke / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(2 * xh.numel() * 4),
+               "d2h_bytes_per_step": int(res["bytes"]), "steps": Ke, "ms_per_step": ms_e / Ke}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    value = world * B * K / (ms / 1e3)
+    # ---- roofline: our dominant kernel family inside the step (GroupNorm epilogue pair, HBM-bound) ----
+    kern = {}
+    for name, (n, tms, nbytes) in sorted(prof.items()):
+        kern[name] = {"calls_per_step": n / K, "ms_per_step": tms / K, "GBps": (nbytes / 1e9) / (tms / 1e3) if tms > 0 else None}
+    ours_ms = sum(v["ms_per_step"] for v in kern.values())
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roofline = None
+    if dom:
+        ach = kern[dom]["GBps"]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
+                    "note": "algorithmic bytes (x read + y written; backward: x, dy read + dx written) / CUDA-event time "
+                            "per call, averaged over the timed region"}
+    step_ms = ms / K
+    unet_tflop = B * 3 * 2 * UNET_FWD_GFLOP / 1e3                       # fwd + input-VJP ~ 2x fwd FLOPs, 3 timesteps
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 sampler state / %s score network" % args.dtype, "data": "synthetic",
+        "config": {"workload": "FFHQ-256 %s HMC, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, "
+                               "random-init ffhq_10m U-Net (BASELINE config[1])" % (args.deg, B),
+                   "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
+                   "parallelism": "chains sharded, dp%d, no collective in the loop" % world},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+        "roofline": roofline, "kernels": kern,
+        "non_unet_share": ours_ms / step_ms if step_ms > 0 else None,
+        "unet": {"algorithmic_tflop_per_step": unet_tflop, "achieved_tflops": unet_tflop / ((step_ms - ours_ms) / 1e3),
+                 "peak_tflops": pk["bf16"], "tensor_pipe_frac": unet_tflop / ((step_ms - ours_ms) / 1e3) / pk["bf16"],
+                 "note": "cuDNN/cuBLAS bf16 convolutions (PyTorch call), time = step - our kernels"},
+        "finite": finite,
+    }
+    if not args.no_cpu_baseline and world >= 1:
+        out["cpu_baseline"] = cpu_baseline(args.deg, steps_timed=1, warm=1)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference path, timed on the host cores
+# ----------------------------------------------------------------------------------------------------
+def _cpu_step_fn(deg):
+    """One leapfrog step of ONE chain at FFHQ-256 with the full ffhq_10m-architecture U-Net on CPU (fp32)."""
+    from oracle import hmc as ohmc, operators as oops, schedule as osch, unet as ounet
+    cfg = ounet.resolve_config(**FFHQ)
+    sd = ounet.seeded_state_dict(cfg, seed=1234)
+    model = lambda xx, tt: ounet.unet_forward(sd, cfg, xx, tt)
+    if deg.startswith("sr"):
+        op = oops.SuperResolution(3, 256, int(deg[2:]))
+    elif "inp" in deg:
+        torch.manual_seed(5678)
+        op = oops.Inpainting(3, 256, oops.random_inpaint_missing_pixels(256))
+    elif "hdr" in deg:
+        op = oops.HDR()
+    elif deg == "deblur_aniso":
+        op = oops.Deblurring2D.from_kernels(oops.gaussian_taps(1.0), oops.gaussian_taps(20.0), 3, 256)
+    else:
+        op = oops.PhaseRetrieval(2.0)
+    gen = torch.Generator().manual_seed(5678)
+    y = op.H(torch.rand(1, 3, 256, 256, generator=gen) * 2 - 1)
+    y = y + 0.1 * torch.randn(y.shape, generator=gen)
+    x = torch.randn(1, 3, 256, 256, generator=gen); p = torch.randn(1, 3, 256, 256, generator=gen)
+    tab = osch.alpha_bar_table(osch.beta_schedule("linear", 1e-4, 0.02, 1000))
+    eps_net = ohmc.module_eps_net(model)
+    state = {"x": x, "p": p}
+    sigma_y, eps = 0.1 + 1.6, 0.05
+
+    def step():
+        state["x"] = ohmc.drift(state["x"], state["p"], eps, 1.0)
+        _, _, g = ohmc.grad_eval(state["x"], eps_net, tab, SEQ, SEQ_NEXT, op, y)
+        state["p"] = ohmc.kick(state["p"], state["x"], g, sigma_y, eps)
+    return step
+
+
+def cpu_baseline(deg, steps_timed=1, warm=1):
+    step = _cpu_step_fn(deg)
+    cores = torch.get_num_threads()
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps_timed):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": steps_timed / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 chain x %d leapfrog step(s) of the same workload (FFHQ-256 %s, full ffhq_10m U-Net, fp32) after %d warm-up; "
+                      "oracle restatement of main_sampling.py:706-713 on torch CPU" % (steps_timed, deg, warm),
+            "ms_per_step": dt / steps_timed * 1e3}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is Python and
+    cannot travel to the GPU box), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    step = _cpu_step_fn(args.deg)
+    cores = torch.get_num_threads()
+    budget_s = 240.0
+    t0 = time.perf_counter()
+    step()
+    first = time.perf_counter() - t0
+    W_run = max(0, min(W, 1) - 1)            # the probe above is the warm-up
+    for _ in range(W_run):
+        step()
+    K_run = max(1, min(K, int(max(1.0, (budget_s - first * (1 + W_run)) / max(first, 1e-3)))))
+    t0 = time.perf_counter()
+    for _ in range(K_run):
+        step()
+    dt = time.perf_counter() - t0
+    v = K_run / dt
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": world, "steps": K_run, "warmup": 1 + W_run,
+           "ms_per_step": dt / K_run * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "FFHQ-256 %s HMC, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, random-init ffhq_10m U-Net "
+                                  "(BASELINE config[1]); bounded sample: 1 chain x 1 leapfrog step per step" % args.deg,
+                      "deg": args.deg},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "1 chain x 1 leapfrog step per step, %d timed steps (requested %d, capped by a %.0f s budget)" % (K_run, K, budget_s)},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (sm_100a); there is no CPU fallback")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -6,6 +6,49 @@ from ._lib import check, lib
 
 _DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
 
+# ---- launch accounting / optional per-kernel timing (bench.py) -------------------------------------
+LAUNCHES = 0          # kernels of libnhmc.so launched so far (python-side count of the C calls' launches)
+_PROFILE = None       # when a dict: name -> list of (start_event, end_event, algorithmic_bytes)
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = {}
+
+
+def profile_stop():
+    """Returns {name: (n_calls, total_ms, total_algorithmic_bytes)} (synchronises)."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, recs in (prof or {}).items():
+        ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        out[name] = (len(recs), ms, sum(b for _, _, b in recs))
+    return out
+
+
+class _timed:
+    """Counts launches; with profiling on, brackets the call with CUDA events on the launching stream."""
+
+    def __init__(self, name, n_launches, nbytes):
+        self.name, self.n, self.nbytes = name, n_launches, nbytes
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.n
+        if _PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.e.record()
+            _PROFILE.setdefault(self.name, []).append((self.s, self.e, self.nbytes))
+        return False
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -31,7 +74,8 @@ def zeros_workspace(nbytes, device):
 
 
 def begin_iteration(chains, sched):
-    check(lib().nhmc_begin_iteration(chains.ptr(), chains.n, sched, _stream()), "nhmc_begin_iteration")
+    with _timed("begin_iteration", 1, chains.n * 144 * 2):
+        check(lib().nhmc_begin_iteration(chains.ptr(), chains.n, sched, _stream()), "nhmc_begin_iteration")
 
 
 def leapfrog_workspace(n_chains, device):
@@ -45,8 +89,10 @@ def leapfrog(mode, x_in, x_out, p, g_a, g_b, loss, chains, mass, ws):
     if x_out is not None: _req(x_out, torch.float32, "x_out")
     if g_b is not None: _req(g_b, torch.float32, "g_b")
     if loss is not None: _req(loss, torch.float64, "loss")
-    check(lib().nhmc_leapfrog(mode, _p(x_in), _p(x_out), _p(p), _p(g_a), _p(g_b), _p(loss), chains.ptr(),
-                              float(mass), B, N, _p(ws), _stream()), "nhmc_leapfrog")
+    nb = B * N * 4 * ((3 if mode == _lib.LF_LAST else 5) + (1 if g_b is not None else 0))
+    with _timed("leapfrog", 1, nb):
+        check(lib().nhmc_leapfrog(mode, _p(x_in), _p(x_out), _p(p), _p(g_a), _p(g_b), _p(loss), chains.ptr(),
+                                  float(mass), B, N, _p(ws), _stream()), "nhmc_leapfrog")
 
 
 def ddim_mask_words(n_per_chain):
@@ -59,8 +105,9 @@ def ddim_fwd(xt, eps, xt_next, mask, coef):
     N = xt[0].numel()
     _req(xt, torch.float32, "xt"); _req(xt_next, torch.float32, "xt_next"); _req(eps, None, "eps")
     c1, sa, c2, ss = coef
-    check(lib().nhmc_ddim_fwd(_p(xt), _p(eps), _DT[eps.dtype], eps[0].numel(), _p(xt_next), _p(mask),
-                              c1, sa, c2, ss, B, N, _stream()), "nhmc_ddim_fwd")
+    with _timed("ddim_fwd", 1, B * N * (8 + eps.element_size()) + B * N // 8):
+        check(lib().nhmc_ddim_fwd(_p(xt), _p(eps), _DT[eps.dtype], eps[0].numel(), _p(xt_next), _p(mask),
+                                  c1, sa, c2, ss, B, N, _stream()), "nhmc_ddim_fwd")
 
 
 def ddim_bwd(g_a, g_b, mask, g_xt, g_eps, coef):
@@ -73,49 +120,57 @@ def ddim_bwd(g_a, g_b, mask, g_xt, g_eps, coef):
         _req(g_eps, None, "g_eps")
         dt, stride = _DT[g_eps.dtype], g_eps[0].numel()
     c1, sa, c2, ss = coef
-    check(lib().nhmc_ddim_bwd(_p(g_a), _p(g_b), _p(mask), _p(g_xt), _p(g_eps), dt, stride, c1, sa, c2, ss, B, N,
-                              _stream()), "nhmc_ddim_bwd")
+    nb = B * N * (8 + (4 if g_b is not None else 0) + (g_eps.element_size() if g_eps is not None else 0)) + B * N // 8
+    with _timed("ddim_bwd", 1, nb):
+        check(lib().nhmc_ddim_bwd(_p(g_a), _p(g_b), _p(mask), _p(g_xt), _p(g_eps), dt, stride, c1, sa, c2, ss, B, N,
+                                  _stream()), "nhmc_ddim_bwd")
 
 
 def accept(chains, u, mass, sched, n_slots):
     _req(u, torch.float32, "u")
-    check(lib().nhmc_accept(chains.ptr(), _p(u), float(mass), sched, n_slots, chains.n, _stream()), "nhmc_accept")
+    with _timed("accept", 1, chains.n * 144 * 2):
+        check(lib().nhmc_accept(chains.ptr(), _p(u), float(mass), sched, n_slots, chains.n, _stream()), "nhmc_accept")
 
 
 def commit(chains, x, x_prop, x_hat, x_keep, samples, sched, n_slots):
     N = x[0].numel()
     for t, n in ((x, "x"), (x_prop, "x_prop"), (x_hat, "x_hat")):
         _req(t, torch.float32, n)
-    check(lib().nhmc_commit(chains.ptr(), _p(x), _p(x_prop), _p(x_hat), _p(x_keep), _p(samples), sched, n_slots,
-                            chains.n, N, _stream()), "nhmc_commit")
+    with _timed("commit", 1, chains.n * N * 4 * 4):
+        check(lib().nhmc_commit(chains.ptr(), _p(x), _p(x_prop), _p(x_hat), _p(x_keep), _p(samples), sched, n_slots,
+                                chains.n, N, _stream()), "nhmc_commit")
 
 
 def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last):
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
-    check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
-                            _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), B, Cc, hw, groups, float(eps),
-                            _stream()), "nhmc_gn_fwd")
+    with _timed("gn_fwd", 2 if channels_last else 1, 2 * x.numel() * x.element_size()):
+        check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
+                                _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), B, Cc, hw, groups, float(eps),
+                                _stream()), "nhmc_gn_fwd")
 
 
 def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last):
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
-    check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
-                            _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), 0, 0, B, Cc, hw, groups,
-                            _stream()), "nhmc_gn_bwd")
+    with _timed("gn_bwd", 2 if channels_last else 1, 3 * x.numel() * x.element_size()):
+        check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
+                                _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), 0, 0, B, Cc, hw, groups,
+                                _stream()), "nhmc_gn_bwd")
 
 
 def softmax_fwd(logits, probs, scale):
     cols = logits.shape[-1]
     rows = logits.numel() // cols
-    check(lib().nhmc_softmax_fwd(_DT[logits.dtype], _p(logits), _p(probs), float(scale), rows, cols, _stream()),
-          "nhmc_softmax_fwd")
+    with _timed("softmax_fwd", 1, 2 * logits.numel() * logits.element_size()):
+        check(lib().nhmc_softmax_fwd(_DT[logits.dtype], _p(logits), _p(probs), float(scale), rows, cols, _stream()),
+              "nhmc_softmax_fwd")
 
 
 def softmax_bwd(probs, dprobs, dlogits, scale):
     cols = probs.shape[-1]
     rows = probs.numel() // cols
-    check(lib().nhmc_softmax_bwd(_DT[probs.dtype], _p(probs), _p(dprobs), _p(dlogits), float(scale), rows, cols,
-                                 _stream()), "nhmc_softmax_bwd")
+    with _timed("softmax_bwd", 1, 3 * probs.numel() * probs.element_size()):
+        check(lib().nhmc_softmax_bwd(_DT[probs.dtype], _p(probs), _p(dprobs), _p(dlogits), float(scale), rows, cols,
+                                     _stream()), "nhmc_softmax_bwd")

@@ -18,6 +18,7 @@ from ._lib import OpDesc, check, lib
 class Operator:
     kind = None
     linear = True
+    loss_grad_launches = 1     # kernels launched by one nhmc_op_loss_grad call
 
     def __init__(self, channels, img_dim, device):
         self.channels, self.img_dim = int(channels), int(img_dim)
@@ -88,9 +89,11 @@ class Operator:
         g = torch.empty_like(x_hat) if g is None else g
         xc = torch.empty_like(x_hat) if xc is None else xc
         loss = torch.empty(B, dtype=torch.float64, device=x_hat.device) if loss is None else loss
-        check(lib().nhmc_op_loss_grad(ctypes.byref(self.desc), x_hat.data_ptr(), y.data_ptr(), g.data_ptr(),
-                                      xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
-                                      kernels._stream()), "nhmc_op_loss_grad")
+        nb = (3 * x_hat.numel() + y.numel()) * 4          # read x_hat + y, write g + clamped image
+        with kernels._timed("op_loss_grad_" + type(self).__name__, self.loss_grad_launches, nb):
+            check(lib().nhmc_op_loss_grad(ctypes.byref(self.desc), x_hat.data_ptr(), y.data_ptr(), g.data_ptr(),
+                                          xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
+                                          kernels._stream()), "nhmc_op_loss_grad")
         return loss, g, xc
 
 
@@ -177,6 +180,7 @@ def gaussian_taps(sigma, half=4):
 class Deblurring2D(Operator):
     """Y_c = U1 (G_c .* (V1^T X_c V2)) U2^T (Hfuncs.py:448-523, tiled-singulars quirk included)."""
     kind = _lib.OP_DEBLUR2D
+    loss_grad_launches = 9
 
     def __init__(self, kernel1, kernel2, channels, img_dim, device, tables=None, zero=3e-2):
         super().__init__(channels, img_dim, device)

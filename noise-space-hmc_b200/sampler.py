@@ -150,6 +150,20 @@ class HMCSampler:
         kernels.commit(ch, self.x, self.x_prop, xc, self.x_keep, self.samples, self.sched, self.n_slots)
         return xc
 
+    def leapfrog_step_host(self, x_host, p_host):
+        """One leapfrog step (main_sampling.py:706-713) on HOST buffers: position and momentum come from
+        (pinned) host memory, the step runs on the device, the per-chain loss and the updated (x, p) go back.
+        Used for end-to-end timing; returns {"loss": [B] float64 (host), "bytes": D2H bytes}."""
+        self.x_prop.copy_(x_host, non_blocking=True)
+        self.p.copy_(p_host, non_blocking=True)
+        loss, g_a, g_b, _ = self.ev(self.x_prop)
+        kernels.leapfrog(_lib.LF_MIDDLE, self.x_prop, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass,
+                         self.ws)
+        x_host.copy_(self.x_prop, non_blocking=True)
+        p_host.copy_(self.p, non_blocking=True)
+        loss_h = loss.cpu()                       # synchronises: the step's result is on the host
+        return {"loss": loss_h, "bytes": 2 * x_host.numel() * 4 + loss_h.numel() * 8}
+
     def collected(self):
         """[B, S, ...] samples in collection order (S = min(n_collected, n_slots), same for all finished chains)."""
         st = self.chains.read()

@@ -1,0 +1,144 @@
+"""GPU parity of the U-Net epilogue kernels (K9/K10) and of the U-Net module built on them."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet as ounet
+
+T = torch.from_numpy
+SMALL = dict(image_size=64, num_channels=32, num_res_blocks=1, channel_mult="", learn_sigma=True,
+             attention_resolutions=16, num_heads=4, num_head_channels=16, use_scale_shift_norm=True,
+             resblock_updown=True)
+
+
+def _gn_ref(x, gamma, beta, scale, shift, mode):
+    """fp32 torch reference of the three epilogue variants (nn.py:17-19, unet_ffhq.py:319-323)."""
+    h = F.group_norm(x.float(), 32, gamma, beta, 1e-5)
+    if mode == 2:
+        h = h * (1 + scale[:, :, None, None]) + shift[:, :, None, None]
+    return h if mode == 0 else F.silu(h)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", [(2, 128, 16, 16), (3, 384, 8, 8), (1, 256, 64, 64), (2, 96, 5, 7)])
+def test_group_norm_epilogue(dtype, cl, mode, shape):
+    from nhmc_b200 import kernels
+    B, C, H, W = shape
+    if cl and C % (4 if dtype == torch.float32 else 8):
+        pytest.skip("channels-last path needs C % vec == 0")
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(shape, generator=g) * 1.7 + 0.4).cuda().to(dtype)
+    dy = torch.randn(shape, generator=g).cuda().to(dtype)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).cuda(); beta = (0.1 * torch.randn(C, generator=g)).cuda()
+    scale = (0.3 * torch.randn(B, C, generator=g)).cuda(); shift = (0.3 * torch.randn(B, C, generator=g)).cuda()
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last); dy = dy.contiguous(memory_format=torch.channels_last)
+    xr = x.float().detach().clone().requires_grad_(True)
+    yr = _gn_ref(xr, gamma, beta, scale, shift, mode)
+    (dxr,) = torch.autograd.grad(yr, xr, dy.float())
+    y = torch.empty_like(x); dx = torch.empty_like(x)
+    stats = torch.empty(B, 32, 2, device="cuda")
+    sc, sh = (scale, shift) if mode == 2 else (None, None)
+    kernels.gn_fwd(mode, x, y, gamma, beta, sc, sh, stats, 32, 1e-5, cl)
+    kernels.gn_bwd(mode, x, dy, dx, gamma, beta, sc, sh, stats, 32, cl)
+    torch.cuda.synchronize()
+    xs = x.float().reshape(B, 32, -1) if not cl else x.float().permute(0, 2, 3, 1).reshape(B, H * W, 32, C // 32).permute(0, 2, 1, 3).reshape(B, 32, -1)
+    np.testing.assert_allclose(stats[:, :, 0].cpu().numpy(), xs.mean(-1).cpu().numpy(), atol=2e-5)
+    np.testing.assert_allclose(stats[:, :, 1].cpu().numpy(), (xs.var(-1, unbiased=False) + 1e-5).rsqrt().cpu().numpy(), rtol=2e-5)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(y.cpu().numpy(), yr.detach().cpu().numpy(), atol=2e-5, rtol=2e-5)
+        np.testing.assert_allclose(dx.cpu().numpy(), dxr.cpu().numpy(), atol=5e-5 * float(dxr.abs().max()), rtol=1e-4)
+    else:   # bf16 output rounding: 2^-8 relative
+        np.testing.assert_allclose(y.float().cpu().numpy(), yr.detach().cpu().numpy(), atol=2e-2, rtol=1e-2)
+        np.testing.assert_allclose(dx.float().cpu().numpy(), dxr.cpu().numpy(), atol=2e-2 * float(dxr.abs().max()), rtol=2e-2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols", [(64, 256), (37, 64), (8, 1024), (5, 4096), (3, 100)])
+def test_softmax_epilogue(dtype, rows, cols):
+    from nhmc_b200 import kernels
+    g = torch.Generator().manual_seed(2)
+    logits = (torch.randn(rows, cols, generator=g) * 3).cuda().to(dtype)
+    dp = torch.randn(rows, cols, generator=g).cuda().to(dtype)
+    scale = 1 / math.sqrt(64)
+    lr = logits.float().detach().clone().requires_grad_(True)
+    pr = torch.softmax(lr * scale, dim=-1)
+    (dlr,) = torch.autograd.grad(pr, lr, dp.float())
+    p = torch.empty_like(logits); dl = torch.empty_like(logits)
+    kernels.softmax_fwd(logits, p, scale)
+    kernels.softmax_bwd(p, dp, dl, scale)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(p.cpu().numpy(), pr.detach().cpu().numpy(), atol=1e-6, rtol=2e-5)
+        np.testing.assert_allclose(dl.cpu().numpy(), dlr.cpu().numpy(), atol=1e-6, rtol=1e-4)
+    else:
+        np.testing.assert_allclose(p.float().cpu().numpy(), pr.detach().cpu().numpy(), atol=4e-3, rtol=1e-2)
+    assert abs(float(p.float().sum(-1).mean()) - 1.0) < 5e-3
+
+
+def _small_model(dtype):
+    from nhmc_b200 import unet
+    m = unet.create_model(**SMALL, dtype=dtype)
+    cfg = ounet.resolve_config(**SMALL)
+    sd = ounet.seeded_state_dict(cfg, seed=1234)
+    assert list(m.state_dict()) == list(sd)
+    m.load_state_dict(sd)
+    return m.prepare("cuda"), sd, cfg
+
+
+def test_unet_fp32_matches_reference_output(golden):
+    """Our U-Net on the fused kernels vs the output of the reference's own UNetModel (golden) and the oracle."""
+    g = golden("unet_small.npz")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd, cfg = _small_model(torch.float32)
+    x = T(g["x"]).cuda().requires_grad_(True)
+    out = m(x, T(g["t"]).cuda())
+    np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=1e-4)
+    (gx,) = torch.autograd.grad(out, x, T(g["w"]).cuda())
+    np.testing.assert_allclose(gx.cpu().numpy(), g["grad_x"], atol=5e-5 * max(1.0, float(np.abs(g["grad_x"]).max())), rtol=1e-3)
+
+
+def test_unet_bf16_close_to_fp32(golden):
+    g = golden("unet_small.npz")
+    m, sd, cfg = _small_model(torch.bfloat16)
+    x = T(g["x"]).cuda().requires_grad_(True)
+    out = m(x, T(g["t"]).cuda())
+    assert out.dtype == torch.bfloat16
+    ref = g["out"]
+    err = np.abs(out.detach().float().cpu().numpy() - ref).max() / np.abs(ref).max()
+    assert err < 0.05, err
+    (gx,) = torch.autograd.grad(out, x, T(g["w"]).cuda().to(torch.bfloat16))
+    gerr = np.abs(gx.float().cpu().numpy() - g["grad_x"]).max() / np.abs(g["grad_x"]).max()
+    assert gx.dtype == torch.float32 and gerr < 0.08, gerr
+
+
+def test_hmc_with_own_unet_small(golden):
+    """End-to-end: one gradient evaluation with our U-Net (fp32) vs the oracle running its functional U-Net on CPU."""
+    from nhmc_b200 import _lib, operators as P, sampler, schedule
+    from oracle import hmc as ohmc, operators as oops, schedule as osch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd, cfg = _small_model(torch.float32)
+    D, seq, seq_next = 64, [250, 500, 750], [-1, 250, 500]
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 3, D, D, generator=gen)
+    oop = oops.SuperResolution(3, D, 4)
+    y = oop.H(torch.rand(1, 3, D, D, generator=gen) * 2 - 1) + 0.1 * torch.randn(1, 3 * 16 * 16, generator=gen)
+    betas = T(osch.beta_schedule("linear", 1e-4, 0.02, 1000)).float()
+    steps = schedule.ddim_steps(schedule.alpha_table(betas), seq, seq_next)
+    op = P.SuperResolution(3, D, 4, "cuda")
+    ev = sampler.GradEvaluator(m, steps, op, y.cuda(), x.cuda())
+    loss, ga, gb, xc = ev(x.cuda())
+    omodel = lambda xx, tt: ounet.unet_forward(sd, cfg, xx, tt)
+    tab = osch.alpha_bar_table(osch.beta_schedule("linear", 1e-4, 0.02, 1000))
+    xh, oloss, og = ohmc.grad_eval(x, ohmc.module_eps_net(omodel), tab, seq, seq_next, oop, y)
+    np.testing.assert_allclose(xc.cpu().numpy(), xh.numpy(), atol=1e-3)                  # north-star tolerance
+    np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=1e-3)
+    np.testing.assert_allclose((ga + gb).cpu().numpy(), og.numpy(), atol=2e-3 * float(og.abs().max()))
