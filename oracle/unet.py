@@ -236,4 +236,4 @@ def seeded_state_dict(cfg, seed=1234, std=0.02):
         w = torch.randn(shapes[k], generator=g) * std
         is_norm = (k.endswith(".weight") and len(shapes[k]) == 1)
         sd[k] = (1.0 + w) if is_norm else w
-    return sd
+    return {k: sd[k] for k in shapes}      # values drawn in sorted-key order, dict in registration order

@@ -147,10 +147,11 @@ def _ops_from_golden(g, D=32):
     }
     tabs = [T(g["deblur_tab_" + k]) for k in ("U_small1", "V_small1", "U_small2", "V_small2", "singulars", "perm")]
     pairs["deblur"] = (P.Deblurring2D(None, None, 3, D, "cuda", tables=tabs), oops.Deblurring2D(3, D, *tabs))
+    pairs["phase"] = (P.PhaseRetrievalOperator(2.0, "cuda", 3, D), oops.PhaseRetrieval(2.0))      # L = 160 = 5 * 32
     return pairs
 
 
-@pytest.mark.parametrize("name", ["inp", "sr4", "sr16", "sr2", "hdr", "deblur"])
+@pytest.mark.parametrize("name", ["inp", "sr4", "sr16", "sr2", "hdr", "deblur", "phase"])
 def test_operator_vs_golden_and_oracle(nb, golden, name):
     g = golden("operators.npz")
     op, oop = _ops_from_golden(g)[name]
@@ -164,6 +165,14 @@ def test_operator_vs_golden_and_oracle(nb, golden, name):
     torch.cuda.synchronize()
     assert torch.equal(xc.cpu(), x.clamp(-1, 1))
     np.testing.assert_allclose(loss.sum().item(), float(g[name + "_loss"]), rtol=2e-5)
+    if name == "phase":
+        pinv = op.H_pinv(dev(y)).cpu()
+        np.testing.assert_allclose(pinv.numpy(), g["phase_pinv"], atol=2e-5, rtol=1e-4)
+        _, oloss = oop.residual(x, y)
+        np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=2e-5)
+        scale = float(np.abs(g["phase_grad"]).max())
+        np.testing.assert_allclose(grad.cpu().numpy(), g["phase_grad"], atol=5e-5 * scale, rtol=1e-4)
+        return
     _, oloss = oop.residual(x, y)
     np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=1e-12 if exact else 2e-5)
     scale = max(1.0, float(np.abs(g[name + "_grad"]).max()))
@@ -180,7 +189,7 @@ def test_operator_vs_golden_and_oracle(nb, golden, name):
         assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
 
 
-@pytest.mark.parametrize("kind", ["inp", "sr4", "sr16", "hdr", "deblur"])
+@pytest.mark.parametrize("kind", ["inp", "sr4", "sr16", "hdr", "deblur", "phase"])
 def test_operator_full_size(nb, kind):
     """FFHQ-256 shapes (BASELINE configs 1-3), B = 2 chains: loss/gradient against the oracle + properties."""
     from nhmc_b200 import operators as P
@@ -196,6 +205,9 @@ def test_operator_full_size(nb, kind):
         r = int(kind[2:]); op = P.SuperResolution(3, D, r, "cuda"); oop = oops.SuperResolution(3, D, r)
     elif kind == "hdr":
         op = P.HDR(3, D, "cuda"); oop = oops.HDR()
+    elif kind == "phase":
+        op = P.PhaseRetrievalOperator(2.0, "cuda", 3, D); oop = oops.PhaseRetrieval(2.0)      # L = 384 = 3 * 128
+        assert op.meas_shape(B) == (B, 3, 384, 384)
     else:
         op = P.Deblurring2D(P.gaussian_taps(1.0), P.gaussian_taps(20.0), 3, D, "cuda")
         assert int((op.gain != 0).sum()) == 3 * 49486
