@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", default=True)
+    ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
+    ap.add_argument("--cuda-profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -183,11 +185,15 @@ def run_ours(args, rank, world, local_rank):
     kernels.profile_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(K):
         step()
     e1.record()
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     prof = kernels.profile_stop()
     launches = kernels.LAUNCHES - launches0
@@ -201,6 +207,14 @@ def run_ours(args, rank, world, local_rank):
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
+
+    if args.torch_profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof_t:
+            step()
+            torch.cuda.synchronize()
+        with open(args.torch_profile, "w") as f:
+            f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
 
     # ---- end-to-end: the same step through the public API with HOST buffers ----
     e2e = None

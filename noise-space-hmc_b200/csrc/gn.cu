@@ -160,39 +160,16 @@ gn_nhwc_stats_kernel(GnArgs a) {
 #pragma unroll
   for (int i = 0; i < V; ++i) { sm0[(size_t)prow * a.C + c0 + i] = s0[i]; sm1[(size_t)prow * a.C + c0 + i] = s1[i]; }
   __syncthreads();
-  double* part = a.partials + ((int64_t)b * kGnMaxBlocks + blk) * a.G * 2;
+  // one fp64 atomic pair per (CTA, group): no serial tail, no partial-sum array.  The accumulators are
+  // zero on entry (scratch is zeroed at allocation; the apply kernel re-zeroes them after its last read).
   for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
     double t0 = 0.0, t1 = 0.0;
     for (int c = g * Cg; c < (g + 1) * Cg; ++c)
       for (int r = 0; r < rows; ++r) { t0 += (double)sm0[(size_t)r * a.C + c]; t1 += (double)sm1[(size_t)r * a.C + c]; }
-    part[g * 2] = t0; part[g * 2 + 1] = t1;
+    atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
+    atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
   }
-  __shared__ bool is_last;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    is_last = atomicInc(a.tickets + b, (unsigned int)(nblk - 1)) == (unsigned int)(nblk - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const double n = (double)Cg * (double)a.HW;
-  for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
-    double t0 = 0.0, t1 = 0.0;
-    for (int k = 0; k < nblk; ++k) {
-      const double* p = a.partials + ((int64_t)b * kGnMaxBlocks + k) * a.G * 2 + g * 2;
-      t0 += __ldcg(p); t1 += __ldcg(p + 1);
-    }
-    if (PHASE == 0) {
-      const double mean = t0 / n;
-      double var = t1 / n - mean * mean; if (var < 0.0) var = 0.0;
-      a.stats[((int64_t)b * a.G + g) * 2] = (float)mean;
-      a.stats[((int64_t)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
-    } else {
-      a.bstats[((int64_t)b * a.G + g) * 2] = (float)(t0 / n);
-      a.bstats[((int64_t)b * a.G + g) * 2 + 1] = (float)(t1 / n);
-    }
-  }
+  (void)nblk; (void)blk;
 }
 
 // PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
@@ -209,10 +186,19 @@ gn_nhwc_apply_kernel(GnArgs a) {
   const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + (int64_t)b * a.HW * a.C : nullptr;
   T* ob = reinterpret_cast<T*>(a.out) + (int64_t)b * a.HW * a.C;
   float ca[V], cb[V], k1[V], k2[V], k3[V];
+  const double n = (double)Cg * (double)a.HW;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = c0 + i, g = c / Cg;
-    const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+    const double a0 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2), a1 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
+    float mean, rstd;
+    if (PHASE == 0) {
+      const double mu = a0 / n;
+      double var = a1 / n - mu * mu; if (var < 0.0) var = 0.0;
+      mean = (float)mu; rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    } else {
+      mean = a.stats[((int64_t)b * a.G + g) * 2]; rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+    }
     const float gam = a.gamma[c], bet = a.beta[c];
     const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
     const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
@@ -222,10 +208,31 @@ gn_nhwc_apply_kernel(GnArgs a) {
     if (PHASE == 1) {
       // dx = rstd*(du - m1 - u*m2), du = dy*act'(z)*gamma*(1+s), u = (x-mean)*rstd
       //    = k1*dy*act'(z) + k2*x + k3
-      const float m1 = a.bstats[((int64_t)b * a.G + g) * 2], m2 = a.bstats[((int64_t)b * a.G + g) * 2 + 1];
+      const float m1 = (float)(a0 / n), m2 = (float)(a1 / n);
       k1[i] = rstd * gam * sc;
       k2[i] = -rstd * rstd * m2;
       k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
+    }
+  }
+  // every CTA has now read the accumulators it needs; the last one to get here publishes (mean, rstd)
+  // for the backward pass and re-zeroes the accumulators for the next call on this stream.
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = atomicInc(a.tickets + b, (unsigned int)(gridDim.x - 1)) == (unsigned int)(gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
+      double* acc = a.partials + ((int64_t)b * 64 + g) * 2;
+      if (PHASE == 0) {
+        const double mu = __ldcg(acc) / n;
+        double var = __ldcg(acc + 1) / n - mu * mu; if (var < 0.0) var = 0.0;
+        a.stats[((int64_t)b * a.G + g) * 2] = (float)mu;
+        a.stats[((int64_t)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+      }
+      acc[0] = 0.0; acc[1] = 0.0;
     }
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
@@ -334,7 +341,8 @@ static int get_scratch(int batch, int G, GnScratch& out) {
     // grow-only; allocation happens outside any stream capture (first call) -- warm up before capturing
     if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); }
     const int nb = batch < 64 ? 64 : batch;
-    if (int e = cuda_status(cudaMalloc(&s.partials, (size_t)nb * kGnMaxBlocks * 64 * 2 * sizeof(double)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMalloc(&s.partials, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMemset(s.partials, 0, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMalloc(&s.tickets, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMalloc(&s.bstats, (size_t)nb * 64 * 2 * sizeof(float)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMemset(s.tickets, 0, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
@@ -352,17 +360,14 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
   int rows = 256 / cvec; if (rows < 1) rows = 1;
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
-  // chunking: ~64 KiB of input per CTA, at most kGnMaxBlocks CTAs per sample
+  // chunking: aim at ~8 CTAs per SM over the whole batch, between 16 KiB and 128 KiB of input per CTA
   const int64_t bytes_per_row = (int64_t)a.C * sizeof(T);
-  int64_t rows_per_cta = (65536 + bytes_per_row - 1) / bytes_per_row;
+  int64_t target = (int64_t)batch * a.HW * bytes_per_row / (kSMs * 8);
+  if (target < 16384) target = 16384;
+  if (target > 131072) target = 131072;
+  int64_t rows_per_cta = (target + bytes_per_row - 1) / bytes_per_row;
   rows_per_cta = ((rows_per_cta + rows - 1) / rows) * rows;
   int64_t nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
-  if (nblk > kGnMaxBlocks) {
-    nblk = kGnMaxBlocks;
-    rows_per_cta = (a.HW + nblk - 1) / nblk;
-    rows_per_cta = ((rows_per_cta + rows - 1) / rows) * rows;
-    nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
-  }
   a.rows_per_cta = rows_per_cta;
   a.rows_per_cta_iter = rows;
   const dim3 grid((unsigned)nblk, batch);
