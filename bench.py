@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-kernels", action="store_true", default=True)
+    ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
     ap.add_argument("--cuda-profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -155,12 +156,13 @@ def run_ours(args, rank, world, local_rank):
     smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
     kernels.begin_iteration(smp.chains, _lib.SCHED_PIXEL)                          # sigma_y for epoch 0
     smp.p.copy_(torch.randn(B, 3, 256, 256, generator=gen).to(dev))
-    loss, ga, gb, _ = ev(smp.x)
-    kernels.leapfrog(_lib.LF_FIRST, smp.x, smp.x_prop, smp.p, ga, gb, loss, smp.chains, 1.0, smp.ws)
+    smp.step(_lib.LF_FIRST)
+    use_graphs = not args.no_graphs
+    if use_graphs:
+        smp.capture_graphs()
 
     def step():
-        l_, a_, b_, _ = ev(smp.x_prop)
-        kernels.leapfrog(_lib.LF_MIDDLE, smp.x_prop, smp.x_prop, smp.p, a_, b_, l_, smp.chains, 1.0, smp.ws)
+        smp.step(_lib.LF_MIDDLE)
 
     dist = None
     if world > 1:
@@ -182,7 +184,8 @@ def run_ours(args, rank, world, local_rank):
     clocks.start()
     time.sleep(0.3)
     launches0 = kernels.LAUNCHES
-    kernels.profile_start()
+    if not use_graphs:
+        kernels.profile_start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if args.cuda_profiler_range:
@@ -195,9 +198,20 @@ def run_ours(args, rank, world, local_rank):
     if args.cuda_profiler_range:
         torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
-    prof = kernels.profile_stop()
     launches = kernels.LAUNCHES - launches0
     clk = clocks.stop()
+    if use_graphs:
+        # per-kernel CUDA events cannot be recorded inside a replayed graph: time our kernels in an eager pass of
+        # the same K steps right after the timed region (same buffers, same launch sequence)
+        graphs, smp._graphs = smp._graphs, None
+        step(); torch.cuda.synchronize()
+        kernels.profile_start()
+        for _ in range(K):
+            step()
+        prof = kernels.profile_stop()
+        smp._graphs = graphs
+    else:
+        prof = kernels.profile_stop()
     finite = bool(torch.isfinite(smp.x_prop).all() and torch.isfinite(smp.p).all())
 
     if dist is not None:
@@ -257,7 +271,7 @@ def run_ours(args, rank, world, local_rank):
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
                     "note": "algorithmic bytes (x read + y written; backward: x, dy read + dx written) / CUDA-event time "
-                            "per call, averaged over the timed region"}
+                            "per call, averaged over K steps" + (" (eager pass after the graph-replayed timed region)" if use_graphs else " of the timed region")}
     step_ms = ms / K
     unet_tflop = B * 3 * 2 * UNET_FWD_GFLOP / 1e3                       # fwd + input-VJP ~ 2x fwd FLOPs, 3 timesteps
     out = {
@@ -267,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": "FFHQ-256 %s HMC, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, "
                                "random-init ffhq_10m U-Net (BASELINE config[1])" % (args.deg, B),
                    "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
-                   "parallelism": "chains sharded, dp%d, no collective in the loop" % world},
+                   "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
         "roofline": roofline, "kernels": kern,
         "non_unet_share": ours_ms / step_ms if step_ms > 0 else None,

@@ -228,6 +228,22 @@ int nhmc_softmax_fwd(int dtype, const void* logits, void* probs, float scale, in
 int nhmc_softmax_bwd(int dtype, const void* probs, const void* dprobs, void* dlogits, float scale,
                      int64_t rows, int cols, nhmc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * U-Net resampling / skip-concat epilogues, channels-last [B, H, W, C] (unet_ffhq.py:153-211 as used
+ * by the up/down ResBlocks :307-316; skip concat :729-731).
+ *   gather : out_small[b,i,j,:] = scale * sum of the 2x2 block of in_big   (avg_pool2d fwd, scale 1/4;
+ *            nearest-upsample backward, scale 1)
+ *   scatter: out_big[b,2i+di,2j+dj,:] = scale * in_small[b,i,j,:]         (nearest-upsample fwd, scale 1;
+ *            avg_pool2d backward, scale 1/4)
+ *   split2 : backward of cat([a,b], channel): in [rows, c1+c2] -> out1 [rows, c1], out2 [rows, c2]
+ * ---------------------------------------------------------------------------------------- */
+int nhmc_pool2_gather(int dtype, const void* in_big, void* out_small, int batch, int h_small,
+                      int w_small, int channels, float scale, nhmc_stream_t stream);
+int nhmc_pool2_scatter(int dtype, const void* in_small, void* out_big, int batch, int h_small,
+                       int w_small, int channels, float scale, nhmc_stream_t stream);
+int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows, int c1, int c2,
+                nhmc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

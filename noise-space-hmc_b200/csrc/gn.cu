@@ -68,6 +68,27 @@ template <> __device__ __forceinline__ void store_vec<__half>(__half* p, const f
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+// raw 16-byte streaming load (read-only path) and in-register unpack: keeps U loads in flight per thread
+__device__ __forceinline__ uint4 ld_raw(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+template <typename T> __device__ __forceinline__ void unpack(const uint4& t, float (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void unpack<float>(const uint4& t, float (&v)[4]) {
+  v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y); v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+}
+template <> __device__ __forceinline__ void unpack<__nv_bfloat16>(const uint4& t, float (&v)[8]) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void unpack<__half>(const uint4& t, float (&v)[8]) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i])); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
 
 struct GnArgs {
@@ -126,20 +147,34 @@ gn_nhwc_stats_kernel(GnArgs a) {
   int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
   // PHASE 1 accumulates t0 = sum dy*act'(z), t1 = sum dy*act'(z)*x per channel; the per-channel
   // affine (gamma(1+s), mean, rstd) is applied once after the loop.
-#pragma unroll 4
-  for (int64_t r = r_begin + prow; r < r_end; r += rows) {
-    float xv[V];
-    load_vec<T>(xb + r * a.C + c0, xv);
-    if (PHASE == 0) {
+  constexpr int U = 4;   // 16-byte loads in flight per thread and stream
+  for (int64_t r0 = r_begin + prow; r0 < r_end; r0 += (int64_t)rows * U) {
+    uint4 rx[U], rd[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
-    } else {
-      float dv[V];
-      load_vec<T>(dyb + r * a.C + c0, dv);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * rows;
+      if (r < r_end) {
+        rx[u] = ld_raw(xb + r * a.C + c0);
+        if (PHASE == 1) rd[u] = ld_raw(dyb + r * a.C + c0);
+      }
+    }
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
-        s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * rows;
+      if (r >= r_end) continue;
+      float xv[V];
+      unpack<T>(rx[u], xv);
+      if (PHASE == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+      } else {
+        float dv[V];
+        unpack<T>(rd[u], dv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+          s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
+        }
       }
     }
   }
@@ -237,23 +272,37 @@ gn_nhwc_apply_kernel(GnArgs a) {
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
   int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
-#pragma unroll 4
-  for (int64_t r = r_begin + prow; r < r_end; r += rows) {
-    float xv[V], ov[V];
-    load_vec<T>(xb + r * a.C + c0, xv);
-    if (PHASE == 0) {
+  constexpr int U = 4;   // 16-byte loads in flight per thread and stream
+  for (int64_t r0 = r_begin + prow; r0 < r_end; r0 += (int64_t)rows * U) {
+    uint4 rx[U], rd[U];
 #pragma unroll
-      for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
-    } else {
-      float dv[V];
-      load_vec<T>(dyb + r * a.C + c0, dv);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
-        ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * rows;
+      if (r < r_end) {
+        rx[u] = ld_raw(xb + r * a.C + c0);
+        if (PHASE == 1) rd[u] = ld_raw(dyb + r * a.C + c0);
       }
     }
-    store_vec<T>(ob + r * a.C + c0, ov);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + (int64_t)u * rows;
+      if (r >= r_end) continue;
+      float xv[V], ov[V];
+      unpack<T>(rx[u], xv);
+      if (PHASE == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
+      } else {
+        float dv[V];
+        unpack<T>(rd[u], dv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+          ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
+        }
+      }
+      store_vec<T>(ob + r * a.C + c0, ov);
+    }
   }
 }
 

@@ -174,3 +174,25 @@ def softmax_bwd(probs, dprobs, dlogits, scale):
     with _timed("softmax_bwd", 1, 3 * probs.numel() * probs.element_size()):
         check(lib().nhmc_softmax_bwd(_DT[probs.dtype], _p(probs), _p(dprobs), _p(dlogits), float(scale), rows, cols,
                                      _stream()), "nhmc_softmax_bwd")
+
+
+def pool2_gather(in_big, out_small, scale):
+    """channels-last 4-D tensors; out_small[b,:,i,j] = scale * sum of the 2x2 block of in_big."""
+    B, Cc, h, w = out_small.shape
+    with _timed("pool2_gather", 1, (in_big.numel() + out_small.numel()) * in_big.element_size()):
+        check(lib().nhmc_pool2_gather(_DT[in_big.dtype], _p(in_big), _p(out_small), B, h, w, Cc, float(scale), _stream()),
+              "nhmc_pool2_gather")
+
+
+def pool2_scatter(in_small, out_big, scale):
+    B, Cc, h, w = in_small.shape
+    with _timed("pool2_scatter", 1, (in_small.numel() + out_big.numel()) * in_small.element_size()):
+        check(lib().nhmc_pool2_scatter(_DT[in_small.dtype], _p(in_small), _p(out_big), B, h, w, Cc, float(scale), _stream()),
+              "nhmc_pool2_scatter")
+
+
+def split2(g, o1, o2):
+    """g: channels-last [B, C1+C2, H, W] -> o1 [B,C1,H,W], o2 [B,C2,H,W] (channels-last)."""
+    rows = g.shape[0] * g.shape[2] * g.shape[3]
+    with _timed("split2", 1, 2 * g.numel() * g.element_size()):
+        check(lib().nhmc_split2(_DT[g.dtype], _p(g), _p(o1), _p(o2), rows, o1.shape[1], o2.shape[1], _stream()), "nhmc_split2")

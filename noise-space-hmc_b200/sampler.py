@@ -131,19 +131,60 @@ class HMCSampler:
         self.ws = kernels.leapfrog_workspace(self.B, dev)
         self.u_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.leapfrog_steps_done = 0
+        self._graphs = None          # {mode: (CUDAGraph, launches)} once capture_graphs() has run
+
+    # ---- one gradient evaluation + leapfrog kernel, eager or as a replayed CUDA graph -------------------
+    def _step_eager(self, mode):
+        src = self.x if mode == _lib.LF_FIRST else self.x_prop
+        loss, g_a, g_b, _ = self.ev(src)
+        kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
+
+    def step(self, mode):
+        """FIRST: evaluate at x, half kick, first drift (x -> x_prop). MIDDLE/LAST: evaluate at x_prop, kick (+ drift)."""
+        if self._graphs is None:
+            self._step_eager(mode)
+        else:
+            g, n = self._graphs[mode]
+            g.replay()
+            kernels.LAUNCHES += n
+
+    def capture_graphs(self, warmup=2):
+        """Capture the three step variants (score-network forwards, fused epilogues, operator, VJPs, leapfrog
+        kernel: several thousand launches each) as CUDA graphs sharing one memory pool.  Per-chain scalars live
+        in device memory (nhmc_chain), so the graphs stay valid for every iteration of every chain.  The sampler
+        state touched while warming up / capturing is restored afterwards."""
+        keep = [t.clone() for t in (self.x, self.x_prop, self.p, self.chains.dev)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # cuDNN autotuning, scratch allocation: outside capture
+                for mode in (_lib.LF_FIRST, _lib.LF_MIDDLE, _lib.LF_LAST):
+                    self._step_eager(mode)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graphs, pool = {}, None
+        for mode in (_lib.LF_FIRST, _lib.LF_MIDDLE, _lib.LF_LAST):
+            g = torch.cuda.CUDAGraph()
+            n0 = kernels.LAUNCHES
+            with torch.cuda.graph(g, pool=pool):
+                self._step_eager(mode)
+            graphs[mode] = (g, kernels.LAUNCHES - n0)
+            pool = g.pool()
+        torch.cuda.synchronize()
+        for dst, src in zip((self.x, self.x_prop, self.p, self.chains.dev), keep):
+            dst.copy_(src)
+        self._graphs = graphs
+        return self
 
     def iteration(self, p, u):
         """One HMC iteration for every chain. p: momentum draw [B,C,H,W]; u: uniform draws [B]."""
         ev, ch, m = self.ev, self.chains, self.mass
         kernels.begin_iteration(ch, self.sched)
         self.p.copy_(p)
-        loss, g_a, g_b, _ = ev(self.x)                                           # main_sampling.py:693-695
-        kernels.leapfrog(_lib.LF_FIRST, self.x, self.x_prop, self.p, g_a, g_b, loss, ch, m, self.ws)
-        xc = None
-        for l in range(self.L):                                                  # main_sampling.py:704-713
-            loss, g_a, g_b, xc = ev(self.x_prop)
-            mode = _lib.LF_LAST if l == self.L - 1 else _lib.LF_MIDDLE
-            kernels.leapfrog(mode, self.x_prop, self.x_prop, self.p, g_a, g_b, loss, ch, m, self.ws)
+        self.step(_lib.LF_FIRST)                                                 # main_sampling.py:693-702,706
+        for l in range(self.L):                                                  # main_sampling.py:704-715
+            self.step(_lib.LF_LAST if l == self.L - 1 else _lib.LF_MIDDLE)
+        xc = ev.xc
         self.leapfrog_steps_done += self.L
         self.u_dev.copy_(torch.as_tensor(u, dtype=torch.float32).reshape(self.B), non_blocking=True)
         kernels.accept(ch, self.u_dev, m, self.sched, self.n_slots)              # main_sampling.py:717-749
@@ -156,12 +197,10 @@ class HMCSampler:
         Used for end-to-end timing; returns {"loss": [B] float64 (host), "bytes": D2H bytes}."""
         self.x_prop.copy_(x_host, non_blocking=True)
         self.p.copy_(p_host, non_blocking=True)
-        loss, g_a, g_b, _ = self.ev(self.x_prop)
-        kernels.leapfrog(_lib.LF_MIDDLE, self.x_prop, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass,
-                         self.ws)
+        self.step(_lib.LF_MIDDLE)
         x_host.copy_(self.x_prop, non_blocking=True)
         p_host.copy_(self.p, non_blocking=True)
-        loss_h = loss.cpu()                       # synchronises: the step's result is on the host
+        loss_h = self.ev.loss.cpu()               # synchronises: the step's result is on the host
         return {"loss": loss_h, "bytes": 2 * x_host.numel() * 4 + loss_h.numel() * 8}
 
     def collected(self):
@@ -210,7 +249,7 @@ def _model_of(algo):
 
 
 def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-        max_iters=None, on_iteration=None, return_sampler=False):
+        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False):
     """Drop-in for main_sampling.hmc (main_sampling.py:660-774).
 
     x: [B,3,H,W] initial noise; b: fp32 betas [1000]; seq/seq_next: timestep lists; algo: object with
@@ -231,6 +270,8 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
     m = float(getattr(opt, "m", 1.0))
     ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
     smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20)
+    if cuda_graphs or getattr(opt, "cuda_graphs", False):
+        smp.capture_graphs()
     dm, du = _default_draws(m)
     _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
     if return_sampler:

@@ -80,6 +80,69 @@ class _ScaledSoftmax(torch.autograd.Function):
         return dlogits, None
 
 
+def _cl(x):
+    return x if _is_channels_last(x) else x.contiguous(memory_format=torch.channels_last)
+
+
+class _AvgPool2(torch.autograd.Function):
+    """avg_pool2d(x, 2) on channels-last activations (Downsample without conv, unet_ffhq.py:187-211)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _cl(x)
+        B, C, H, W = x.shape
+        y = torch.empty((B, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        kernels.pool2_gather(x, y, 0.25)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _cl(dy)
+        B, C, h, w = dy.shape
+        dx = torch.empty((B, C, 2 * h, 2 * w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        kernels.pool2_scatter(dy, dx, 0.25)
+        return dx
+
+
+class _Upsample2(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2, mode="nearest") on channels-last activations (unet_ffhq.py:153-184)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _cl(x)
+        B, C, h, w = x.shape
+        y = torch.empty((B, C, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        kernels.pool2_scatter(x, y, 1.0)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _cl(dy)
+        B, C, H, W = dy.shape
+        dx = torch.empty((B, C, H // 2, W // 2), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        kernels.pool2_gather(dy, dx, 1.0)
+        return dx
+
+
+class _Cat2(torch.autograd.Function):
+    """cat([a, b], dim=1) whose backward hands back two DENSE channels-last gradients (one split pass)
+    instead of strided views of the concatenated gradient (unet_ffhq.py:730)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.c1, ctx.c2 = a.shape[1], b.shape[1]
+        return torch.cat([_cl(a), _cl(b)], dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _cl(g)
+        B, _, H, W = g.shape
+        ga = torch.empty((B, ctx.c1, H, W), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
+        gb = torch.empty((B, ctx.c2, H, W), dtype=g.dtype, device=g.device, memory_format=torch.channels_last)
+        kernels.split2(g, ga, gb)
+        return ga, gb
+
+
 def group_norm_act(x, norm, mode, scale=None, shift=None):
     if not x.is_cuda:
         raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
@@ -130,11 +193,11 @@ class ResBlock(nn.Module):
         """emb_act = SiLU(time embedding) (shared by all blocks: computed once per forward)."""
         h = group_norm_act(x, self.in_layers[0], _lib.GN_SILU)
         if self.up:
-            h = F.interpolate(h, scale_factor=2, mode="nearest")
-            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            h = _Upsample2.apply(h)
+            x = _Upsample2.apply(x)
         elif self.down:
-            h = F.avg_pool2d(h, 2)
-            x = F.avg_pool2d(x, 2)
+            h = _AvgPool2.apply(h)
+            x = _AvgPool2.apply(x)
         h = self.in_layers[2](h)
         e = self.emb_layers[1](emb_act).float()
         if self.film:
@@ -246,7 +309,7 @@ class UNetModel(nn.Module):
             hs.append(h)
         h = self.middle_block(h, emb_act)
         for module in self.output_blocks:
-            h = module(torch.cat([h, hs.pop()], dim=1), emb_act)
+            h = module(_Cat2.apply(h, hs.pop()), emb_act)
         h = group_norm_act(h, self.out[0], _lib.GN_SILU)
         return self.out[2](h)
 

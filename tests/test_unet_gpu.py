@@ -144,3 +144,31 @@ def test_hmc_with_own_unet_small(golden):
     np.testing.assert_allclose(xc.cpu().numpy(), xh.numpy(), atol=1e-3)                  # north-star tolerance
     np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=1e-3)
     np.testing.assert_allclose((ga + gb).cpu().numpy(), og.numpy(), atol=2e-3 * float(og.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_resample_and_split_kernels(dtype):
+    from nhmc_b200 import unet
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 12, 20, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = unet._AvgPool2.apply(x)
+    yr = F.avg_pool2d(x.detach().float(), 2)
+    np.testing.assert_allclose(y.detach().float().cpu().numpy(), yr.cpu().numpy(), atol=1e-6 if dtype == torch.float32 else 2e-2)
+    w = torch.randn(y.shape, generator=g).cuda().to(dtype)
+    (gx,) = torch.autograd.grad(y, x, w)
+    gr = F.interpolate(w.float(), scale_factor=2, mode="nearest") / 4
+    np.testing.assert_allclose(gx.float().cpu().numpy(), gr.cpu().numpy(), atol=1e-6 if dtype == torch.float32 else 1e-2)
+    u = unet._Upsample2.apply(x)
+    assert torch.equal(u.detach(), F.interpolate(x.detach(), scale_factor=2, mode="nearest"))
+    w2 = torch.randn(u.shape, generator=g).cuda().to(dtype)
+    (gu,) = torch.autograd.grad(u, x, w2)
+    gur = F.avg_pool2d(w2.float(), 2) * 4
+    np.testing.assert_allclose(gu.float().cpu().numpy(), gur.cpu().numpy(), atol=1e-5 if dtype == torch.float32 else 5e-2)
+    a = torch.randn(2, 32, 6, 10, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    b = torch.randn(2, 96, 6, 10, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    c = unet._Cat2.apply(a, b)
+    assert torch.equal(c.detach(), torch.cat([a.detach(), b.detach()], 1))
+    w3 = torch.randn(c.shape, generator=g).cuda().to(dtype)
+    ga, gb = torch.autograd.grad(c, (a, b), w3)
+    assert torch.equal(ga, w3[:, :32]) and torch.equal(gb, w3[:, 32:])
+    assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
