@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Per-kernel roofline microbenchmark: each custom kernel alone, on tensors larger than L2, CUDA-event timed.
+
+    python tools/kernel_microbench.py [--only gn] [--reps 20]
+
+Prints one JSON line per (kernel, shape): algorithmic bytes, microseconds, GB/s, fraction of the measured HBM peak.
+Used with `ncu --set full` for the per-kernel captures committed under profiles/.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nhmc_b200  # noqa: E402
+from nhmc_b200 import _lib, kernels, operators as P  # noqa: E402
+from nhmc_b200.chain import ChainState, new_host_state  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.isfile(p) else 6650.0
+
+
+def timeit(fn, reps, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); fn(); e.record()
+        torch.cuda.synchronize()
+        ms.append(s.elapsed_time(e))
+    ms.sort()
+    return ms[len(ms) // 2]
+
+
+def report(name, shape, nbytes, ms, pk):
+    gbs = nbytes / 1e9 / (ms / 1e3)
+    print(json.dumps({"kernel": name, "shape": shape, "alg_MB": round(nbytes / 1e6, 2), "us": round(ms * 1e3, 2),
+                      "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / pk, 3)}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--chains", type=int, default=64)
+    a = ap.parse_args()
+    pk = peak()
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    want = lambda k: (not a.only) or a.only in k
+
+    if want("gn"):
+        for (B, C, H) in [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 512, 64), (8, 1024, 32), (8, 512, 8), (1, 128, 256)]:
+            for dt in (torch.bfloat16,):
+                x = torch.randn(B, C, H, H, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
+                dy = torch.randn_like(x); y = torch.empty_like(x); dx = torch.empty_like(x)
+                gamma = torch.ones(C, device=dev); beta = torch.zeros(C, device=dev)
+                sc = torch.zeros(B, C, device=dev); sh = torch.zeros(B, C, device=dev)
+                stats = torch.empty(B, 32, 2, device=dev)
+                nb = x.numel() * x.element_size()
+                for mode, nm in ((_lib.GN_SILU, "silu"), (_lib.GN_FILM_SILU, "film")):
+                    s_, h_ = (sc, sh) if mode == _lib.GN_FILM_SILU else (None, None)
+                    ms = timeit(lambda: kernels.gn_fwd(mode, x, y, gamma, beta, s_, h_, stats, 32, 1e-5, True), a.reps, flush)
+                    report("gn_fwd_" + nm, [B, C, H, H], 2 * nb, ms, pk)
+                    ms = timeit(lambda: kernels.gn_bwd(mode, x, dy, dx, gamma, beta, s_, h_, stats, 32, True), a.reps, flush)
+                    report("gn_bwd_" + nm, [B, C, H, H], 3 * nb, ms, pk)
+    if want("leapfrog") or want("ddim") or want("op"):
+        B = a.chains
+        N = 3 * 256 * 256
+        x = torch.randn(B, 3, 256, 256, device=dev); p = torch.randn_like(x); g = torch.randn_like(x); g2 = torch.randn_like(x)
+        xo = torch.empty_like(x)
+        ch = ChainState(new_host_state(B, 1.0, 0.05, 0.1), dev)
+        kernels.begin_iteration(ch, _lib.SCHED_PIXEL)
+        ws = kernels.leapfrog_workspace(B, dev)
+        loss = torch.zeros(B, dtype=torch.float64, device=dev)
+        if want("leapfrog"):
+            for mode, nm, nbuf in ((_lib.LF_FIRST, "first", 6), (_lib.LF_MIDDLE, "middle", 6), (_lib.LF_LAST, "last", 5)):
+                ms = timeit(lambda: kernels.leapfrog(mode, x, xo, p, g, g2, loss, ch, 1.0, ws), a.reps, flush)
+                report("leapfrog_" + nm, [B, 3, 256, 256], nbuf * B * N * 4, ms, pk)
+        if want("ddim"):
+            eps = torch.randn(B, 6, 256, 256, device=dev, dtype=torch.bfloat16)
+            mask = torch.empty(B, kernels.ddim_mask_words(N), dtype=torch.int32, device=dev)
+            coef = (0.96, 0.28, 0.69, 0.72)
+            ms = timeit(lambda: kernels.ddim_fwd(x, eps, xo, mask, coef), a.reps, flush)
+            report("ddim_fwd", [B, 3, 256, 256], B * N * (4 + 2 + 4) + B * N // 8, ms, pk)
+            ge = torch.zeros_like(eps); gx = torch.empty_like(x)
+            ms = timeit(lambda: kernels.ddim_bwd(g, g2, mask, gx, ge, coef), a.reps, flush)
+            report("ddim_bwd", [B, 3, 256, 256], B * N * (4 + 4 + 4 + 2) + B * N // 8, ms, pk)
+        if want("op"):
+            torch.manual_seed(5678)
+            ops = {"inpaint": P.Inpainting.random(3, 256, dev), "sr4": P.SuperResolution(3, 256, 4, dev),
+                   "sr16": P.SuperResolution(3, 256, 16, dev), "hdr": P.HDR(3, 256, dev),
+                   "deblur": P.Deblurring2D(P.gaussian_taps(1.0), P.gaussian_taps(20.0), 3, 256, dev),
+                   "phase": P.PhaseRetrievalOperator(2.0, dev, 3, 256)}
+            for nm, op in ops.items():
+                Bo = B if nm not in ("deblur", "phase") else min(B, 16)
+                xs = x[:Bo].contiguous()
+                y = op.H(xs)
+                gg = torch.empty_like(xs); xc = torch.empty_like(xs); ls = torch.zeros(Bo, dtype=torch.float64, device=dev)
+                ms = timeit(lambda: op.loss_grad(xs, y, g=gg, xc=xc, loss=ls), a.reps, flush)
+                report("op_loss_grad_" + nm, [Bo, 3, 256, 256], (3 * xs.numel() + y.numel()) * 4, ms, pk)
+    if want("pool") or want("split"):
+        B, C, H = 8, 256, 128
+        big = torch.randn(B, C, 2 * H, 2 * H, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        small = torch.empty(B, C, H, H, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        nb = (big.numel() + small.numel()) * 2
+        report("pool2_gather", [B, C, 2 * H, 2 * H], nb, timeit(lambda: kernels.pool2_gather(big, small, 0.25), a.reps, flush), pk)
+        report("pool2_scatter", [B, C, H, H], nb, timeit(lambda: kernels.pool2_scatter(small, big, 1.0), a.reps, flush), pk)
+        o1 = torch.empty(B, 128, 2 * H, 2 * H, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        o2 = torch.empty_like(o1)
+        report("split2", [B, C, 2 * H, 2 * H], 2 * big.numel() * 2, timeit(lambda: kernels.split2(big, o1, o2), a.reps, flush), pk)
+
+
+if __name__ == "__main__":
+    main()
