@@ -114,20 +114,93 @@ template <int MODE> __device__ __forceinline__ float gn_dact(float z) {  // d ac
 }
 
 // ============================== channels-last ==============================================
-// PHASE 0: forward statistics (sum x, sum x^2)            -> stats  = (mean, rstd)
-// PHASE 1: backward statistics (sum du, sum du*u)          -> bstats = (S1/n, S2/n)
+// A CTA owns `rows_per_cta` consecutive pixels of one sample = ONE contiguous byte range of the NHWC
+// tensor.  The range is streamed through a shared-memory ring with TMA 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx): bytes in flight are set by the ring depth, not by registers,
+// so the per-thread channel constants can stay in registers.  Thread t always lands on the same
+// VEC channels (stage size is a whole number of passes of blockDim * 16 B = rows * C elements).
+constexpr int kGnStages = 4;
+constexpr int kGnPasses = 2;   // stage = kGnPasses * blockDim * 16 bytes (8 KiB at 256 threads)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Streams NSRC byte ranges (x, and dy for the backward kernels) of `total` bytes each through the ring
+// and calls body(offset_in_range, x_vec, dy_vec) for every 16-byte vector owned by this thread.
+template <int NSRC, typename Body>
+__device__ __forceinline__ void stream_ranges(const char* src0, const char* src1, int64_t total, unsigned char* ring,
+                                              uint64_t* bars, Body body) {
+  const unsigned stage_bytes = kGnPasses * blockDim.x * 16u;
+  const int64_t n_it = (total + stage_bytes - 1) / stage_bytes;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kGnStages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int64_t it) {
+    const int s = (int)(it % kGnStages);
+    const int64_t off = it * stage_bytes;
+    const unsigned bytes = (unsigned)((total - off) < (int64_t)stage_bytes ? (total - off) : stage_bytes);
+    mbar_expect_tx(bars + s, bytes * NSRC);
+    bulk_g2s(ring + (size_t)s * NSRC * stage_bytes, src0 + off, bytes, bars + s);
+    if (NSRC == 2) bulk_g2s(ring + (size_t)s * NSRC * stage_bytes + stage_bytes, src1 + off, bytes, bars + s);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t it = 0; it < kGnStages && it < n_it; ++it) issue(it);
+  for (int64_t it = 0; it < n_it; ++it) {
+    const int s = (int)(it % kGnStages);
+    mbar_wait(bars + s, (unsigned)((it / kGnStages) & 1));
+    const unsigned char* st = ring + (size_t)s * NSRC * stage_bytes;
+#pragma unroll
+    for (int ps = 0; ps < kGnPasses; ++ps) {
+      const unsigned o = (ps * blockDim.x + threadIdx.x) * 16u;
+      const int64_t goff = it * stage_bytes + o;
+      if (goff < total) {
+        const uint4 vx = *reinterpret_cast<const uint4*>(st + o);
+        uint4 vd = make_uint4(0, 0, 0, 0);
+        if (NSRC == 2) vd = *reinterpret_cast<const uint4*>(st + stage_bytes + o);
+        body(goff, vx, vd);
+      }
+    }
+    __syncthreads();                                   // every thread is done with slot s
+    if (threadIdx.x == 0 && it + kGnStages < n_it) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(it + kGnStages);
+    }
+  }
+}
+
+// PHASE 0: forward statistics (sum x, sum x^2)            -> fp64 accumulators [B][64][2]
+// PHASE 1: backward statistics (sum du, sum du*u)          -> same accumulators
 template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256)
 gn_nhwc_stats_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
-  extern __shared__ float sm[];  // [rows][C][2]
-  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bars[kGnStages];
+  const int b = blockIdx.y, blk = blockIdx.x;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
   const int Cg = a.C / a.G;
-  const T* xb = reinterpret_cast<const T*>(a.x) + (int64_t)b * a.HW * a.C;
-  const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + (int64_t)b * a.HW * a.C : nullptr;
   float s0[V], s1[V], ca[V], cb[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; ca[i] = 0.f; cb[i] = 0.f; }
@@ -145,39 +218,29 @@ gn_nhwc_stats_kernel(GnArgs a) {
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
   int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+  const int64_t row_bytes = (int64_t)a.C * sizeof(T);
+  const char* xsrc = reinterpret_cast<const char*>(a.x) + ((int64_t)b * a.HW + r_begin) * row_bytes;
+  const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + ((int64_t)b * a.HW + r_begin) * row_bytes : nullptr;
+  const unsigned ring_bytes = kGnStages * (PHASE == 1 ? 2 : 1) * kGnPasses * blockDim.x * 16u;
   // PHASE 1 accumulates t0 = sum dy*act'(z), t1 = sum dy*act'(z)*x per channel; the per-channel
   // affine (gamma(1+s), mean, rstd) is applied once after the loop.
-  constexpr int U = 4;   // 16-byte loads in flight per thread and stream
-  for (int64_t r0 = r_begin + prow; r0 < r_end; r0 += (int64_t)rows * U) {
-    uint4 rx[U], rd[U];
+  stream_ranges<PHASE == 1 ? 2 : 1>(xsrc, dsrc, (r_end - r_begin) * row_bytes, dyn, bars,
+      [&](int64_t, const uint4& rx, const uint4& rd) {
+        float xv[V];
+        unpack<T>(rx, xv);
+        if (PHASE == 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * rows;
-      if (r < r_end) {
-        rx[u] = ld_raw(xb + r * a.C + c0);
-        if (PHASE == 1) rd[u] = ld_raw(dyb + r * a.C + c0);
-      }
-    }
+          for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+        } else {
+          float dv[V];
+          unpack<T>(rd, dv);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * rows;
-      if (r >= r_end) continue;
-      float xv[V];
-      unpack<T>(rx[u], xv);
-      if (PHASE == 0) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
-      } else {
-        float dv[V];
-        unpack<T>(rd[u], dv);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
-          s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
+          for (int i = 0; i < V; ++i) {
+            const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+            s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
+          }
         }
-      }
-    }
-  }
+      });
   if (PHASE == 1) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
@@ -190,8 +253,8 @@ gn_nhwc_stats_kernel(GnArgs a) {
       s1[i] = cgm * rstd * (t1 - mean * t0);
     }
   }
-  // ordered reduce over the CTA's pixel rows, then over the channels of each group
-  float* sm0 = sm; float* sm1 = sm + (size_t)rows * a.C;
+  // ordered reduce over the CTA's pixel rows, then over the channels of each group (ring memory is free now)
+  float* sm0 = reinterpret_cast<float*>(dyn + ring_bytes); float* sm1 = sm0 + (size_t)rows * a.C;
 #pragma unroll
   for (int i = 0; i < V; ++i) { sm0[(size_t)prow * a.C + c0 + i] = s0[i]; sm1[(size_t)prow * a.C + c0 + i] = s1[i]; }
   __syncthreads();
@@ -204,7 +267,6 @@ gn_nhwc_stats_kernel(GnArgs a) {
     atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
     atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
   }
-  (void)nblk; (void)blk;
 }
 
 // PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
@@ -212,14 +274,13 @@ template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256)
 gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bars[kGnStages];
   const int b = blockIdx.y, blk = blockIdx.x;
   const int cvec = a.C / V;
-  const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
+  const int cv = threadIdx.x % cvec;
   const int c0 = cv * V;
   const int Cg = a.C / a.G;
-  const T* xb = reinterpret_cast<const T*>(a.x) + (int64_t)b * a.HW * a.C;
-  const T* dyb = PHASE == 1 ? reinterpret_cast<const T*>(a.dy) + (int64_t)b * a.HW * a.C : nullptr;
-  T* ob = reinterpret_cast<T*>(a.out) + (int64_t)b * a.HW * a.C;
   float ca[V], cb[V], k1[V], k2[V], k3[V];
   const double n = (double)Cg * (double)a.HW;
 #pragma unroll
@@ -249,10 +310,34 @@ gn_nhwc_apply_kernel(GnArgs a) {
       k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
     }
   }
-  // every CTA has now read the accumulators it needs; the last one to get here publishes (mean, rstd)
-  // for the backward pass and re-zeroes the accumulators for the next call on this stream.
+  const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
+  int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+  const int64_t row_bytes = (int64_t)a.C * sizeof(T);
+  const int64_t base = ((int64_t)b * a.HW + r_begin) * row_bytes;
+  const char* xsrc = reinterpret_cast<const char*>(a.x) + base;
+  const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + base : nullptr;
+  char* dst = reinterpret_cast<char*>(a.out) + base;
+  stream_ranges<PHASE == 1 ? 2 : 1>(xsrc, dsrc, (r_end - r_begin) * row_bytes, dyn, bars,
+      [&](int64_t off, const uint4& rx, const uint4& rd) {
+        float xv[V], ov[V];
+        unpack<T>(rx, xv);
+        if (PHASE == 0) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
+        } else {
+          float dv[V];
+          unpack<T>(rd, dv);
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+            ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
+          }
+        }
+        store_vec<T>(reinterpret_cast<T*>(dst + off), ov);
+      });
+  // Every CTA read the accumulators before streaming; the last CTA to finish publishes (mean, rstd) for the
+  // backward pass and re-zeroes the accumulators for the next call on this stream (no wait on the hot path).
   __shared__ bool is_last;
-  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     is_last = atomicInc(a.tickets + b, (unsigned int)(gridDim.x - 1)) == (unsigned int)(gridDim.x - 1);
@@ -268,40 +353,6 @@ gn_nhwc_apply_kernel(GnArgs a) {
         a.stats[((int64_t)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
       }
       acc[0] = 0.0; acc[1] = 0.0;
-    }
-  }
-  const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
-  int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
-  constexpr int U = 4;   // 16-byte loads in flight per thread and stream
-  for (int64_t r0 = r_begin + prow; r0 < r_end; r0 += (int64_t)rows * U) {
-    uint4 rx[U], rd[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * rows;
-      if (r < r_end) {
-        rx[u] = ld_raw(xb + r * a.C + c0);
-        if (PHASE == 1) rd[u] = ld_raw(dyb + r * a.C + c0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = r0 + (int64_t)u * rows;
-      if (r >= r_end) continue;
-      float xv[V], ov[V];
-      unpack<T>(rx[u], xv);
-      if (PHASE == 0) {
-#pragma unroll
-        for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
-      } else {
-        float dv[V];
-        unpack<T>(rd[u], dv);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
-          ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
-        }
-      }
-      store_vec<T>(ob + r * a.C + c0, ov);
     }
   }
 }
@@ -420,9 +471,17 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
   a.rows_per_cta = rows_per_cta;
   a.rows_per_cta_iter = rows;
   const dim3 grid((unsigned)nblk, batch);
-  const size_t smem = (size_t)rows * a.C * 2 * sizeof(float);
-  gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, smem, st>>>(a);
-  gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, 0, st>>>(a);
+  const size_t ring = (size_t)kGnStages * (PHASE == 1 ? 2 : 1) * kGnPasses * threads * 16;
+  const size_t smem_stats = ring + (size_t)rows * a.C * 2 * sizeof(float);
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(gn_nhwc_stats_kernel<T, MODE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaFuncSetAttribute(gn_nhwc_apply_kernel<T, MODE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    attr_done = true;
+  }
+  NHMC_CHECK_ARG(smem_stats <= 160 * 1024, "GroupNorm shared-memory ring too large");
+  gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, smem_stats, st>>>(a);
+  gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, ring, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
 
