@@ -104,12 +104,22 @@ struct GnArgs {
 };
 
 // per-element pieces --------------------------------------------------------------------------
-template <int MODE> __device__ __forceinline__ float gn_act(float z) {
-  return MODE == NHMC_GN_PLAIN ? z : z * sigmoidf_fast(z);
+// sigmoid: one MUFU (tanh.approx, rel. error 2^-11 < half a bf16/fp16 ulp) for 16-bit activations -- the SFU
+// pipe, not HBM, bounded the apply kernels with the 2-MUFU ex2+rcp form; fp32 activations keep the exact form.
+template <typename T> __device__ __forceinline__ float sigmoid_t(float z) {
+  if (sizeof(T) == 2) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
+  }
+  return sigmoidf_fast(z);
 }
-template <int MODE> __device__ __forceinline__ float gn_dact(float z) {  // d act / dz
+template <int MODE, typename T> __device__ __forceinline__ float gn_act(float z) {
+  return MODE == NHMC_GN_PLAIN ? z : z * sigmoid_t<T>(z);
+}
+template <int MODE, typename T> __device__ __forceinline__ float gn_dact(float z) {  // d act / dz
   if (MODE == NHMC_GN_PLAIN) return 1.0f;
-  const float s = sigmoidf_fast(z);
+  const float s = sigmoid_t<T>(z);
   return s * (1.0f + z * (1.0f - s));
 }
 
@@ -236,7 +246,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
           unpack<T>(rd, dv);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+            const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
           }
         }
@@ -253,8 +263,10 @@ gn_nhwc_stats_kernel(GnArgs a) {
       s1[i] = cgm * rstd * (t1 - mean * t0);
     }
   }
-  // ordered reduce over the CTA's pixel rows, then over the channels of each group (ring memory is free now)
-  float* sm0 = reinterpret_cast<float*>(dyn + ring_bytes); float* sm1 = sm0 + (size_t)rows * a.C;
+  // ordered reduce over the CTA's pixel rows, then over the channels of each group; the ring is drained
+  // (stream_ranges ends on a __syncthreads after the last slot was consumed), so its memory is reused
+  (void)ring_bytes;
+  float* sm0 = reinterpret_cast<float*>(dyn); float* sm1 = sm0 + (size_t)rows * a.C;
 #pragma unroll
   for (int i = 0; i < V; ++i) { sm0[(size_t)prow * a.C + c0 + i] = s0[i]; sm1[(size_t)prow * a.C + c0 + i] = s1[i]; }
   __syncthreads();
@@ -283,18 +295,26 @@ gn_nhwc_apply_kernel(GnArgs a) {
   const int Cg = a.C / a.G;
   float ca[V], cb[V], k1[V], k2[V], k3[V];
   const double n = (double)Cg * (double)a.HW;
+  // group statistics once per CTA (G <= 64 threads touch fp64), everybody else reads floats from shared memory
+  __shared__ float g_mean[64], g_rstd[64], g_m1[64], g_m2[64];
+  if (threadIdx.x < a.G) {
+    const int g = threadIdx.x;
+    const double inv_n = 1.0 / n;
+    const double a0 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2) * inv_n;
+    const double a1 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1) * inv_n;
+    if (PHASE == 0) {
+      double var = a1 - a0 * a0; if (var < 0.0) var = 0.0;
+      g_mean[g] = (float)a0; g_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+    } else {
+      g_mean[g] = a.stats[((int64_t)b * a.G + g) * 2]; g_rstd[g] = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      g_m1[g] = (float)a0; g_m2[g] = (float)a1;
+    }
+  }
+  __syncthreads();
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = c0 + i, g = c / Cg;
-    const double a0 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2), a1 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
-    float mean, rstd;
-    if (PHASE == 0) {
-      const double mu = a0 / n;
-      double var = a1 / n - mu * mu; if (var < 0.0) var = 0.0;
-      mean = (float)mu; rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    } else {
-      mean = a.stats[((int64_t)b * a.G + g) * 2]; rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
-    }
+    const float mean = g_mean[g], rstd = g_rstd[g];
     const float gam = a.gamma[c], bet = a.beta[c];
     const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
     const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
@@ -304,7 +324,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
     if (PHASE == 1) {
       // dx = rstd*(du - m1 - u*m2), du = dy*act'(z)*gamma*(1+s), u = (x-mean)*rstd
       //    = k1*dy*act'(z) + k2*x + k3
-      const float m1 = (float)(a0 / n), m2 = (float)(a1 / n);
+      const float m1 = g_m1[g], m2 = g_m2[g];
       k1[i] = rstd * gam * sc;
       k2[i] = -rstd * rstd * m2;
       k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
@@ -323,13 +343,13 @@ gn_nhwc_apply_kernel(GnArgs a) {
         unpack<T>(rx, xv);
         if (PHASE == 0) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE>(fmaf(ca[i], xv[i], cb[i]));
+          for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
         } else {
           float dv[V];
           unpack<T>(rd, dv);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float d = dv[i] * gn_dact<MODE>(fmaf(ca[i], xv[i], cb[i]));
+            const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
           }
         }
@@ -347,10 +367,8 @@ gn_nhwc_apply_kernel(GnArgs a) {
     for (int g = threadIdx.x; g < a.G; g += blockDim.x) {
       double* acc = a.partials + ((int64_t)b * 64 + g) * 2;
       if (PHASE == 0) {
-        const double mu = __ldcg(acc) / n;
-        double var = __ldcg(acc + 1) / n - mu * mu; if (var < 0.0) var = 0.0;
-        a.stats[((int64_t)b * a.G + g) * 2] = (float)mu;
-        a.stats[((int64_t)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+        a.stats[((int64_t)b * a.G + g) * 2] = g_mean[g];
+        a.stats[((int64_t)b * a.G + g) * 2 + 1] = g_rstd[g];
       }
       acc[0] = 0.0; acc[1] = 0.0;
     }
@@ -401,14 +419,14 @@ gn_nchw_kernel(GnArgs a) {
   if (PHASE == 0) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      ob[i] = Elem<T>::from_f(gn_act<MODE>(fmaf(ca, Elem<T>::to_f(xb[i]), cb)));
+      ob[i] = Elem<T>::from_f(gn_act<MODE, T>(fmaf(ca, Elem<T>::to_f(xb[i]), cb)));
     }
   } else {
     double s[2] = {0.0, 0.0};
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
       const float xv = Elem<T>::to_f(xb[i]);
-      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE>(fmaf(ca, xv, cb)) * cgm;
+      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       s[0] += du; s[1] += (double)du * (double)((xv - mean) * rstd);
     }
     block_sum<double, 2>(s, red);
@@ -418,7 +436,7 @@ gn_nchw_kernel(GnArgs a) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
       const float xv = Elem<T>::to_f(xb[i]);
-      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE>(fmaf(ca, xv, cb)) * cgm;
+      const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       const float u = (xv - mean) * rstd;
       ob[i] = Elem<T>::from_f(rstd * (du - m1 - u * m2));
     }
@@ -460,11 +478,11 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
   int rows = 256 / cvec; if (rows < 1) rows = 1;
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
-  // chunking: aim at ~8 CTAs per SM over the whole batch, between 16 KiB and 128 KiB of input per CTA
+  // chunking: aim at ~4 CTAs per SM over the whole batch, between 32 KiB and 256 KiB of input per CTA
   const int64_t bytes_per_row = (int64_t)a.C * sizeof(T);
-  int64_t target = (int64_t)batch * a.HW * bytes_per_row / (kSMs * 8);
-  if (target < 16384) target = 16384;
-  if (target > 131072) target = 131072;
+  int64_t target = (int64_t)batch * a.HW * bytes_per_row / (kSMs * 4);
+  if (target < 32768) target = 32768;
+  if (target > 262144) target = 262144;
   int64_t rows_per_cta = (target + bytes_per_row - 1) / bytes_per_row;
   rows_per_cta = ((rows_per_cta + rows - 1) / rows) * rows;
   int64_t nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
@@ -472,7 +490,8 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
   a.rows_per_cta_iter = rows;
   const dim3 grid((unsigned)nblk, batch);
   const size_t ring = (size_t)kGnStages * (PHASE == 1 ? 2 : 1) * kGnPasses * threads * 16;
-  const size_t smem_stats = ring + (size_t)rows * a.C * 2 * sizeof(float);
+  const size_t red = (size_t)rows * a.C * 2 * sizeof(float);
+  const size_t smem_stats = ring > red ? ring : red;
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
     cudaFuncSetAttribute(gn_nhwc_stats_kernel<T, MODE, PHASE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
