@@ -201,7 +201,9 @@ int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const f
  *   NHMC_GN_SILU  : y = silu(gn(x))                    (in_layers / out)
  *   NHMC_GN_FILM_SILU : y = silu(gn(x)*(1+scale)+shift) (out_layers, use_scale_shift_norm)
  * x, y: [B, C, HW] contiguous (NCHW) or channels-last [B, HW, C] (layout flag), dtype
- * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32-or-dtype [B, C] (FiLM only).
+ * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32 [B, C] (FiLM only); in_bias fp32 [C] or
+ * NULL: the tensor that is normalised is x + in_bias[c] (the bias of the convolution that
+ * produced x, folded in here instead of a separate broadcast-add pass).
  * stats_out: fp32 [B, G, 2] (mean, rstd) saved for the backward.
  * ---------------------------------------------------------------------------------------- */
 #define NHMC_GN_PLAIN 0
@@ -210,13 +212,15 @@ int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const f
 #define NHMC_LAYOUT_NCHW 0
 #define NHMC_LAYOUT_NHWC 1
 int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
-                const float* beta, const float* scale, const float* shift, float* stats_out,
+                const float* beta, const float* scale, const float* shift, const float* in_bias,
+                float* stats_out,
                 int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream);
 /* dx (and optionally dscale/dshift [B,C] fp32) given dy; weights are frozen on this path, so
  * no dgamma/dbeta. */
 int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                 const float* gamma, const float* beta, const float* scale, const float* shift,
-                const float* stats, float* dscale, float* dshift, int batch, int channels,
+                const float* in_bias, const float* stats, float* dscale, float* dshift, int batch,
+                int channels,
                 int64_t hw, int groups, nhmc_stream_t stream);
 
 /* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of
@@ -243,6 +247,10 @@ int nhmc_pool2_scatter(int dtype, const void* in_small, void* out_big, int batch
                        int w_small, int channels, float scale, nhmc_stream_t stream);
 int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows, int c1, int c2,
                 nhmc_stream_t stream);
+/* out[r, c] = a[r, c] (+ b[r, c]) (+ bias[c]): residual add of the ResBlock (unet_ffhq.py:327) with the
+ * biases of the convolutions that produced a / b folded in; channels-last rows, out may alias a. */
+int nhmc_bias_add(int dtype, const void* a, const void* b, const float* bias, void* out,
+                  int64_t rows, int channels, nhmc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,7 @@ __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f
 struct GnArgs {
   const void* x; const void* dy; void* out;
   const float* gamma; const float* beta; const float* scale; const float* shift;  // scale/shift: [B,C] fp32 or null
+  const float* in_bias;  // [C] fp32 or null: the normalised tensor is x + in_bias[c] (conv bias folded in)
   float* stats;      // [B][G][2]: fwd (mean, rstd)
   float* bstats;     // [B][G][2]: bwd (sum du / n, sum du*u / n)
   double* partials;  // [B][kGnMaxBlocks][G][2]
@@ -218,7 +219,8 @@ gn_nhwc_stats_kernel(GnArgs a) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
       const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
@@ -251,11 +253,23 @@ gn_nhwc_stats_kernel(GnArgs a) {
           }
         }
       });
+  if (PHASE == 0 && a.in_bias) {
+    // statistics of x + bias from the raw sums: this thread saw `cnt` pixels of each of its channels
+    const int64_t span = r_end - r_begin - prow;
+    const int64_t cnt = span > 0 ? (span + rows - 1) / rows : 0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float bia = a.in_bias[c0 + i];
+      s1[i] = s1[i] + 2.0f * bia * s0[i] + (float)cnt * bia * bia;
+      s0[i] = s0[i] + (float)cnt * bia;
+    }
+  }
   if (PHASE == 1) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2], rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
       const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
       const float t0 = s0[i], t1 = s1[i];
@@ -314,7 +328,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = c0 + i, g = c / Cg;
-    const float mean = g_mean[g], rstd = g_rstd[g];
+    const float mean = g_mean[g] - (a.in_bias ? a.in_bias[c] : 0.0f), rstd = g_rstd[g];
     const float gam = a.gamma[c], bet = a.beta[c];
     const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
     const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
@@ -394,7 +408,7 @@ gn_nchw_kernel(GnArgs a) {
   if (PHASE == 0) {
     double s[2] = {0.0, 0.0};
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = Elem<T>::to_f(xb[i]);
+      const float v = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       s[0] += v; s[1] += (double)v * v;
     }
     block_sum<double, 2>(s, red);
@@ -419,13 +433,14 @@ gn_nchw_kernel(GnArgs a) {
   if (PHASE == 0) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      ob[i] = Elem<T>::from_f(gn_act<MODE, T>(fmaf(ca, Elem<T>::to_f(xb[i]), cb)));
+      const float bia = a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f;
+      ob[i] = Elem<T>::from_f(gn_act<MODE, T>(fmaf(ca, Elem<T>::to_f(xb[i]) + bia, cb)));
     }
   } else {
     double s[2] = {0.0, 0.0};
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      const float xv = Elem<T>::to_f(xb[i]);
+      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       s[0] += du; s[1] += (double)du * (double)((xv - mean) * rstd);
     }
@@ -435,7 +450,7 @@ gn_nchw_kernel(GnArgs a) {
     const float m1 = bc[0], m2 = bc[1];
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      const float xv = Elem<T>::to_f(xb[i]);
+      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       const float u = (xv - mean) * rstd;
       ob[i] = Elem<T>::from_f(rstd * (du - m1 - u * m2));
@@ -548,21 +563,21 @@ static int check_common(int mode, int layout, int dtype, const void* x, const vo
 using namespace nhmc;
 
 extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
-                           const float* beta, const float* scale, const float* shift, float* stats_out, int batch,
+                           const float* beta, const float* scale, const float* shift, const float* in_bias, float* stats_out, int batch,
                            int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(stats_out, "stats_out required");
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
-  a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = stats_out;
+  a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.stats = stats_out;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
   return dispatch<0>(mode, layout, dtype, a, batch, (cudaStream_t)stream);
 }
 
 extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                            const float* gamma, const float* beta, const float* scale, const float* shift,
-                           const float* stats, float* dscale, float* dshift, int batch, int channels, int64_t hw,
+                           const float* in_bias, const float* stats, float* dscale, float* dshift, int batch, int channels, int64_t hw,
                            int groups, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(dy && stats, "dy and stats required");
@@ -571,7 +586,7 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
-  a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift;
+  a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias;
   a.stats = const_cast<float*>(stats);
   a.bstats = s.bstats;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;

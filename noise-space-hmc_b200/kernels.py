@@ -141,23 +141,23 @@ def commit(chains, x, x_prop, x_hat, x_keep, samples, sched, n_slots):
                                 chains.n, N, _stream()), "nhmc_commit")
 
 
-def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last):
+def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last, in_bias=None):
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
     with _timed("gn_fwd", 2 if channels_last else 1, 2 * x.numel() * x.element_size()):
         check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
-                                _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), B, Cc, hw, groups, float(eps),
-                                _stream()), "nhmc_gn_fwd")
+                                _p(gamma), _p(beta), _p(scale), _p(shift), _p(in_bias), _p(stats), B, Cc, hw, groups,
+                                float(eps), _stream()), "nhmc_gn_fwd")
 
 
-def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last):
+def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None):
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
     with _timed("gn_bwd", 2 if channels_last else 1, 3 * x.numel() * x.element_size()):
         check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
-                                _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(stats), 0, 0, B, Cc, hw, groups,
-                                _stream()), "nhmc_gn_bwd")
+                                _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(in_bias), _p(stats), 0, 0, B, Cc, hw,
+                                groups, _stream()), "nhmc_gn_bwd")
 
 
 def softmax_fwd(logits, probs, scale):
@@ -196,3 +196,11 @@ def split2(g, o1, o2):
     rows = g.shape[0] * g.shape[2] * g.shape[3]
     with _timed("split2", 1, 2 * g.numel() * g.element_size()):
         check(lib().nhmc_split2(_DT[g.dtype], _p(g), _p(o1), _p(o2), rows, o1.shape[1], o2.shape[1], _stream()), "nhmc_split2")
+
+
+def bias_add(a, b, bias, out):
+    """channels-last 4-D tensors: out = a (+ b) (+ bias[c]); out may alias a."""
+    B, Cc, H, W = a.shape
+    nb = (a.numel() * (2 + (1 if b is not None else 0))) * a.element_size()
+    with _timed("bias_add", 1, nb):
+        check(lib().nhmc_bias_add(_DT[a.dtype], _p(a), _p(b), _p(bias), _p(out), B * H * W, Cc, _stream()), "nhmc_bias_add")

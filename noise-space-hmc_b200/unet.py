@@ -40,24 +40,24 @@ class _GroupNormAct(torch.autograd.Function):
     """y = act(GN32(x) [*(1+scale)+shift]); saves x and the per-group (mean, rstd) only."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mode):
+    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias):
         cl = _is_channels_last(x)
         if not cl and not x.is_contiguous():
             x = x.contiguous()
         y = torch.empty_like(x)
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
-        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, GN_EPS, cl)
-        ctx.save_for_backward(x, gamma, beta, scale, shift, stats)
+        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, GN_EPS, cl, in_bias)
+        ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
         ctx.mode, ctx.cl = mode, cl
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma, beta, scale, shift, stats = ctx.saved_tensors
+        x, gamma, beta, scale, shift, stats, in_bias = ctx.saved_tensors
         dy = dy.contiguous(memory_format=torch.channels_last) if ctx.cl else dy.contiguous()
         dx = torch.empty_like(x)
-        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, ctx.cl)
-        return dx, None, None, None, None, None
+        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, ctx.cl, in_bias)
+        return dx, None, None, None, None, None, None
 
 
 class _ScaledSoftmax(torch.autograd.Function):
@@ -143,10 +143,33 @@ class _Cat2(torch.autograd.Function):
         return ga, gb
 
 
-def group_norm_act(x, norm, mode, scale=None, shift=None):
+class _BiasAdd(torch.autograd.Function):
+    """out = a (+ b) (+ bias[c]) in one pass; the gradient of a and b is the incoming gradient itself
+    (residual add of unet_ffhq.py:327 with the producing convolutions' biases folded in)."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias):
+        a = _cl(a)
+        b = _cl(b) if b is not None else None
+        out = torch.empty_like(a)
+        kernels.bias_add(a, b, bias, out)
+        ctx.has_b = b is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (g if ctx.has_b else None), None
+
+
+def group_norm_act(x, norm, mode, scale=None, shift=None, in_bias=None):
+    """act(GN32(x + in_bias[c]) ...): in_bias folds the bias of the convolution that produced x."""
     if not x.is_cuda:
         raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
-    return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode)
+    return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode, in_bias)
+
+
+def _conv_nobias(conv, x):
+    return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,15 +221,31 @@ class ResBlock(nn.Module):
         elif self.down:
             h = _AvgPool2.apply(h)
             x = _AvgPool2.apply(x)
-        h = self.in_layers[2](h)
+        # conv biases never get their own broadcast-add pass: b1 is folded into the GroupNorm that follows,
+        # b2 (+ the 1x1 skip conv's bias) into the residual add
+        b1, b_out = self._fp32_biases()
+        h = _conv_nobias(self.in_layers[2], h)
         e = self.emb_layers[1](emb_act).float()
         if self.film:
             scale, shift = e[:, : self.out_channels].contiguous(), e[:, self.out_channels:].contiguous()
-            h = group_norm_act(h, self.out_layers[0], _lib.GN_FILM_SILU, scale, shift)
+            h = group_norm_act(h, self.out_layers[0], _lib.GN_FILM_SILU, scale, shift, in_bias=b1)
         else:
-            h = group_norm_act(h + e.to(h.dtype)[:, :, None, None], self.out_layers[0], _lib.GN_SILU)
-        h = self.out_layers[3](h)
-        return self.skip_connection(x) + h
+            h = group_norm_act(h + (e + b1).to(h.dtype)[:, :, None, None], self.out_layers[0], _lib.GN_SILU)
+        h = _conv_nobias(self.out_layers[3], h)
+        skip = x if isinstance(self.skip_connection, nn.Identity) else _conv_nobias(self.skip_connection, x)
+        return _BiasAdd.apply(skip, h, b_out)
+
+    def _fp32_biases(self):
+        """fp32 copies of the conv biases (weights are frozen; cached after the first call)."""
+        cache = getattr(self, "_bias_cache", None)
+        b = self.in_layers[2].bias
+        if cache is None or cache[0].device != b.device:
+            b_out = self.out_layers[3].bias.detach().float()
+            if not isinstance(self.skip_connection, nn.Identity):
+                b_out = b_out + self.skip_connection.bias.detach().float()
+            cache = (b.detach().float().contiguous(), b_out.contiguous())
+            self._bias_cache = cache
+        return cache
 
 
 class AttentionBlock(nn.Module):
@@ -291,6 +330,22 @@ class UNetModel(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
 
+    def _first_bias(self):
+        b = self.input_blocks[0][0].bias
+        c = getattr(self, "_first_bias_cache", None)
+        if c is None or c.device != b.device:
+            c = b.detach().float().contiguous()
+            self._first_bias_cache = c
+        return c
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        self._first_bias_cache = None
+        for m in self.modules():
+            if isinstance(m, ResBlock):
+                m._bias_cache = None
+        return r
+
     def prepare(self, device="cuda"):
         """Move to the device in the compute dtype (norm affines stay fp32), channels-last conv weights."""
         self.to(device=device, dtype=self.compute_dtype)
@@ -299,13 +354,19 @@ class UNetModel(nn.Module):
 
     def forward(self, x, timesteps, y=None):
         """x: [B,3,H,W] fp32 (or compute dtype), timesteps: [B] -> [B,out_channels,H,W] in the compute dtype."""
+        if not x.is_cuda:
+            raise _lib.NhmcError("the U-Net runs on CUDA only (fused sm_100a epilogues); no CPU fallback")
         dt = self.compute_dtype
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(dt))
         emb_act = F.silu(emb)                                  # the SiLU that opens every emb_layers (unet_ffhq.py:263)
         h = x.to(dt).contiguous(memory_format=torch.channels_last)
         hs = []
-        for module in self.input_blocks:
-            h = module(h, emb_act)
+        for i, module in enumerate(self.input_blocks):
+            if i == 0:
+                conv = module[0]
+                h = _BiasAdd.apply(_conv_nobias(conv, h), None, self._first_bias())
+            else:
+                h = module(h, emb_act)
             hs.append(h)
         h = self.middle_block(h, emb_act)
         for module in self.output_blocks:

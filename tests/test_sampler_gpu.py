@@ -73,9 +73,10 @@ def test_hmc_teacher_forced_against_reference_trace(golden):
         xc = smp.iteration(p.cuda(), u)
         st = smp.chains.read()
         assert abs(st["sigma_y"][0] - sig) < 1e-12
-        prob_ref = min(1.0, float(g["prob"][it])); prob = float(st["prob"][0]); acc = bool(g["accept"][it])
-        band = 0.02 * max(prob_ref, 1e-3) + 1e-6
-        if abs(prob - prob_ref) > band:
+        prob_ref = min(1.0, float(g["prob"][it])); acc = bool(g["accept"][it])
+        dH, dH_ref = float(st["H"][0][1] - st["H"][0][0]), -float(np.log(g["prob"][it]))    # recorded ratio is exp(-dH), unclipped
+        band = 0.03 * max(prob_ref, 1e-3) + 1e-6
+        if abs(dH - dH_ref) > 0.03:
             outliers += 1                             # clip-boundary flip inside the trajectory (see oracle test)
         else:
             if abs(float(u) - prob_ref) > band:
