@@ -261,7 +261,72 @@ def gold_hmc_trace():
          samples=out.detach(), seed=np.array(777))
 
 
+# ---------------------------------------------------------------------------- full hmc_latent() trace
+def gold_hmc_latent_trace():
+    """The REAL hmc_latent (main_sampling_latent.py:623-762) driven with a tiny stand-in LDM."""
+    import types as _t
+    class _Any(_t.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return lambda *a, **kw: 0.0
+    for n in ("omegaconf", "pytorch_lightning", "pytorch_lightning.utilities", "pytorch_lightning.utilities.distributed",
+              "taming", "taming.modules", "taming.modules.vqvae", "taming.modules.vqvae.quantize", "ldm_loader"):
+        if n not in sys.modules:
+            try:
+                __import__(n)
+            except Exception:
+                sys.modules[n] = _Any(n)
+    import main_sampling_latent as msl
+    from algos.unconditional_latent import Unconditional_Latent
+    from oracle.tinynet import TinyLDM
+    msl.config, msl.device = ms.config, torch.device("cpu")
+    ldm = TinyLDM()
+    D, h = 64, 16
+    H = Hfuncs.SuperResolution(3, D, 4, "cpu")
+    sigma_0 = 0.1
+    algo = Unconditional_Latent(ldm, H, sigma_0)
+    g = torch.Generator().manual_seed(41)
+    x_orig = torch.rand(1, 3, D, D, generator=g) * 2 - 1
+    y_0 = H.H(x_orig) + sigma_0 * torch.randn(1, 3 * 16 * 16, generator=g)
+    z = torch.randn(1, 3, h, h, generator=g)
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=sigma_0, sigma_y=0.5, algo="hmc_latent", noise="ddpm",
+                                image_folder="/tmp/nhmc_golden_unused")
+    seq, seq_next = [250, 500, 750], [-1, 250, 500]
+    rec = dict(x_start=[], prob=[], u=[])
+    real_randn_like, real_rand = torch.randn_like, torch.rand
+
+    def randn_like(t, *a, **kw):
+        rec["x_start"].append(t.detach().clone())
+        return real_randn_like(t, *a, **kw)
+
+    def rand(*a, **kw):
+        v = real_rand(*a, **kw)
+        rec["u"].append(float(v))
+        return v
+
+    def rec_min(one, ratio):
+        rec["prob"].append(float(ratio))
+        return min(one, ratio)
+
+    torch.randn_like, torch.rand = randn_like, rand
+    msl.min = rec_min
+    msl.print = lambda *a, **k: None
+    try:
+        torch.manual_seed(778)
+        out = msl.hmc_latent(z, 1, seq, seq_next, algo, opt, y_0, H, x_orig)
+    finally:
+        torch.randn_like, torch.rand = real_randn_like, real_rand
+        del msl.min, msl.print
+    n_it = len(rec["u"])
+    accept = np.array([rec["u"][i] < min(1.0, rec["prob"][i]) for i in range(n_it)])
+    print("hmc_latent trace: iterations", n_it, "accepted", int(accept.sum()), "samples", tuple(out.shape))
+    save("hmc_latent_trace.npz", x_orig=x_orig, y_0=y_0, z_init=z, sigma_0=np.array(sigma_0), sigma_y=np.array(0.5),
+         u=np.array(rec["u"]), prob=np.array(rec["prob"]), accept=accept, x_start=torch.cat(rec["x_start"]),
+         samples=out.detach(), seed=np.array(778))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "ddim", "unet", "hmc_trace"]
+    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "ddim", "unet", "hmc_trace", "hmc_latent_trace"]
     for w in which:
         globals()["gold_" + w]()

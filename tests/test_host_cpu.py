@@ -127,3 +127,26 @@ def test_unet_state_dict_keys_equal_reference_names(golden):
     assert list(sd) == list(shapes)
     assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
     assert sum(int(np.prod(s)) for s in shapes.values()) == int(golden("unet_ffhq10m_meta.npz")["nparam"])
+
+
+def test_cli_flag_surface_matches_reference():
+    """Same flags and defaults as main_sampling.get_parser (main_sampling.py:923-1015); unknown flags ignored."""
+    from nhmc_b200 import cli
+    p = cli.get_parser()
+    opt, unknown = p.parse_known_args("--ni --dataset ffhq --doc ffhq --algo hmc --timesteps 3 --deg inpaint_random "
+                                      "--sigma_0 0.05 -i exp/x --tau 1.0 --epsilon 0.05".split())
+    assert unknown == ["--ni", "--doc", "ffhq"]
+    assert (opt.seed, opt.tau, opt.epsilon, opt.m, opt.sigma_y, opt.num_timesteps, opt.timesteps) == (5678, 1.0, 0.05, 1.0, 0.5, 1000, 3)
+    assert opt.image_folder == "exp/x" and opt.noise == "ddpm" and opt.chains == 1
+    d = p.parse_known_args(["--deg", "sr4", "--sigma_0", "0.05"])[0]
+    assert d.dataset == "celeba" and d.algo == "resample" and d.timesteps == 10 and d.subset_start == -1
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "config_ffhq.yml")))
+    ns = cli.dict2namespace(cfg)
+    assert ns.model_type == "ffhq" and ns.data.image_size == 256 and ns.diffusion.beta_end == 0.02
+    assert cfg["model"]["num_channels"] == 128 and cfg["model"]["attention_resolutions"] == 16 and cfg["sampling"]["batch_size"] == 1
+    opt2 = types.SimpleNamespace(deg="sr4", sigma_0=0.05)
+    H, s0, deg = cli.prepare_measurement(opt2, ns, "cpu")
+    assert s0 == 0.1 and opt2.sigma_0 == 0.1 and H.meas_size() == 3 * 64 * 64       # sigma_0 doubled (main_sampling.py:348)
+    with pytest.raises(SystemExit):
+        cli.prepare_measurement(types.SimpleNamespace(deg="color", sigma_0=0.05), ns, "cpu")

@@ -195,3 +195,38 @@ def test_hmc_schedule_replay(golden):
         n += 1
     assert sch.done() and n == len(g["accept"]) and sch.accepted == 100 and collected == 20
     assert abs(sch.sigma_y - float(g["sigma_0"])) < 1e-12
+
+
+def test_latent_schedule_and_teacher_forced_iterations(golden):
+    """hmc_latent: the oracle under the recorded draws reproduces the real function's dH / accepts, and the
+    LatentSchedule replay reproduces its collected-sample count (one accept behind, main_sampling_latent.py:705-713)."""
+    from oracle.tinynet import TinyLDM
+    g = golden("hmc_latent_trace.npz")
+    ldm = TinyLDM()
+    ac, acp = osch.ldm_alphas_cumprod()
+    assert torch.equal(ac, ldm.alphas_cumprod)
+    np.testing.assert_allclose(ac[[250, 500, 750]].numpy(), [0.5084, 0.1149, 0.0083], atol=2e-4)      # SURVEY.md 3.3
+    tab = osch.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev)
+    op = oops.SuperResolution(3, 64, 4)
+    y = T(g["y_0"])
+    seq, seq_next = [250, 500, 750], [-1, 250, 500]
+    sch = osch.LatentSchedule(1.0, 0.05, float(g["sigma_0"]), float(g["sigma_y"]))
+    eval_fn = lambda z_: ohmc.grad_eval(z_, ohmc.latent_eps_net(ldm), tab, seq, seq_next, op, y,
+                                        decode=ldm.differentiable_decode_first_stage)
+    torch.manual_seed(int(g["seed"]))
+    outliers = collected = 0
+    for it in range(len(g["u"])):
+        z = T(g["x_start"][it:it + 1])
+        p = torch.randn_like(z)
+        u = torch.rand(1)
+        acc = bool(g["accept"][it])
+        if it < 24:
+            sig, eps_now = sch.begin_iteration()
+            out = ohmc.hmc_iteration(z, p, None, sig, eps_now, sch.L, 1.0, eval_fn)
+            dH, dH_ref = float(out["H1"] - out["H0"]), -float(np.log(max(g["prob"][it], 1e-300)))
+            if abs(dH - dH_ref) > 0.03 * max(1.0, abs(dH_ref)):
+                outliers += 1
+        collected += bool(sch.end_iteration(acc))
+    assert outliers <= 2, outliers
+    assert sch.done() and sch.accepted == int(g["accept"].sum())
+    assert collected == g["samples"].shape[0]

@@ -181,3 +181,62 @@ def test_cuda_graph_replay_matches_eager(golden):
     np.testing.assert_allclose(xg.numpy(), xe.numpy(), atol=1e-5)
     assert stg["accepted"].tolist() == ste["accepted"].tolist() and stg["iters"].tolist() == [3, 3]
     np.testing.assert_allclose(stg["H"], ste["H"], rtol=1e-5)
+
+
+def test_hmc_latent_teacher_forced_against_reference_trace(golden):
+    """hmc_latent on the GPU kernels vs the recorded run of the real main_sampling_latent.hmc_latent."""
+    import nhmc_b200
+    from nhmc_b200 import _lib, operators as P, sampler, schedule
+    from oracle.tinynet import TinyLDM
+    g = golden("hmc_latent_trace.npz")
+    ldm = TinyLDM().cuda()
+    op = P.SuperResolution(3, 64, 4, "cuda")
+    op.set_clamp(False)
+    table = schedule.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev)
+    steps = schedule.ddim_steps(table, SEQ, SEQ_NEXT)
+    z0 = T(g["x_start"][0:1]).cuda()
+    ev = sampler.GradEvaluator(lambda z, t: ldm.apply_model(z, t, None), steps, op, T(g["y_0"]).cuda(), z0, net_grad=False,
+                               decode=ldm.differentiable_decode_first_stage)
+    smp = sampler.HMCSampler(z0, ev, 1.0, 0.05, float(g["sigma_0"]), sched=_lib.SCHED_LATENT, sigma_y=float(g["sigma_y"]), n_slots=10)
+    sch = osch.LatentSchedule(1.0, 0.05, float(g["sigma_0"]), float(g["sigma_y"]))
+    torch.manual_seed(int(g["seed"]))
+    outliers = 0
+    for it in range(len(g["u"])):
+        zs = T(g["x_start"][it:it + 1])
+        p = torch.randn_like(zs)
+        u = torch.rand(1)
+        acc = bool(g["accept"][it])
+        smp.x.copy_(zs)
+        st = smp.chains.read()
+        st["epoch"], st["rejected"], st["epsilon"], st["tau"], st["sigma_y"] = sch.epoch, sch.rejected, sch.epsilon, sch.tau, sch.sigma_y
+        st["accepted"] = sch.accepted
+        smp.chains.write(st)
+        smp.iteration(p.cuda(), u)
+        st = smp.chains.read()
+        prob_ref = min(1.0, float(g["prob"][it]))
+        dH, dH_ref = float(st["H"][0][1] - st["H"][0][0]), -float(np.log(max(g["prob"][it], 1e-300)))
+        if abs(dH - dH_ref) > 0.03 * max(1.0, abs(dH_ref)):
+            outliers += 1
+        elif abs(float(u) - prob_ref) > 0.03 * max(prob_ref, 1e-3) + 1e-6:
+            assert bool(st["accept"][0]) == acc, it
+        sch.end_iteration(acc)
+    assert outliers <= 4, outliers
+    assert not bool(smp.chains.read()["active"][0])
+
+
+def test_hmc_latent_drop_in_call(golden):
+    import nhmc_b200
+    from nhmc_b200 import operators as P
+    from oracle.tinynet import TinyLDM
+    g = golden("hmc_latent_trace.npz")
+    ldm = TinyLDM().cuda()
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=float(g["sigma_0"]), sigma_y=float(g["sigma_y"]))
+    algo = types.SimpleNamespace(model=ldm, cls_fn=None)
+    torch.manual_seed(778)
+    smp = nhmc_b200.hmc_latent(T(g["z_init"]).cuda(), 1, SEQ, SEQ_NEXT, algo, opt, T(g["y_0"]).cuda(),
+                               P.SuperResolution(3, 64, 4, "cuda"), T(g["x_orig"]).cuda(), image_size=64, return_sampler=True)
+    st = smp.chains.read()
+    assert int(st["epoch"][0]) == 70 and int(st["iters"][0]) == 70 and not bool(st["active"][0])
+    out = smp.collected()[0]
+    assert out.shape[1:] == (3, 16, 16) and out.shape[0] == int(st["n_collected"][0]) <= 10
+    assert torch.isfinite(smp.x).all()
