@@ -17,6 +17,9 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # parity is stated for fp32 arithmetic: no TF32 in the score-network / decoder convolutions
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:
