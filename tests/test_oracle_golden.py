@@ -220,11 +220,13 @@ def test_latent_schedule_and_teacher_forced_iterations(golden):
         p = torch.randn_like(z)
         u = torch.rand(1)
         acc = bool(g["accept"][it])
-        if it < 24:
+        if it < 70:
             sig, eps_now = sch.begin_iteration()
             out = ohmc.hmc_iteration(z, p, None, sig, eps_now, sch.L, 1.0, eval_fn)
             dH, dH_ref = float(out["H1"] - out["H0"]), -float(np.log(max(g["prob"][it], 1e-300)))
-            if abs(dH - dH_ref) > 0.03 * max(1.0, abs(dH_ref)):
+            if g["prob"][it] == 0.0:                     # exp(-dH) underflowed in the reference's fp32: dH > ~103
+                outliers += int(dH < 80.0)
+            elif abs(dH - dH_ref) > 0.03 * max(1.0, abs(dH_ref)):
                 outliers += 1
         collected += bool(sch.end_iteration(acc))
     assert outliers <= 2, outliers
