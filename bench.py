@@ -229,6 +229,7 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
         with open(args.torch_profile, "w") as f:
             f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+        prof_t.export_chrome_trace(args.torch_profile + ".trace.json")     # per-launch durations + grid sizes, in situ
 
     # ---- end-to-end: the same step through the public API with HOST buffers ----
     e2e = None

@@ -201,7 +201,9 @@ int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const f
  *   NHMC_GN_SILU  : y = silu(gn(x))                    (in_layers / out)
  *   NHMC_GN_FILM_SILU : y = silu(gn(x)*(1+scale)+shift) (out_layers, use_scale_shift_norm)
  * x, y: [B, C, HW] contiguous (NCHW) or channels-last [B, HW, C] (layout flag), dtype
- * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32 [B, C] (FiLM only); in_bias fp32 [C] or
+ * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32 rows of C values, sample b at
+ * scale + b*film_stride (FiLM only; film_stride 0 means C: this lets both point into one
+ * [B, 2C] embedding projection, unet_ffhq.py:319-321, without a split copy); in_bias fp32 [C] or
  * NULL: the tensor that is normalised is x + in_bias[c] (the bias of the convolution that
  * produced x, folded in here instead of a separate broadcast-add pass).
  * stats_out: fp32 [B, G, 2] (mean, rstd) saved for the backward.
@@ -212,16 +214,30 @@ int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const f
 #define NHMC_LAYOUT_NCHW 0
 #define NHMC_LAYOUT_NHWC 1
 int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
-                const float* beta, const float* scale, const float* shift, const float* in_bias,
-                float* stats_out,
+                const float* beta, const float* scale, const float* shift, int64_t film_stride,
+                const float* in_bias, float* stats_out,
                 int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream);
 /* dx (and optionally dscale/dshift [B,C] fp32) given dy; weights are frozen on this path, so
- * no dgamma/dbeta. */
+ * no dgamma/dbeta.  dx_add (nullable, same dtype/layout as dx, channels-last only): a tensor added to
+ * dx in the same pass -- the gradient arriving through the ResBlock's skip branch
+ * (unet_ffhq.py:327), which autograd would otherwise add with a separate read-read-write pass.
+ *
+ * Channels-last execution: when one sample's slab fits in the shared memory of the chip (every
+ * FFHQ-256 site except the backward of the two 256-channel 256x256 sites), ONE kernel reads the
+ * tensor once into shared memory (TMA bulk copies), reduces, synchronises the CTAs of a sample
+ * through a per-sample arrival counter and normalises out of shared memory: HBM traffic equals
+ * the algorithmic bytes.  Otherwise a statistics kernel + an apply kernel (two reads). */
 int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                 const float* gamma, const float* beta, const float* scale, const float* shift,
-                const float* in_bias, const float* stats, float* dscale, float* dshift, int batch,
-                int channels,
-                int64_t hw, int groups, nhmc_stream_t stream);
+                int64_t film_stride, const float* in_bias, const float* stats, float* dscale, float* dshift,
+                const void* dx_add, int batch, int channels, int64_t hw, int groups,
+                nhmc_stream_t stream);
+/* 0 unless a per-sample barrier of the shared-memory-resident GroupNorm path ever timed out on the
+ * current device (synchronises; for tests and debugging, not for the hot loop). */
+int nhmc_gn_check(void);
+/* Switch the shared-memory-resident channels-last path on (default) or off (statistics + apply
+ * kernels); returns the previous setting.  For A/B measurements and tests. */
+int nhmc_gn_set_resident(int on);
 
 /* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of
  * logits [rows, T] (dtype f32/bf16/f16), computed in fp32; logits are multiplied by

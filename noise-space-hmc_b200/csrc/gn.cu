@@ -10,11 +10,11 @@
 // per-channel affine (rstd*gamma*(1+scale), ...) is computed once per thread.  Statistics: fp32
 // per-thread partials -> shared-memory ordered reduce -> fp64 per-(sample, group) finish by the last CTA
 // (deterministic).  Weights are frozen on this path (sampling), so backward produces dx only.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nhmc {
-
-constexpr int kGnMaxBlocks = 256;  // CTAs per sample in the statistics kernels
 
 template <typename T> struct VecOf { static constexpr int N = 16 / sizeof(T); };
 
@@ -93,6 +93,7 @@ __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f
 
 struct GnArgs {
   const void* x; const void* dy; void* out;
+  const void* add;   // backward: optional tensor added to dx in the same pass (skip-branch gradient), or null
   const float* gamma; const float* beta; const float* scale; const float* shift;  // scale/shift: [B,C] fp32 or null
   const float* in_bias;  // [C] fp32 or null: the normalised tensor is x + in_bias[c] (conv bias folded in)
   float* stats;      // [B][G][2]: fwd (mean, rstd)
@@ -100,6 +101,8 @@ struct GnArgs {
   double* partials;  // [B][kGnMaxBlocks][G][2]
   unsigned int* tickets;  // [B]
   int C, G; int64_t HW; float eps;
+  int64_t film_stride;  // elements between two samples' rows of scale / shift (>= C)
+  int b0;            // first sample of this launch (two-kernel path launched per L2-sized group of samples)
   int rows_per_cta_iter;  // pixel rows covered by one CTA pass (channels-last)
   int64_t rows_per_cta;   // pixel rows owned by a CTA (channels-last)
 };
@@ -207,7 +210,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bars[kGnStages];
-  const int b = blockIdx.y, blk = blockIdx.x;
+  const int b = blockIdx.y + a.b0, blk = blockIdx.x;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
@@ -222,8 +225,8 @@ gn_nhwc_stats_kernel(GnArgs a) {
       const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float gam = a.gamma[c], bet = a.beta[c];
-      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
-      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
       ca[i] = rstd * gam * sc;                       // z = ca*x + cb
       cb[i] = (bet - mean * rstd * gam) * sc + sh;
     }
@@ -270,7 +273,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
       const int c = c0 + i, g = c / Cg;
       const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
-      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
       const float t0 = s0[i], t1 = s1[i];
       s0[i] = cgm * t0;
@@ -302,7 +305,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ uint64_t bars[kGnStages];
-  const int b = blockIdx.y, blk = blockIdx.x;
+  const int b = blockIdx.y + a.b0, blk = blockIdx.x;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec;
   const int c0 = cv * V;
@@ -330,8 +333,8 @@ gn_nhwc_apply_kernel(GnArgs a) {
     const int c = c0 + i, g = c / Cg;
     const float mean = g_mean[g] - (a.in_bias ? a.in_bias[c] : 0.0f), rstd = g_rstd[g];
     const float gam = a.gamma[c], bet = a.beta[c];
-    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
-    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
     ca[i] = rstd * gam * sc;
     cb[i] = (bet - mean * rstd * gam) * sc + sh;
     k1[i] = k2[i] = k3[i] = 0.f;
@@ -351,6 +354,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
   const char* xsrc = reinterpret_cast<const char*>(a.x) + base;
   const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + base : nullptr;
   char* dst = reinterpret_cast<char*>(a.out) + base;
+  const char* asrc = (PHASE == 1 && a.add) ? reinterpret_cast<const char*>(a.add) + base : nullptr;
   stream_ranges<PHASE == 1 ? 2 : 1>(xsrc, dsrc, (r_end - r_begin) * row_bytes, dyn, bars,
       [&](int64_t off, const uint4& rx, const uint4& rd) {
         float xv[V], ov[V];
@@ -365,6 +369,12 @@ gn_nhwc_apply_kernel(GnArgs a) {
           for (int i = 0; i < V; ++i) {
             const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
+          }
+          if (asrc) {
+            float ad[V];
+            unpack<T>(ld_raw(asrc + off), ad);
+#pragma unroll
+            for (int i = 0; i < V; ++i) ov[i] += ad[i];
           }
         }
         store_vec<T>(reinterpret_cast<T*>(dst + off), ov);
@@ -385,6 +395,291 @@ gn_nhwc_apply_kernel(GnArgs a) {
         a.stats[((int64_t)b * a.G + g) * 2 + 1] = g_rstd[g];
       }
       acc[0] = 0.0; acc[1] = 0.0;
+    }
+  }
+}
+
+// ============================== channels-last, shared-memory resident ========================
+// ONE kernel, ONE read and ONE write of the tensor (the algorithmic minimum): a CTA pulls its contiguous
+// slab of pixels into shared memory with TMA bulk copies (the whole slab is in flight at once), reduces
+// its per-group partial sums while the chunks land, publishes them with fp64 atomics, waits until every
+// CTA of the same SAMPLE has done so (per-sample arrival counter), then normalises straight out of shared
+// memory.  Nothing is read twice, no second launch.
+//
+// Forward progress without a cooperative launch: a CTA takes its logical index from a global ticket when it
+// STARTS, so logical indices follow start order; the CTAs of the lowest unfinished sample are therefore
+// either running or next in line, and the host sizes slabs so that one sample's CTAs always fit on the chip
+// together (occupancy API).  The spin is bounded anyway: on timeout an error flag is raised, never a hang.
+constexpr int kResChunks = 16;   // mbarriers per CTA (chunks of the slab)
+
+struct GnResArgs {
+  GnArgs a;
+  int nb;                   // CTAs per sample
+  int chunk_passes;         // passes (blockDim * 16 B) per chunk
+  unsigned int total_ctas;
+  unsigned int* ticket;     // [1]   start-order ticket, wraps to 0 by itself
+  unsigned int* arrive;     // [B]   CTAs of the sample whose partial sums are published
+  unsigned int* done;       // [B]   CTAs of the sample that have read the totals (wraps to 0 by itself)
+  unsigned int* err;        // [1]   set to 1 if a wait timed out
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Group totals of per-channel partial sums (s0, s1) of this CTA -> g_acc[g][0..1] (fp64), then -- when the
+// sample spans several CTAs -- through the global accumulators and the per-sample barrier.  Ends with the
+// sample-wide totals in g_acc, visible to every thread.
+template <int V>
+__device__ __forceinline__ void group_totals(const float (&s0)[V], const float (&s1)[V], const GnResArgs& r, int b,
+                                             int c0, int cvec, int rows, float4* part, double (*g_acc)[2]) {
+  const GnArgs& a = r.a;
+  const int Cg = a.C / a.G;
+  const int g0 = c0 / Cg;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);      // (slot0.s0, slot0.s1, slot1.s0, slot1.s1)
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    if ((c0 + i) / Cg == g0) { q.x += s0[i]; q.y += s1[i]; } else { q.z += s0[i]; q.w += s1[i]; }
+  }
+  part[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < a.G) {
+    const int g = threadIdx.x;
+    const int cv_lo = (g * Cg) / V, cv_hi = ((g + 1) * Cg - 1) / V;
+    double t0 = 0.0, t1 = 0.0;
+    for (int cv = cv_lo; cv <= cv_hi; ++cv) {
+      const int j = g - (cv * V) / Cg;             // 0 or 1 (host guarantees a thread spans <= 2 groups)
+      for (int pr = 0; pr < rows; ++pr) {
+        const float4 t = part[pr * cvec + cv];
+        t0 += (double)(j ? t.z : t.x); t1 += (double)(j ? t.w : t.y);
+      }
+    }
+    if (r.nb > 1) {
+      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
+      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
+      __threadfence();
+    } else {
+      g_acc[g][0] = t0; g_acc[g][1] = t1;
+    }
+  }
+  __syncthreads();
+  if (r.nb > 1) {
+    if (threadIdx.x == 0) {
+      atomicAdd(r.arrive + b, 1u);
+      const long long t_start = clock64();
+      while (ld_acquire_u32(r.arrive + b) < (unsigned int)r.nb) {
+        __nanosleep(64);
+        if (clock64() - t_start > (1ll << 31)) { atomicExch(r.err, 1u); break; }   // ~1 s: never hang the device
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < a.G) {
+      const int g = threadIdx.x;
+      g_acc[g][0] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2);
+      g_acc[g][1] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
+    }
+    __syncthreads();
+    // the last CTA of the sample to have read the totals re-zeroes them for the next call on this stream
+    if (threadIdx.x == 0) {
+      const bool last = atomicInc(r.done + b, (unsigned int)(r.nb - 1)) == (unsigned int)(r.nb - 1);
+      if (last) {
+        for (int g = 0; g < a.G; ++g) { a.partials[((int64_t)b * 64 + g) * 2] = 0.0; a.partials[((int64_t)b * 64 + g) * 2 + 1] = 0.0; }
+        r.arrive[b] = 0u;
+      }
+    }
+  }
+}
+
+// PHASE 0: y = act(gn(x + in_bias));  PHASE 1: dx = gn_bwd(dy) (+ add)
+template <typename T, int MODE, int PHASE>
+__global__ void __launch_bounds__(256, PHASE == 1 ? 3 : 4)
+gn_nhwc_resident_kernel(const GnResArgs r) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int NSRC = PHASE == 1 ? 2 : 1;
+  const GnArgs& a = r.a;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ uint64_t bars[kResChunks];
+  __shared__ float4 part[256];
+  __shared__ double g_acc[32][2];      // the resident path takes G <= 32 (static shared memory is part of the budget)
+  __shared__ float g_c0[32], g_c1[32];
+  __shared__ unsigned int s_lid;
+  if (threadIdx.x == 0) {
+    s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
+    for (int k = 0; k < kResChunks; ++k) mbar_init(bars + k, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int b = (int)(s_lid / (unsigned int)r.nb), blk = (int)(s_lid % (unsigned int)r.nb);
+  const int cvec = a.C / V;
+  const int cv = threadIdx.x % cvec, rows = blockDim.x / cvec;
+  const int c0 = cv * V;
+  const int Cg = a.C / a.G;
+  const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
+  int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+  const int64_t row_bytes = (int64_t)a.C * sizeof(T);
+  const int64_t base = ((int64_t)b * a.HW + r_begin) * row_bytes;
+  const unsigned total = r_end > r_begin ? (unsigned)((r_end - r_begin) * row_bytes) : 0u;
+  const unsigned pass_bytes = blockDim.x * 16u;
+  const unsigned chunk_bytes = (unsigned)r.chunk_passes * pass_bytes;
+  const unsigned n_pass = (total + pass_bytes - 1) / pass_bytes;
+  const unsigned slab = (unsigned)(((a.rows_per_cta * row_bytes + 127) / 128) * 128);   // dy lives behind x
+  unsigned char* sx = dyn;
+  unsigned char* sd = dyn + slab;
+  const char* xsrc = reinterpret_cast<const char*>(a.x) + base;
+  const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + base : nullptr;
+  if (threadIdx.x == 0) {
+    for (unsigned k = 0, off = 0; off < total; ++k, off += chunk_bytes) {
+      const unsigned bytes = total - off < chunk_bytes ? total - off : chunk_bytes;
+      mbar_expect_tx(bars + k, bytes * NSRC);
+      bulk_g2s(sx + off, xsrc + off, bytes, bars + k);
+      if (NSRC == 2) bulk_g2s(sd + off, dsrc + off, bytes, bars + k);
+    }
+  }
+  const unsigned my_off = threadIdx.x * 16u;
+  float s0[V], s1[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+
+  if (PHASE == 0) {
+    // ---- statistics while the chunks land ----
+    for (unsigned ps = 0; ps < n_pass; ++ps) {
+      if (ps % (unsigned)r.chunk_passes == 0) mbar_wait(bars + ps / (unsigned)r.chunk_passes, 0);
+      const unsigned o = ps * pass_bytes + my_off;
+      if (o < total) {
+        float xv[V];
+        unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+      }
+    }
+    if (a.in_bias) {
+      const float cnt = my_off < total ? (float)((total - my_off + pass_bytes - 1) / pass_bytes) : 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float bia = a.in_bias[c0 + i];
+        s1[i] = s1[i] + 2.0f * bia * s0[i] + cnt * bia * bia;
+        s0[i] = s0[i] + cnt * bia;
+      }
+    }
+    group_totals<V>(s0, s1, r, b, c0, cvec, rows, part, g_acc);
+    if (threadIdx.x < a.G) {
+      const int g = threadIdx.x;
+      const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
+      const double m = g_acc[g][0] * inv_n;
+      double var = g_acc[g][1] * inv_n - m * m; if (var < 0.0) var = 0.0;
+      g_c0[g] = (float)m; g_c1[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+      if (blk == 0) {
+        a.stats[((int64_t)b * a.G + g) * 2] = g_c0[g];
+        a.stats[((int64_t)b * a.G + g) * 2 + 1] = g_c1[g];
+      }
+    }
+    __syncthreads();
+    float ca[V], cb[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = g_c0[g] - (a.in_bias ? a.in_bias[c] : 0.0f), rstd = g_c1[g];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
+      ca[i] = rstd * gam * sc;
+      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+    }
+    char* dst = reinterpret_cast<char*>(a.out) + base;
+#pragma unroll 4
+    for (unsigned ps = 0; ps < n_pass; ++ps) {
+      const unsigned o = ps * pass_bytes + my_off;
+      if (o < total) {
+        float xv[V], ov[V];
+        unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+        store_vec<T>(reinterpret_cast<T*>(dst + o), ov);
+      }
+    }
+  } else {
+    // ---- backward: d = dy * act'(z) replaces dy in shared memory; t0 = sum d, t1 = sum d*x per channel ----
+    float ca[V], cb[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
+      ca[i] = rstd * gam * sc;
+      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+    }
+    for (unsigned ps = 0; ps < n_pass; ++ps) {
+      if (ps % (unsigned)r.chunk_passes == 0) mbar_wait(bars + ps / (unsigned)r.chunk_passes, 0);
+      const unsigned o = ps * pass_bytes + my_off;
+      if (o < total) {
+        float xv[V], dv[V];
+        unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+        unpack<T>(*reinterpret_cast<const uint4*>(sd + o), dv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          dv[i] = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+          s0[i] += dv[i]; s1[i] = fmaf(dv[i], xv[i], s1[i]);
+        }
+        if (MODE != NHMC_GN_PLAIN) store_vec<T>(reinterpret_cast<T*>(sd + o), dv);   // own 16 bytes: no sync needed
+      }
+    }
+    float k1[V], k2[V], k3[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
+      const float t0 = s0[i], t1 = s1[i];
+      s0[i] = cgm * t0;
+      s1[i] = cgm * rstd * (t1 - mean * t0);
+      k1[i] = rstd * cgm; k2[i] = mean; k3[i] = rstd;   // finished below once the group means are known
+    }
+    group_totals<V>(s0, s1, r, b, c0, cvec, rows, part, g_acc);
+    if (threadIdx.x < a.G) {
+      const int g = threadIdx.x;
+      const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
+      g_c0[g] = (float)(g_acc[g][0] * inv_n); g_c1[g] = (float)(g_acc[g][1] * inv_n);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      // dx = rstd*(du - m1 - u*m2) = k1*d + k2*x + k3
+      const int g = (c0 + i) / Cg;
+      const float m1 = g_c0[g], m2 = g_c1[g], mean = k2[i], rstd = k3[i];
+      k2[i] = -rstd * rstd * m2;
+      k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
+    }
+    char* dst = reinterpret_cast<char*>(a.out) + base;
+    const char* asrc = a.add ? reinterpret_cast<const char*>(a.add) + base : nullptr;
+    constexpr int U = 4;
+    for (unsigned ps0 = 0; ps0 < n_pass; ps0 += U) {
+      uint4 av[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned o = (ps0 + u) * pass_bytes + my_off;
+        av[u] = make_uint4(0, 0, 0, 0);
+        if (asrc && o < total) av[u] = ld_raw(asrc + o);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned o = (ps0 + u) * pass_bytes + my_off;
+        if (o < total) {
+          float xv[V], dv[V], ov[V], ad[V];
+          unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+          unpack<T>(*reinterpret_cast<const uint4*>(sd + o), dv);
+          unpack<T>(av[u], ad);
+#pragma unroll
+          for (int i = 0; i < V; ++i) ov[i] = fmaf(k1[i], dv[i], fmaf(k2[i], xv[i], k3[i])) + ad[i];
+          store_vec<T>(reinterpret_cast<T*>(dst + o), ov);
+        }
+      }
     }
   }
 }
@@ -426,8 +721,8 @@ gn_nchw_kernel(GnArgs a) {
   }
   auto coef = [&](int c, float& ca, float& cb, float& cgm) {
     const float gam = a.gamma[c], bet = a.beta[c];
-    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.C + c] : 1.0f;
-    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.C + c] : 0.0f;
+    const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+    const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
     ca = rstd * gam * sc; cb = (bet - mean * rstd * gam) * sc + sh; cgm = gam * sc;
   };
   if (PHASE == 0) {
@@ -462,7 +757,7 @@ gn_nchw_kernel(GnArgs a) {
 // GN scratch (partials + tickets) lives in a library-static device buffer per device: it is tiny,
 // self-resetting, and keeping it here spares every caller a workspace argument on the hottest
 // U-Net path.  (The header's "library allocates nothing" covers tensors; this is documented there.)
-struct GnScratch { double* partials; unsigned int* tickets; float* bstats; int batch; };
+struct GnScratch { double* partials; unsigned int* tickets; float* bstats; unsigned int* res; int batch; };  // res: [ticket, err, pad, pad, arrive[nb], done[nb]]
 static GnScratch g_scratch[16] = {};
 
 static int get_scratch(int batch, int G, GnScratch& out) {
@@ -472,13 +767,15 @@ static int get_scratch(int batch, int G, GnScratch& out) {
   GnScratch& s = g_scratch[dev];
   if (s.batch < batch || !s.partials) {
     // grow-only; allocation happens outside any stream capture (first call) -- warm up before capturing
-    if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); }
+    if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); cudaFree(s.res); }
     const int nb = batch < 64 ? 64 : batch;
     if (int e = cuda_status(cudaMalloc(&s.partials, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMemset(s.partials, 0, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMalloc(&s.tickets, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMalloc(&s.bstats, (size_t)nb * 64 * 2 * sizeof(float)), "gn scratch")) return e;
     if (int e = cuda_status(cudaMemset(s.tickets, 0, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMalloc(&s.res, (size_t)(4 + 2 * nb) * sizeof(unsigned int)), "gn scratch")) return e;
+    if (int e = cuda_status(cudaMemset(s.res, 0, (size_t)(4 + 2 * nb) * sizeof(unsigned int)), "gn scratch")) return e;
     s.batch = nb;
   }
   (void)G;
@@ -486,16 +783,115 @@ static int get_scratch(int batch, int G, GnScratch& out) {
   return NHMC_OK;
 }
 
+struct DevInfo { int sms, smem_sm, smem_optin, smem_reserved; bool ok; };
+static DevInfo dev_info() {
+  static DevInfo info[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  DevInfo& d = info[dev];
+  if (!d.ok) {
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+    d.ok = d.sms > 0;
+  }
+  return d;
+}
+
+static int g_resident_mode = -1;   // NHMC_GN_RESIDENT=0 / nhmc_gn_set_resident(0) force the two-kernel path (A/B measurements, tests)
+static int resident_mode() {
+  if (g_resident_mode < 0) { const char* e = getenv("NHMC_GN_RESIDENT"); g_resident_mode = (e && e[0] == '0') ? 0 : 1; }
+  return g_resident_mode;
+}
+
+// Returns NHMC_OK after launching, NHMC_ERR_UNSUPPORTED when the shape does not fit the resident scheme
+// (the caller then takes the two-kernel path).
 template <typename T, int MODE, int PHASE>
-static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
+static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, int threads, cudaStream_t st) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int NSRC = PHASE == 1 ? 2 : 1;
+  if (!resident_mode() || threads > 256 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  const int Cg = a0.C / a0.G, cvec = a0.C / V;
+  for (int cv = 0; cv < cvec; ++cv)
+    if ((cv * V + V - 1) / Cg - (cv * V) / Cg > 1) return NHMC_ERR_UNSUPPORTED;   // a thread may span at most 2 groups
+  const DevInfo d = dev_info();
+  if (!d.ok) return NHMC_ERR_UNSUPPORTED;
+  auto kern = gn_nhwc_resident_kernel<T, MODE, PHASE>;
+  static int static_smem = -1;   // per instantiation
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return NHMC_ERR_UNSUPPORTED; }
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
+      cudaGetLastError(); return NHMC_ERR_UNSUPPORTED;
+    }
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int64_t row_bytes = (int64_t)a0.C * sizeof(T);
+  const int64_t pass_bytes = (int64_t)threads * 16;
+  // Single wave only: every CTA of the launch must be on the chip at once (k CTAs per SM).  Larger tensors go
+  // through the statistics + apply kernels, whose second read is served by the L2 for what still fits there
+  // (measured in situ: the resident scheme loses once a launch needs several waves, because the per-sample
+  // barrier then serialises load -> reduce -> store phases that the two-kernel path overlaps).
+  for (int k = 4; k >= 1; --k) {
+    int64_t dyn_limit = d.smem_sm / k - d.smem_reserved;
+    if (dyn_limit > d.smem_optin) dyn_limit = d.smem_optin;
+    dyn_limit -= static_smem;
+    const int64_t slab_limit = (dyn_limit / NSRC) & ~(int64_t)127;
+    if (slab_limit < row_bytes) continue;
+    int64_t nb = ((int64_t)k * d.sms) / batch;                    // CTAs per sample that keep the launch in one wave
+    if (nb < 1) continue;
+    int64_t rows_per_cta = (a0.HW + nb - 1) / nb;
+    if (rows_per_cta * row_bytes < 8192) rows_per_cta = (8192 + row_bytes - 1) / row_bytes;   // never below 8 KiB per CTA
+    if (rows_per_cta > a0.HW) rows_per_cta = a0.HW;
+    if (rows_per_cta * row_bytes > slab_limit) continue;
+    nb = (a0.HW + rows_per_cta - 1) / rows_per_cta;
+    const int64_t slab = ((rows_per_cta * row_bytes + 127) / 128) * 128;
+    const size_t dyn = (size_t)slab * NSRC;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, dyn) != cudaSuccess) { cudaGetLastError(); continue; }
+    if ((int64_t)occ * d.sms < nb * batch) continue;
+    GnResArgs r{};
+    r.a = a0;
+    r.a.rows_per_cta = rows_per_cta;
+    r.nb = (int)nb;
+    const int64_t n_pass = (rows_per_cta * row_bytes + pass_bytes - 1) / pass_bytes;
+    r.chunk_passes = (int)((n_pass + kResChunks - 1) / kResChunks);
+    r.total_ctas = (unsigned int)(nb * batch);
+    r.ticket = s.res; r.err = s.res + 1; r.arrive = s.res + 4; r.done = s.res + 4 + s.batch;
+    kern<<<r.total_ctas, threads, dyn, st>>>(r);
+    return NHMC_LAUNCH_CHECK();
+  }
+  return NHMC_ERR_UNSUPPORTED;
+}
+
+template <typename T, int MODE, int PHASE>
+static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
   const int cvec = a.C / V;
   int rows = 256 / cvec; if (rows < 1) rows = 1;
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
-  // chunking: aim at ~4 CTAs per SM over the whole batch, between 32 KiB and 256 KiB of input per CTA
+  {
+    const int e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
+    if (e != NHMC_ERR_UNSUPPORTED) return e;
+  }
+  // Samples are processed in groups whose working set (inputs + output) stays inside the L2, so that the apply
+  // kernel's re-read of what the statistics kernel just streamed is an L2 hit, not a second trip to HBM.
   const int64_t bytes_per_row = (int64_t)a.C * sizeof(T);
-  int64_t target = (int64_t)batch * a.HW * bytes_per_row / (kSMs * 4);
+  const int64_t sample_bytes = a.HW * bytes_per_row;
+  static int64_t group_bytes = -1;
+  if (group_bytes < 0) { const char* e = getenv("NHMC_GN_GROUP_MB"); group_bytes = (e ? atoll(e) : 0) << 20; }
+  int gsz = batch;
+  if (group_bytes > 0) {
+    const int64_t per_sample = sample_bytes * (PHASE == 1 ? 3 : 2);
+    gsz = (int)(group_bytes / per_sample);
+    if (gsz < 1) gsz = 1;
+    if (gsz > batch) gsz = batch;
+  }
+  // chunking: aim at ~4 CTAs per SM over the group, between 32 KiB and 256 KiB of input per CTA
+  int64_t target = (int64_t)gsz * sample_bytes / (kSMs * 4);
   if (target < 32768) target = 32768;
   if (target > 262144) target = 262144;
   int64_t rows_per_cta = (target + bytes_per_row - 1) / bytes_per_row;
@@ -503,7 +899,6 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
   int64_t nblk = (a.HW + rows_per_cta - 1) / rows_per_cta;
   a.rows_per_cta = rows_per_cta;
   a.rows_per_cta_iter = rows;
-  const dim3 grid((unsigned)nblk, batch);
   const size_t ring = (size_t)kGnStages * (PHASE == 1 ? 2 : 1) * kGnPasses * threads * 16;
   const size_t red = (size_t)rows * a.C * 2 * sizeof(float);
   const size_t smem_stats = ring > red ? ring : red;
@@ -514,25 +909,30 @@ static int run_nhwc(GnArgs a, int batch, cudaStream_t st) {
     attr_done = true;
   }
   NHMC_CHECK_ARG(smem_stats <= 160 * 1024, "GroupNorm shared-memory ring too large");
-  gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, smem_stats, st>>>(a);
-  gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, ring, st>>>(a);
+  for (int b0 = 0; b0 < batch; b0 += gsz) {
+    const dim3 grid((unsigned)nblk, (unsigned)(batch - b0 < gsz ? batch - b0 : gsz));
+    a.b0 = b0;
+    gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, smem_stats, st>>>(a);
+    gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, ring, st>>>(a);
+  }
   return NHMC_LAUNCH_CHECK();
 }
 
 template <typename T, int MODE, int PHASE>
-static int run_any(int layout, GnArgs a, int batch, cudaStream_t st) {
-  if (layout == NHMC_LAYOUT_NHWC) return run_nhwc<T, MODE, PHASE>(a, batch, st);
+static int run_any(int layout, GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
+  if (layout == NHMC_LAYOUT_NHWC) return run_nhwc<T, MODE, PHASE>(a, s, batch, st);
+  NHMC_CHECK_ARG(!a.add, "dx_add needs the channels-last layout");
   gn_nchw_kernel<T, MODE, PHASE><<<dim3(a.G, batch), 256, 0, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
 
 template <int PHASE>
-static int dispatch(int mode, int layout, int dtype, GnArgs a, int batch, cudaStream_t st) {
+static int dispatch(int mode, int layout, int dtype, GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
 #define GN_CASE(T)                                                                      \
   switch (mode) {                                                                       \
-    case NHMC_GN_PLAIN: return run_any<T, NHMC_GN_PLAIN, PHASE>(layout, a, batch, st);   \
-    case NHMC_GN_SILU: return run_any<T, NHMC_GN_SILU, PHASE>(layout, a, batch, st);     \
-    case NHMC_GN_FILM_SILU: return run_any<T, NHMC_GN_FILM_SILU, PHASE>(layout, a, batch, st); \
+    case NHMC_GN_PLAIN: return run_any<T, NHMC_GN_PLAIN, PHASE>(layout, a, s, batch, st);   \
+    case NHMC_GN_SILU: return run_any<T, NHMC_GN_SILU, PHASE>(layout, a, s, batch, st);     \
+    case NHMC_GN_FILM_SILU: return run_any<T, NHMC_GN_FILM_SILU, PHASE>(layout, a, s, batch, st); \
   }
   switch (dtype) {
     case NHMC_F32: GN_CASE(float) break;
@@ -563,8 +963,8 @@ static int check_common(int mode, int layout, int dtype, const void* x, const vo
 using namespace nhmc;
 
 extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
-                           const float* beta, const float* scale, const float* shift, const float* in_bias, float* stats_out, int batch,
-                           int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
+                           const float* beta, const float* scale, const float* shift, int64_t film_stride, const float* in_bias,
+                           float* stats_out, int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(stats_out, "stats_out required");
   GnScratch s;
@@ -572,17 +972,20 @@ extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void*
   GnArgs a{};
   a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.stats = stats_out;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
-  return dispatch<0>(mode, layout, dtype, a, batch, (cudaStream_t)stream);
+  a.film_stride = film_stride > 0 ? film_stride : channels;
+  NHMC_CHECK_ARG(a.film_stride >= channels, "film_stride must be >= channels");
+  return dispatch<0>(mode, layout, dtype, a, s, batch, (cudaStream_t)stream);
 }
 
 extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                            const float* gamma, const float* beta, const float* scale, const float* shift,
-                           const float* in_bias, const float* stats, float* dscale, float* dshift, int batch, int channels, int64_t hw,
-                           int groups, nhmc_stream_t stream) {
+                           int64_t film_stride, const float* in_bias, const float* stats, float* dscale, float* dshift, const void* dx_add, int batch,
+                           int channels, int64_t hw, int groups, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(dy && stats, "dy and stats required");
   NHMC_CHECK_ARG(!dscale && !dshift, "dscale/dshift are not produced on the sampling path (timestep embedding carries no gradient)");
   NHMC_CHECK_ARG(layout != NHMC_LAYOUT_NHWC || aligned16(dy), "dy must be 16-byte aligned");
+  NHMC_CHECK_ARG(!dx_add || aligned16(dx_add), "dx_add must be 16-byte aligned");
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
@@ -590,5 +993,25 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   a.stats = const_cast<float*>(stats);
   a.bstats = s.bstats;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;
-  return dispatch<1>(mode, layout, dtype, a, batch, (cudaStream_t)stream);
+  a.film_stride = film_stride > 0 ? film_stride : channels;
+  NHMC_CHECK_ARG(a.film_stride >= channels, "film_stride must be >= channels");
+  a.add = dx_add;
+  return dispatch<1>(mode, layout, dtype, a, s, batch, (cudaStream_t)stream);
+}
+
+extern "C" int nhmc_gn_check(void) {
+  // 0 = no wait of the resident GroupNorm path ever timed out on the current device (synchronises)
+  int dev = 0;
+  if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
+  if (dev < 0 || dev >= 16 || !g_scratch[dev].res) return NHMC_OK;
+  unsigned int flag = 0;
+  if (int e = cuda_status(cudaMemcpy(&flag, g_scratch[dev].res + 1, sizeof(flag), cudaMemcpyDeviceToHost), "gn check")) return e;
+  if (flag) { set_error("resident GroupNorm: a per-sample barrier timed out (results of that call are invalid)"); return NHMC_ERR_CUDA; }
+  return NHMC_OK;
+}
+
+extern "C" int nhmc_gn_set_resident(int on) {
+  const int prev = resident_mode();
+  g_resident_mode = on ? 1 : 0;
+  return prev;
 }

@@ -141,23 +141,41 @@ def commit(chains, x, x_prop, x_hat, x_keep, samples, sched, n_slots):
                                 chains.n, N, _stream()), "nhmc_commit")
 
 
+def _film_stride(scale, shift, channels):
+    """scale / shift: fp32 [B, C] rows, unit stride along C, possibly views into one [B, 2C] projection."""
+    if scale is None:
+        return 0
+    for t, n in ((scale, "scale"), (shift, "shift")):
+        if t.dtype != torch.float32 or t.dim() != 2 or t.shape[1] != channels or t.stride(1) != 1:
+            raise _lib.NhmcError("%s must be fp32 [B, C] with unit stride along C" % n)
+    if scale.stride(0) != shift.stride(0):
+        raise _lib.NhmcError("scale and shift must share their row stride")
+    return scale.stride(0)
+
+
 def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last, in_bias=None):
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
-    with _timed("gn_fwd", 2 if channels_last else 1, 2 * x.numel() * x.element_size()):
+    with _timed("gn_fwd", 1, 2 * x.numel() * x.element_size()):
         check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
-                                _p(gamma), _p(beta), _p(scale), _p(shift), _p(in_bias), _p(stats), B, Cc, hw, groups,
-                                float(eps), _stream()), "nhmc_gn_fwd")
+                                _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc), _p(in_bias),
+                                _p(stats), B, Cc, hw, groups, float(eps), _stream()), "nhmc_gn_fwd")
 
 
-def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None):
+def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None, dx_add=None):
+    """dx = d/dx act(GN(x)) . dy (+ dx_add, e.g. the gradient of the ResBlock's skip branch, in the same pass)."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
-    with _timed("gn_bwd", 2 if channels_last else 1, 3 * x.numel() * x.element_size()):
+    with _timed("gn_bwd", 1, (3 + (1 if dx_add is not None else 0)) * x.numel() * x.element_size()):
         check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
-                                _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _p(in_bias), _p(stats), 0, 0, B, Cc, hw,
-                                groups, _stream()), "nhmc_gn_bwd")
+                                _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc),
+                                _p(in_bias), _p(stats), 0, 0, _p(dx_add), B, Cc, hw, groups, _stream()), "nhmc_gn_bwd")
+
+
+def gn_check():
+    """Raises if a per-sample barrier of the resident GroupNorm path ever timed out (synchronises)."""
+    check(lib().nhmc_gn_check(), "nhmc_gn_check")
 
 
 def softmax_fwd(logits, probs, scale):

@@ -84,6 +84,34 @@ def _cl(x):
     return x if _is_channels_last(x) else x.contiguous(memory_format=torch.channels_last)
 
 
+class _GroupNormActSkip(torch.autograd.Function):
+    """(y, x_skip) = (act(GN32(x) ...), x): the block input feeds the norm AND the skip branch
+    (unet_ffhq.py:309-327).  The backward adds the skip branch's gradient inside the GroupNorm backward
+    kernel (dx_add) instead of leaving autograd a separate read-read-write accumulation pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias):
+        x = _cl(x)
+        y = torch.empty_like(x)
+        stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
+        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, GN_EPS, True, in_bias)
+        ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
+        ctx.mode = mode
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        x, gamma, beta, scale, shift, stats, in_bias = ctx.saved_tensors
+        if dy is None:
+            return dskip, None, None, None, None, None, None
+        dy = _cl(dy)
+        if dskip is not None:
+            dskip = _cl(dskip)
+        dx = torch.empty_like(x)
+        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias, dx_add=dskip)
+        return dx, None, None, None, None, None, None
+
+
 class _AvgPool2(torch.autograd.Function):
     """avg_pool2d(x, 2) on channels-last activations (Downsample without conv, unet_ffhq.py:187-211)."""
 
@@ -168,6 +196,15 @@ def group_norm_act(x, norm, mode, scale=None, shift=None, in_bias=None):
     return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode, in_bias)
 
 
+def group_norm_act_skip(x, norm, mode):
+    """(act(GN32(x)), x): use the second output on the skip branch so that its gradient is added in-kernel."""
+    if not x.is_cuda:
+        raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
+    if x.dim() != 4 or x.shape[1] % (4 if x.dtype == torch.float32 else 8):
+        return group_norm_act(x, norm, mode), x
+    return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None)
+
+
 def _conv_nobias(conv, x):
     return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
 
@@ -212,9 +249,10 @@ class ResBlock(nn.Module):
         self.out_layers = nn.Sequential(_Norm(oc), nn.Identity(), nn.Identity(), nn.Conv2d(oc, oc, 3, padding=1))
         self.skip_connection = nn.Identity() if oc == channels else nn.Conv2d(channels, oc, 1)
 
-    def forward(self, x, emb_act):
-        """emb_act = SiLU(time embedding) (shared by all blocks: computed once per forward)."""
-        h = group_norm_act(x, self.in_layers[0], _lib.GN_SILU)
+    def forward(self, x, e):
+        """e = this block's embedding projection emb_layers(emb) in fp32, [B, 2*oc] (FiLM) or [B, oc]: a view into
+        the one batched projection UNetModel.forward computes for all blocks (unet_ffhq.py:263-270,317-321)."""
+        h, x = group_norm_act_skip(x, self.in_layers[0], _lib.GN_SILU)
         if self.up:
             h = _Upsample2.apply(h)
             x = _Upsample2.apply(x)
@@ -225,9 +263,8 @@ class ResBlock(nn.Module):
         # b2 (+ the 1x1 skip conv's bias) into the residual add
         b1, b_out = self._fp32_biases()
         h = _conv_nobias(self.in_layers[2], h)
-        e = self.emb_layers[1](emb_act).float()
         if self.film:
-            scale, shift = e[:, : self.out_channels].contiguous(), e[:, self.out_channels:].contiguous()
+            scale, shift = e[:, : self.out_channels], e[:, self.out_channels:]       # strided views, no split copies
             h = group_norm_act(h, self.out_layers[0], _lib.GN_FILM_SILU, scale, shift, in_bias=b1)
         else:
             h = group_norm_act(h + (e + b1).to(h.dtype)[:, :, None, None], self.out_layers[0], _lib.GN_SILU)
@@ -261,7 +298,7 @@ class AttentionBlock(nn.Module):
         B, C, H, W = x.shape
         T, nh = H * W, self.num_heads
         ch = C // nh
-        xn = group_norm_act(x, self.norm, _lib.GN_PLAIN)
+        xn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
         # channels-last: [B, T, C] views without copies
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)
         qkv = F.linear(tok, self.qkv.weight[:, :, 0], self.qkv.bias)               # [B, T, 3C]
@@ -280,9 +317,9 @@ class AttentionBlock(nn.Module):
 class _Seq(nn.Sequential):
     """TimestepEmbedSequential (unet_ffhq.py:137-150)."""
 
-    def forward(self, x, emb_act):
+    def forward(self, x, embs):
         for layer in self:
-            x = layer(x, emb_act) if isinstance(layer, ResBlock) else layer(x)
+            x = layer(x, embs[layer]) if isinstance(layer, ResBlock) else layer(x)
         return x
 
 
@@ -338,9 +375,30 @@ class UNetModel(nn.Module):
             self._first_bias_cache = c
         return c
 
+    def _emb_projection(self, emb_act):
+        """All ResBlocks' emb_layers Linear (unet_ffhq.py:263-270) as ONE GEMM on concatenated (frozen) weights;
+        returns {block: fp32 view [B, n_out]} into the single result (29 GEMMs + 87 copy kernels -> 1 + 1)."""
+        cache = getattr(self, "_emb_cache", None)
+        w0 = self.time_embed[0].weight
+        if cache is None or cache[0].device != w0.device or cache[0].dtype != w0.dtype:
+            blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+            W = torch.cat([m.emb_layers[1].weight.detach() for m in blocks], 0).contiguous()
+            b = torch.cat([m.emb_layers[1].bias.detach() for m in blocks], 0).contiguous()
+            offs, o = [], 0
+            for m in blocks:
+                n = m.emb_layers[1].weight.shape[0]
+                offs.append((m, o, n))
+                o += n
+            cache = (W, b, offs)
+            self._emb_cache = cache
+        W, b, offs = cache
+        e_all = F.linear(emb_act, W, b).float()
+        return {m: e_all[:, o: o + n] for m, o, n in offs}
+
     def load_state_dict(self, *args, **kwargs):
         r = super().load_state_dict(*args, **kwargs)
         self._first_bias_cache = None
+        self._emb_cache = None
         for m in self.modules():
             if isinstance(m, ResBlock):
                 m._bias_cache = None
@@ -359,6 +417,7 @@ class UNetModel(nn.Module):
         dt = self.compute_dtype
         emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(dt))
         emb_act = F.silu(emb)                                  # the SiLU that opens every emb_layers (unet_ffhq.py:263)
+        embs = self._emb_projection(emb_act)
         h = x.to(dt).contiguous(memory_format=torch.channels_last)
         hs = []
         for i, module in enumerate(self.input_blocks):
@@ -366,11 +425,11 @@ class UNetModel(nn.Module):
                 conv = module[0]
                 h = _BiasAdd.apply(_conv_nobias(conv, h), None, self._first_bias())
             else:
-                h = module(h, emb_act)
+                h = module(h, embs)
             hs.append(h)
-        h = self.middle_block(h, emb_act)
+        h = self.middle_block(h, embs)
         for module in self.output_blocks:
-            h = module(_Cat2.apply(h, hs.pop()), emb_act)
+            h = module(_Cat2.apply(h, hs.pop()), embs)
         h = group_norm_act(h, self.out[0], _lib.GN_SILU)
         return self.out[2](h)
 

@@ -174,6 +174,51 @@ def test_resample_and_split_kernels(dtype):
     assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
 
 
+@pytest.mark.parametrize("resident", [1, 0])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", [0, 2])
+@pytest.mark.parametrize("shape", [(8, 128, 128, 128), (3, 384, 64, 64), (2, 256, 256, 256), (5, 1024, 16, 16), (2, 128, 33, 7),
+                                   (8, 512, 8, 8), (2, 224, 32, 32)])
+def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
+    """Channels-last GroupNorm on both execution paths (shared-memory resident single kernel / statistics + apply
+    kernels): samples spanning many CTAs, a sample filling the whole chip, ragged pixel counts, the folded conv
+    bias and the fused skip-gradient add; repeated calls check that the self-resetting counters reset."""
+    from nhmc_b200 import kernels, _lib
+    B, C, H, W = shape
+    if dtype == torch.float32 and B * C * H * W > 2 ** 25:
+        pytest.skip("fp32 copy of the largest shape is covered in bf16")
+    g = torch.Generator().manual_seed(3)
+    cl = torch.channels_last
+    x = (torch.randn(shape, generator=g) * 1.7 + 0.4).cuda().to(dtype).contiguous(memory_format=cl)
+    dy = torch.randn(shape, generator=g).cuda().to(dtype).contiguous(memory_format=cl)
+    add = torch.randn(shape, generator=g).cuda().to(dtype).contiguous(memory_format=cl)
+    bias = (0.5 * torch.randn(C, generator=g)).cuda()
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).cuda(); beta = (0.1 * torch.randn(C, generator=g)).cuda()
+    scale = (0.3 * torch.randn(B, C, generator=g)).cuda(); shift = (0.3 * torch.randn(B, C, generator=g)).cuda()
+    sc, sh = (scale, shift) if mode == 2 else (None, None)
+    xr = x.float().detach().clone().requires_grad_(True)
+    yr = _gn_ref(xr + bias[None, :, None, None], gamma, beta, scale, shift, mode)
+    (dxr,) = torch.autograd.grad(yr, xr, dy.float())
+    dxr = dxr + add.float()
+    prev = _lib.lib().nhmc_gn_set_resident(resident)
+    try:
+        for rep in range(3):
+            y = torch.empty_like(x); dx = torch.empty_like(x); stats = torch.empty(B, 32, 2, device="cuda")
+            kernels.gn_fwd(mode, x, y, gamma, beta, sc, sh, stats, 32, 1e-5, True, bias)
+            kernels.gn_bwd(mode, x, dy, dx, gamma, beta, sc, sh, stats, 32, True, bias, dx_add=add)
+            kernels.gn_check()
+            if dtype == torch.float32:
+                tol = dict(atol=5e-5, rtol=1e-4)
+            else:
+                tol = dict(atol=3e-2, rtol=2e-2)
+            yd = (y.float() - yr.detach()).abs()
+            assert float((yd - tol["atol"] - tol["rtol"] * yr.detach().abs()).max()) <= 0, (rep, float(yd.max()))
+            dd = (dx.float() - dxr).abs()
+            assert float((dd - tol["atol"] * float(dxr.abs().max()) - tol["rtol"] * dxr.abs()).max()) <= 0, (rep, float(dd.max()))
+    finally:
+        _lib.lib().nhmc_gn_set_resident(prev)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("cl", [False, True])
 def test_group_norm_with_folded_conv_bias(dtype, cl):

@@ -52,14 +52,16 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--chains", type=int, default=64)
+    ap.add_argument("--resident", type=int, default=1, help="GroupNorm: 1 = shared-memory resident single kernel, 0 = statistics + apply kernels")
     a = ap.parse_args()
     pk = peak()
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     want = lambda k: (not a.only) or a.only in k
+    _lib.lib().nhmc_gn_set_resident(a.resident)
 
     if want("gn"):
-        for (B, C, H) in [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 512, 64), (8, 1024, 32), (8, 512, 8), (1, 128, 256)]:
+        for (B, C, H) in [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]:
             for dt in (torch.bfloat16,):
                 x = torch.randn(B, C, H, H, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
                 dy = torch.randn_like(x); y = torch.empty_like(x); dx = torch.empty_like(x)
@@ -73,6 +75,7 @@ def main():
                     report("gn_fwd_" + nm, [B, C, H, H], 2 * nb, ms, pk)
                     ms = timeit(lambda: kernels.gn_bwd(mode, x, dy, dx, gamma, beta, s_, h_, stats, 32, True), a.reps, flush)
                     report("gn_bwd_" + nm, [B, C, H, H], 3 * nb, ms, pk)
+                kernels.gn_check()
     if want("leapfrog") or want("ddim") or want("op"):
         B = a.chains
         N = 3 * 256 * 256
