@@ -26,6 +26,8 @@ def peak():
 
 
 def timeit(fn, reps, flush=None):
+    """Median CUDA-event time of fn() with a cold, CLEAN L2: the flush buffer (> L2) is written, then read back,
+    so that the timed kernel neither hits in L2 nor pays for the write-back of the flush's dirty lines."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -33,6 +35,7 @@ def timeit(fn, reps, flush=None):
     for _ in range(reps):
         if flush is not None:
             flush.zero_()
+            flush.view(torch.int32).sum()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record()
         torch.cuda.synchronize()
@@ -52,6 +55,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--chains", type=int, default=64)
+    ap.add_argument("--shape", default="", help="GroupNorm: only this B,C,H (e.g. 8,128,256)")
     ap.add_argument("--resident", type=int, default=1, help="GroupNorm: 1 = shared-memory resident single kernel, 0 = statistics + apply kernels")
     a = ap.parse_args()
     pk = peak()
@@ -61,7 +65,10 @@ def main():
     _lib.lib().nhmc_gn_set_resident(a.resident)
 
     if want("gn"):
-        for (B, C, H) in [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]:
+        shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]
+        if a.shape:
+            shapes = [tuple(int(v) for v in a.shape.split(","))]
+        for (B, C, H) in shapes:
             for dt in (torch.bfloat16,):
                 x = torch.randn(B, C, H, H, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
                 dy = torch.randn_like(x); y = torch.empty_like(x); dx = torch.empty_like(x)
