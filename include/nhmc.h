@@ -234,6 +234,20 @@ int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, 
                 nhmc_stream_t stream);
 /* 0 unless a per-sample barrier of the shared-memory-resident GroupNorm path ever timed out on the
  * current device (synchronises; for tests and debugging, not for the hot loop). */
+/* GroupNorm over the VIRTUAL concatenation cat([x0, x1], channel) (the skip connections of the output
+ * blocks, unet_ffhq.py:729-731): x0 [B, HW, c0] and x1 [B, HW, c1] are separate dense channels-last
+ * tensors, y is the dense [B, HW, c0+c1] result the next convolution reads; gamma/beta/scale/shift index
+ * the concatenated channel.  The backward writes the two input gradients separately and can add a tensor
+ * to each in the same pass (add0/add1, independently nullable).  Saves the concat pass forward and the
+ * split pass backward. */
+int nhmc_gn_cat_fwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, void* y,
+                    const float* gamma, const float* beta, const float* scale, const float* shift,
+                    int64_t film_stride, float* stats_out, int batch, int64_t hw, int groups, float eps,
+                    nhmc_stream_t stream);
+int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, const void* dy,
+                    void* dx0, void* dx1, const float* gamma, const float* beta, const float* scale,
+                    const float* shift, int64_t film_stride, const float* stats, const void* add0,
+                    const void* add1, int batch, int64_t hw, int groups, nhmc_stream_t stream);
 int nhmc_gn_check(void);
 /* Switch the shared-memory-resident channels-last path on (default) or off (statistics + apply
  * kernels); returns the previous setting.  For A/B measurements and tests. */
@@ -263,9 +277,10 @@ int nhmc_pool2_scatter(int dtype, const void* in_small, void* out_big, int batch
                        int w_small, int channels, float scale, nhmc_stream_t stream);
 int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows, int c1, int c2,
                 nhmc_stream_t stream);
-/* out[r, c] = a[r, c] (+ b[r, c]) (+ bias[c]): residual add of the ResBlock (unet_ffhq.py:327) with the
- * biases of the convolutions that produced a / b folded in; channels-last rows, out may alias a. */
-int nhmc_bias_add(int dtype, const void* a, const void* b, const float* bias, void* out,
+/* out[r, c] = a[r, c] (+ b[r, c] (+ c3[r, c])) (+ bias[c]): residual add of the ResBlock (unet_ffhq.py:327) with
+ * the biases of the convolutions that produced the addends folded in; the third addend is the second half of a
+ * skip 1x1 convolution applied block-wise to a virtual concatenation.  channels-last rows, out may alias a. */
+int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c3, const float* bias, void* out,
                   int64_t rows, int channels, nhmc_stream_t stream);
 
 #ifdef __cplusplus

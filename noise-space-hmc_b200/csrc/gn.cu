@@ -94,6 +94,10 @@ __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f
 struct GnArgs {
   const void* x; const void* dy; void* out;
   const void* add;   // backward: optional tensor added to dx in the same pass (skip-branch gradient), or null
+  // virtual concatenation (unet_ffhq.py:730): when x1 != null the normalised tensor is cat([x, x1], channel) with
+  // c_split channels in x and C - c_split in x1, each a dense channels-last block of its own; the backward then
+  // writes dx / reads add per block (out, out1 / add, add1; add and add1 are independently nullable)
+  const void* x1; void* out1; const void* add1; int c_split;
   const float* gamma; const float* beta; const float* scale; const float* shift;  // scale/shift: [B,C] fp32 or null
   const float* in_bias;  // [C] fp32 or null: the normalised tensor is x + in_bias[c] (conv bias folded in)
   float* stats;      // [B][G][2]: fwd (mean, rstd)
@@ -153,32 +157,64 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsign
                ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// Streams NSRC byte ranges (x, and dy for the backward kernels) of `total` bytes each and calls
-// body(offset_in_range, x_vec, dy_vec) for every 16-byte vector owned by this thread.  Plain 16-byte
-// read-only loads, U (x NSRC) of them in flight per thread before the first use: measured on B200 this simple
-// form streams at 6-7 TB/s, while the earlier mbarrier/TMA shared-memory ring topped out at ~4.5 TB/s
-// (profiles/: 59 % issue slots busy on ring bookkeeping, 57 % DRAM throughput).  TMA stays where it buys
-// something: the resident kernel below, which needs the slab in shared memory anyway.
-template <int NSRC, typename Body>
-__device__ __forceinline__ void stream_ranges(const char* src0, const char* src1, int64_t total64, Body body) {
+// This thread's 16-byte vector of a channels-last [rows, C] tensor: p = address in row 0, stride = bytes per row.
+// The tensor is one dense block, or -- virtual concatenation -- two dense blocks split at channel c_split.
+struct RowPtr { char* p; int64_t stride; };
+template <typename T>
+__device__ __forceinline__ RowPtr row_ptr(const void* block, int width, int c_in_block, int64_t first_row) {
+  RowPtr r;
+  r.stride = (int64_t)width * sizeof(T);
+  r.p = const_cast<char*>(reinterpret_cast<const char*>(block)) + first_row * r.stride + (int64_t)c_in_block * sizeof(T);
+  return r;
+}
+// Which block of a (possibly split) tensor holds this thread's channels c0 .. c0+V-1.
+struct SegSel { bool second; int width, cc; };
+__device__ __forceinline__ SegSel seg_select(const void* x1, int c_split, int C, int c0) {
+  SegSel s;
+  s.second = x1 != nullptr && c0 >= c_split;
+  s.width = x1 != nullptr ? (s.second ? C - c_split : c_split) : C;
+  s.cc = s.second ? c0 - c_split : c0;
+  return s;
+}
+
+// Streams rows [r_begin, r_end) of x (and dy for the backward kernels): this thread visits rows r_begin + prow,
+// + rows, ... and calls body(x_vec, dy_vec, ep) where ep[i] is the address of this thread's vector of the i-th
+// extra tensor (outputs, addends) in the same row.  Plain 16-byte read-only loads, U (x NSRC) of them in flight
+// per thread before the first use; every address advances by pointer bumps (no per-load multiplies: these
+// kernels sit within 2x of the issue limit).  Measured on B200 this simple form streams at 6-7 TB/s, while the
+// earlier mbarrier/TMA shared-memory ring topped out at ~4.5 TB/s (59 % issue slots busy on ring bookkeeping,
+// 57 % DRAM throughput).  TMA stays where it buys something: the resident kernel below, which needs the slab in
+// shared memory anyway.
+template <int NSRC, int NX, typename Body>
+__device__ __forceinline__ void stream_rows(const RowPtr x, const RowPtr d, const RowPtr (&ex)[NX], int64_t r_begin,
+                                            int64_t r_end, int prow, int rows, Body body) {
   constexpr int U = NSRC == 2 ? 4 : 8;
-  const unsigned total = (unsigned)total64;            // a CTA's range is far below 4 GiB
-  const unsigned pass = blockDim.x * 16u;
-  for (unsigned off0 = threadIdx.x * 16u; off0 < total; off0 += U * pass) {
+  const int64_t r0 = r_begin + prow;
+  const int n = r_end > r0 ? (int)((r_end - r0 + rows - 1) / rows) : 0;      // rows this thread visits
+  const char* px = x.p + r0 * x.stride;
+  const char* pd = NSRC == 2 ? d.p + r0 * d.stride : nullptr;
+  const int64_t sx = (int64_t)rows * x.stride, sd = (int64_t)rows * d.stride;
+  char* pe[NX];
+  int64_t se[NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) { pe[i] = ex[i].p + r0 * ex[i].stride; se[i] = (int64_t)rows * ex[i].stride; }
+  for (int k = 0; k < n; k += U) {
     uint4 vx[U], vd[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const unsigned off = off0 + u * pass;
       vx[u] = make_uint4(0, 0, 0, 0); vd[u] = make_uint4(0, 0, 0, 0);
-      if (off < total) {
-        vx[u] = ld_raw(src0 + off);
-        if (NSRC == 2) vd[u] = ld_raw(src1 + off);
+      if (k + u < n) {
+        vx[u] = ld_raw(px);
+        if (NSRC == 2) vd[u] = ld_raw(pd);
       }
+      px += sx;
+      if (NSRC == 2) pd += sd;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const unsigned off = off0 + u * pass;
-      if (off < total) body((int64_t)off, vx[u], vd[u]);
+      if (k + u < n) body(vx[u], vd[u], pe);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pe[i] += se[i];
     }
   }
 }
@@ -186,7 +222,7 @@ __device__ __forceinline__ void stream_ranges(const char* src0, const char* src1
 // PHASE 0: forward statistics (sum x, sum x^2)            -> fp64 accumulators [B][64][2]
 // PHASE 1: backward statistics (sum du, sum du*u)          -> same accumulators
 template <typename T, int MODE, int PHASE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gn_nhwc_stats_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -213,13 +249,14 @@ gn_nhwc_stats_kernel(GnArgs a) {
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
   int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
-  const int64_t row_bytes = (int64_t)a.C * sizeof(T);
-  const char* xsrc = reinterpret_cast<const char*>(a.x) + ((int64_t)b * a.HW + r_begin) * row_bytes;
-  const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + ((int64_t)b * a.HW + r_begin) * row_bytes : nullptr;
+  const SegSel sel = seg_select(a.x1, a.c_split, a.C, c0);
+  const RowPtr xr = row_ptr<T>(sel.second ? a.x1 : a.x, sel.width, sel.cc, (int64_t)b * a.HW);
+  const RowPtr dr = row_ptr<T>(a.dy, a.C, c0, (int64_t)b * a.HW);
   // PHASE 1 accumulates t0 = sum dy*act'(z), t1 = sum dy*act'(z)*x per channel; the per-channel
   // affine (gamma(1+s), mean, rstd) is applied once after the loop.
-  stream_ranges<PHASE == 1 ? 2 : 1>(xsrc, dsrc, (r_end - r_begin) * row_bytes,
-      [&](int64_t, const uint4& rx, const uint4& rd) {
+  const RowPtr none[1] = {{nullptr, 0}};
+  stream_rows<PHASE == 1 ? 2 : 1, 1>(xr, dr, none, r_begin, r_end, prow, rows,
+      [&](const uint4& rx, const uint4& rd, char* const (&)[1]) {
         float xv[V];
         unpack<T>(rx, xv);
         if (PHASE == 0) {
@@ -277,12 +314,12 @@ gn_nhwc_stats_kernel(GnArgs a) {
 
 // PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
 template <typename T, int MODE, int PHASE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
   const int cvec = a.C / V;
-  const int cv = threadIdx.x % cvec;
+  const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
   const int Cg = a.C / a.G;
   float ca[V], cb[V], k1[V], k2[V], k3[V];
@@ -324,14 +361,18 @@ gn_nhwc_apply_kernel(GnArgs a) {
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
   int64_t r_end = r_begin + a.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
-  const int64_t row_bytes = (int64_t)a.C * sizeof(T);
-  const int64_t base = ((int64_t)b * a.HW + r_begin) * row_bytes;
-  const char* xsrc = reinterpret_cast<const char*>(a.x) + base;
-  const char* dsrc = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + base : nullptr;
-  char* dst = reinterpret_cast<char*>(a.out) + base;
-  const char* asrc = (PHASE == 1 && a.add) ? reinterpret_cast<const char*>(a.add) + base : nullptr;
-  stream_ranges<PHASE == 1 ? 2 : 1>(xsrc, dsrc, (r_end - r_begin) * row_bytes,
-      [&](int64_t off, const uint4& rx, const uint4& rd) {
+  const int64_t first = (int64_t)b * a.HW;
+  const SegSel sel = seg_select(a.x1, a.c_split, a.C, c0);
+  const RowPtr xr = row_ptr<T>(sel.second ? a.x1 : a.x, sel.width, sel.cc, first);
+  const RowPtr dr = row_ptr<T>(a.dy, a.C, c0, first);
+  // forward: y is one dense tensor; backward: dx (and add) follow the layout of x
+  const RowPtr orow = PHASE == 0 ? row_ptr<T>(a.out, a.C, c0, first)
+                                 : row_ptr<T>(sel.second ? a.out1 : a.out, sel.width, sel.cc, first);
+  const void* addp = sel.second ? a.add1 : a.add;
+  const bool has_add = PHASE == 1 && addp != nullptr;
+  const RowPtr extra[2] = {orow, row_ptr<T>(addp, sel.width, sel.cc, first)};
+  stream_rows<PHASE == 1 ? 2 : 1, 2>(xr, dr, extra, r_begin, r_end, prow, rows,
+      [&](const uint4& rx, const uint4& rd, char* const (&ep)[2]) {
         float xv[V], ov[V];
         unpack<T>(rx, xv);
         if (PHASE == 0) {
@@ -345,14 +386,14 @@ gn_nhwc_apply_kernel(GnArgs a) {
             const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
           }
-          if (asrc) {
+          if (has_add) {
             float ad[V];
-            unpack<T>(ld_raw(asrc + off), ad);
+            unpack<T>(ld_raw(ep[1]), ad);
 #pragma unroll
             for (int i = 0; i < V; ++i) ov[i] += ad[i];
           }
         }
-        store_vec<T>(reinterpret_cast<T*>(dst + off), ov);
+        store_vec<T>(reinterpret_cast<T*>(ep[0]), ov);
       });
   // Every CTA read the accumulators before streaming; the last CTA to finish publishes (mean, rstd) for the
   // backward pass and re-zeroes the accumulators for the next call on this stream (no wait on the hot path).
@@ -848,7 +889,7 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   int rows = 256 / cvec; if (rows < 1) rows = 1;
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
-  {
+  if (!a.x1) {
     const int e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
   }
@@ -959,6 +1000,47 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   NHMC_CHECK_ARG(a.film_stride >= channels, "film_stride must be >= channels");
   a.add = dx_add;
   return dispatch<1>(mode, layout, dtype, a, s, batch, (cudaStream_t)stream);
+}
+
+// Virtual concatenation: GroupNorm over cat([x0, x1], channel) without materialising the concatenation
+// (channels-last only, statistics + apply kernels).
+extern "C" int nhmc_gn_cat_fwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, void* y,
+                               const float* gamma, const float* beta, const float* scale, const float* shift,
+                               int64_t film_stride, float* stats_out, int batch, int64_t hw, int groups, float eps,
+                               nhmc_stream_t stream) {
+  const int channels = c0 + c1;
+  if (int e = check_common(mode, NHMC_LAYOUT_NHWC, dtype, x0, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
+  const int V = dtype == NHMC_F32 ? 4 : 8;
+  NHMC_CHECK_ARG(x1 && c0 > 0 && c1 > 0 && c0 % V == 0 && c1 % V == 0 && aligned16(x1), "both blocks need C % (16B/elem) == 0 and 16-byte alignment");
+  NHMC_CHECK_ARG(stats_out, "stats_out required");
+  GnScratch s;
+  if (int e = get_scratch(batch, groups, s)) return e;
+  GnArgs a{};
+  a.x = x0; a.x1 = x1; a.c_split = c0; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = stats_out;
+  a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
+  a.film_stride = film_stride > 0 ? film_stride : channels;
+  return dispatch<0>(mode, NHMC_LAYOUT_NHWC, dtype, a, s, batch, (cudaStream_t)stream);
+}
+
+extern "C" int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, const void* dy,
+                               void* dx0, void* dx1, const float* gamma, const float* beta, const float* scale,
+                               const float* shift, int64_t film_stride, const float* stats, const void* add0,
+                               const void* add1, int batch, int64_t hw, int groups, nhmc_stream_t stream) {
+  const int channels = c0 + c1;
+  if (int e = check_common(mode, NHMC_LAYOUT_NHWC, dtype, x0, dx0, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
+  const int V = dtype == NHMC_F32 ? 4 : 8;
+  NHMC_CHECK_ARG(x1 && dx1 && c0 > 0 && c1 > 0 && c0 % V == 0 && c1 % V == 0 && aligned16(x1) && aligned16(dx1),
+                 "both blocks need C % (16B/elem) == 0 and 16-byte alignment");
+  NHMC_CHECK_ARG(dy && stats && aligned16(dy), "dy (16-byte aligned) and stats required");
+  NHMC_CHECK_ARG((!add0 || aligned16(add0)) && (!add1 || aligned16(add1)), "add blocks must be 16-byte aligned");
+  GnScratch s;
+  if (int e = get_scratch(batch, groups, s)) return e;
+  GnArgs a{};
+  a.x = x0; a.x1 = x1; a.c_split = c0; a.dy = dy; a.out = dx0; a.out1 = dx1; a.add = add0; a.add1 = add1;
+  a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = const_cast<float*>(stats); a.bstats = s.bstats;
+  a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;
+  a.film_stride = film_stride > 0 ? film_stride : channels;
+  return dispatch<1>(mode, NHMC_LAYOUT_NHWC, dtype, a, s, batch, (cudaStream_t)stream);
 }
 
 extern "C" int nhmc_gn_check(void) {

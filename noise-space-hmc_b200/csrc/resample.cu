@@ -104,7 +104,7 @@ split2_kernel(const T* __restrict__ in, T* __restrict__ o1, T* __restrict__ o2, 
 
 template <typename T, bool HAS_B, bool HAS_BIAS>
 __global__ void __launch_bounds__(256)
-bias_add_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* __restrict__ bias, T* out, int64_t total, int cvec) {
+bias_add_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const float* __restrict__ bias, T* out, int64_t total, int cvec) {
   constexpr int V = V16<T>::N;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     float va[V], vb[V];
@@ -112,6 +112,12 @@ bias_add_kernel(const T* __restrict__ a, const T* __restrict__ b, const float* _
     const uint4 ra = *reinterpret_cast<const uint4*>(a + idx * V);
     up<T>(ra, va);
     if (HAS_B) { up<T>(ldg16(b + idx * V), vb); }
+    if (HAS_B && c != nullptr) {
+      float vc[V];
+      up<T>(ldg16(c + idx * V), vc);
+#pragma unroll
+      for (int k = 0; k < V; ++k) vb[k] += vc[k];
+    }
     const int c0 = (int)(idx % cvec) * V;
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -185,27 +191,28 @@ extern "C" int nhmc_split2(int dtype, const void* in, void* out1, void* out2, in
 }
 
 template <typename T>
-static int run_bias_add(const void* a, const void* b, const float* bias, void* out, int64_t rows, int C, cudaStream_t st) {
+static int run_bias_add(const void* a, const void* b, const void* c, const float* bias, void* out, int64_t rows, int C, cudaStream_t st) {
   constexpr int V = V16<T>::N;
   NHMC_CHECK_ARG(C % V == 0, "channels must be a multiple of the 16-byte vector width");
   const int64_t total = rows * (C / V);
   const unsigned g = grid_for(total);
-#define BA(HB, HBI) bias_add_kernel<T, HB, HBI><<<g, 256, 0, st>>>((const T*)a, (const T*)b, bias, (T*)out, total, C / V)
+#define BA(HB, HBI) bias_add_kernel<T, HB, HBI><<<g, 256, 0, st>>>((const T*)a, (const T*)b, (const T*)c, bias, (T*)out, total, C / V)
   if (b) { if (bias) BA(true, true); else BA(true, false); }
   else   { if (bias) BA(false, true); else BA(false, false); }
 #undef BA
   return NHMC_LAUNCH_CHECK();
 }
 
-extern "C" int nhmc_bias_add(int dtype, const void* a, const void* b, const float* bias, void* out, int64_t rows,
-                             int channels, nhmc_stream_t stream) {
+extern "C" int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c, const float* bias, void* out,
+                             int64_t rows, int channels, nhmc_stream_t stream) {
   NHMC_CHECK_ARG(a && out && rows > 0 && channels > 0, "bad arguments");
-  NHMC_CHECK_ARG(aligned16(a) && aligned16(out) && (!b || aligned16(b)), "pointers must be 16-byte aligned");
+  NHMC_CHECK_ARG(!c || b, "a third addend needs the second");
+  NHMC_CHECK_ARG(aligned16(a) && aligned16(out) && (!b || aligned16(b)) && (!c || aligned16(c)), "pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case NHMC_F32: return run_bias_add<float>(a, b, bias, out, rows, channels, st);
-    case NHMC_BF16: return run_bias_add<__nv_bfloat16>(a, b, bias, out, rows, channels, st);
-    case NHMC_F16: return run_bias_add<__half>(a, b, bias, out, rows, channels, st);
+    case NHMC_F32: return run_bias_add<float>(a, b, c, bias, out, rows, channels, st);
+    case NHMC_BF16: return run_bias_add<__nv_bfloat16>(a, b, c, bias, out, rows, channels, st);
+    case NHMC_F16: return run_bias_add<__half>(a, b, c, bias, out, rows, channels, st);
   }
   set_error("bias_add: unknown dtype %d", dtype);
   return NHMC_ERR_ARG;

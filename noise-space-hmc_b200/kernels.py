@@ -216,9 +216,29 @@ def split2(g, o1, o2):
         check(lib().nhmc_split2(_DT[g.dtype], _p(g), _p(o1), _p(o2), rows, o1.shape[1], o2.shape[1], _stream()), "nhmc_split2")
 
 
-def bias_add(a, b, bias, out):
-    """channels-last 4-D tensors: out = a (+ b) (+ bias[c]); out may alias a."""
+def bias_add(a, b, bias, out, c=None):
+    """channels-last 4-D tensors: out = a (+ b (+ c)) (+ bias[ch]); out may alias a."""
     B, Cc, H, W = a.shape
-    nb = (a.numel() * (2 + (1 if b is not None else 0))) * a.element_size()
+    nb = (a.numel() * (2 + (1 if b is not None else 0) + (1 if c is not None else 0))) * a.element_size()
     with _timed("bias_add", 1, nb):
-        check(lib().nhmc_bias_add(_DT[a.dtype], _p(a), _p(b), _p(bias), _p(out), B * H * W, Cc, _stream()), "nhmc_bias_add")
+        check(lib().nhmc_bias_add(_DT[a.dtype], _p(a), _p(b), _p(c), _p(bias), _p(out), B * H * W, Cc, _stream()), "nhmc_bias_add")
+
+
+def gn_cat_fwd(mode, x0, x1, y, gamma, beta, scale, shift, stats, groups, eps):
+    """GroupNorm (+ follow-up) over the virtual concatenation cat([x0, x1], 1); all tensors channels-last."""
+    B, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
+    hw = x0[0, 0].numel()
+    with _timed("gn_fwd", 2, 2 * y.numel() * y.element_size()):
+        check(lib().nhmc_gn_cat_fwd(mode, _DT[x0.dtype], _p(x0), _p(x1), c0, c1, _p(y), _p(gamma), _p(beta), _p(scale),
+                                    _p(shift), _film_stride(scale, shift, c0 + c1), _p(stats), B, hw, groups, float(eps),
+                                    _stream()), "nhmc_gn_cat_fwd")
+
+
+def gn_cat_bwd(mode, x0, x1, dy, dx0, dx1, gamma, beta, scale, shift, stats, groups, add0=None, add1=None):
+    B, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
+    hw = x0[0, 0].numel()
+    n_add = (add0.numel() if add0 is not None else 0) + (add1.numel() if add1 is not None else 0)
+    with _timed("gn_bwd", 2, (3 * dy.numel() + n_add) * dy.element_size()):
+        check(lib().nhmc_gn_cat_bwd(mode, _DT[x0.dtype], _p(x0), _p(x1), c0, c1, _p(dy), _p(dx0), _p(dx1), _p(gamma), _p(beta),
+                                    _p(scale), _p(shift), _film_stride(scale, shift, c0 + c1), _p(stats), _p(add0), _p(add1),
+                                    B, hw, groups, _stream()), "nhmc_gn_cat_bwd")

@@ -60,6 +60,34 @@ class _GroupNormAct(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+class _CatGroupNormAct(torch.autograd.Function):
+    """(y, x0', x1') = (act(GN32(cat([x0, x1], 1))), x0, x1) without materialising the concatenation
+    (unet_ffhq.py:729-731 + the in_layers norm of the output blocks).  The pass-through outputs feed the two halves
+    of the skip 1x1 convolution; their gradients are added inside the GroupNorm backward kernel, which writes the
+    gradients of x0 and x1 separately (no concat pass forward, no split pass and no accumulation pass backward)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, gamma, beta, mode):
+        x0, x1 = _cl(x0), _cl(x1)
+        B, c0, H, W = x0.shape
+        y = torch.empty((B, c0 + x1.shape[1], H, W), dtype=x0.dtype, device=x0.device, memory_format=torch.channels_last)
+        stats = torch.empty(B, GROUPS, 2, dtype=torch.float32, device=x0.device)
+        kernels.gn_cat_fwd(mode, x0, x1, y, gamma, beta, None, None, stats, GROUPS, GN_EPS)
+        ctx.save_for_backward(x0, x1, gamma, beta, stats)
+        ctx.mode = mode
+        return y, x0.view_as(x0), x1.view_as(x1)
+
+    @staticmethod
+    def backward(ctx, dy, d0, d1):
+        x0, x1, gamma, beta, stats = ctx.saved_tensors
+        dy = _cl(dy)
+        d0 = _cl(d0) if d0 is not None else None
+        d1 = _cl(d1) if d1 is not None else None
+        dx0, dx1 = torch.empty_like(x0), torch.empty_like(x1)
+        kernels.gn_cat_bwd(ctx.mode, x0, x1, dy, dx0, dx1, gamma, beta, None, None, stats, GROUPS, add0=d0, add1=d1)
+        return dx0, dx1, None, None, None
+
+
 class _ScaledSoftmax(torch.autograd.Function):
     """softmax(scale * logits) over the last dim, fp32 inside (unet_ffhq.py:421-424)."""
 
@@ -176,17 +204,18 @@ class _BiasAdd(torch.autograd.Function):
     (residual add of unet_ffhq.py:327 with the producing convolutions' biases folded in)."""
 
     @staticmethod
-    def forward(ctx, a, b, bias):
+    def forward(ctx, a, b, bias, c=None):
         a = _cl(a)
         b = _cl(b) if b is not None else None
+        c = _cl(c) if c is not None else None
         out = torch.empty_like(a)
-        kernels.bias_add(a, b, bias, out)
-        ctx.has_b = b is not None
+        kernels.bias_add(a, b, bias, out, c)
+        ctx.has_b, ctx.has_c = b is not None, c is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
-        return g, (g if ctx.has_b else None), None
+        return g, (g if ctx.has_b else None), None, (g if ctx.has_c else None)
 
 
 def group_norm_act(x, norm, mode, scale=None, shift=None, in_bias=None):
@@ -252,7 +281,12 @@ class ResBlock(nn.Module):
     def forward(self, x, e):
         """e = this block's embedding projection emb_layers(emb) in fp32, [B, 2*oc] (FiLM) or [B, oc]: a view into
         the one batched projection UNetModel.forward computes for all blocks (unet_ffhq.py:263-270,317-321)."""
-        h, x = group_norm_act_skip(x, self.in_layers[0], _lib.GN_SILU)
+        xs = None
+        if isinstance(x, tuple):                 # virtual concatenation (h, skip) of an output block
+            h, xa, xb = _CatGroupNormAct.apply(x[0], x[1], self.in_layers[0].weight, self.in_layers[0].bias, _lib.GN_SILU)
+            xs = (xa, xb)
+        else:
+            h, x = group_norm_act_skip(x, self.in_layers[0], _lib.GN_SILU)
         if self.up:
             h = _Upsample2.apply(h)
             x = _Upsample2.apply(x)
@@ -269,8 +303,21 @@ class ResBlock(nn.Module):
         else:
             h = group_norm_act(h + (e + b1).to(h.dtype)[:, :, None, None], self.out_layers[0], _lib.GN_SILU)
         h = _conv_nobias(self.out_layers[3], h)
+        if xs is not None:                       # skip 1x1 conv of cat([xa, xb]) = conv(xa, W[:, :c0]) + conv(xb, W[:, c0:])
+            w0, w1 = self._split_skip_weights(xs[0].shape[1])
+            return _BiasAdd.apply(F.conv2d(xs[0], w0), h, b_out, F.conv2d(xs[1], w1))
         skip = x if isinstance(self.skip_connection, nn.Identity) else _conv_nobias(self.skip_connection, x)
         return _BiasAdd.apply(skip, h, b_out)
+
+    def _split_skip_weights(self, c0):
+        """The skip 1x1 convolution's (frozen) weight split at input channel c0, as two dense channels-last filters."""
+        w = self.skip_connection.weight
+        cache = getattr(self, "_skip_split", None)
+        if cache is None or cache[0] != c0 or cache[1].device != w.device or cache[1].dtype != w.dtype:
+            cl = torch.channels_last
+            cache = (c0, w.detach()[:, :c0].contiguous(memory_format=cl), w.detach()[:, c0:].contiguous(memory_format=cl))
+            self._skip_split = cache
+        return cache[1], cache[2]
 
     def _fp32_biases(self):
         """fp32 copies of the conv biases (weights are frozen; cached after the first call)."""
@@ -332,6 +379,7 @@ class UNetModel(nn.Module):
             raise NotImplementedError("only the resblock_updown=True variant (ffhq_10m) is on the accelerated path")
         self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
         self.out_channels, self.compute_dtype = out_channels, dtype
+        self.virtual_cat_min_pixels = 64 * 64      # skip concatenations at >= this many pixels stay virtual
         E = model_channels * 4
         self.time_embed = nn.Sequential(nn.Linear(model_channels, E), nn.SiLU(), nn.Linear(E, E))
         rb = dict(film=use_scale_shift_norm)
@@ -402,6 +450,7 @@ class UNetModel(nn.Module):
         for m in self.modules():
             if isinstance(m, ResBlock):
                 m._bias_cache = None
+                m._skip_split = None
         return r
 
     def prepare(self, device="cuda"):
@@ -428,8 +477,14 @@ class UNetModel(nn.Module):
                 h = module(h, embs)
             hs.append(h)
         h = self.middle_block(h, embs)
+        vec = 4 if dt == torch.float32 else 8
         for module in self.output_blocks:
-            h = module(_Cat2.apply(h, hs.pop()), embs)
+            skip = hs.pop()
+            if (h.shape[2] * h.shape[3] >= self.virtual_cat_min_pixels and h.shape[1] % vec == 0 and skip.shape[1] % vec == 0
+                    and not module[0].up and not module[0].down):
+                h = module((h, skip), embs)            # large maps: never materialise the concatenation
+            else:
+                h = module(_Cat2.apply(h, skip), embs)  # small maps: cheap concat, single-kernel resident GroupNorm
         h = group_norm_act(h, self.out[0], _lib.GN_SILU)
         return self.out[2](h)
 

@@ -264,3 +264,61 @@ def test_bias_add_kernel():
     assert torch.equal(ga, w) and torch.equal(gb, w)
     out1 = unet._BiasAdd.apply(a, None, bias)
     assert torch.equal(out1.detach(), (a.float() + bias[None, :, None, None]).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 128, 128, 64, 64), (3, 256, 128, 32, 40), (8, 512, 256, 16, 16), (1, 64, 96, 9, 5)])
+def test_group_norm_over_virtual_concat(dtype, shape):
+    """GroupNorm+SiLU over cat([x0, x1], 1) without the concatenation: forward, both input gradients, fused adds."""
+    from nhmc_b200 import unet, _lib
+    B, c0, c1, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    cl = torch.channels_last
+    mk = lambda c: (torch.randn(B, c, H, W, generator=g) * 1.5 + 0.3).cuda().to(dtype).contiguous(memory_format=cl)
+    x0, x1 = mk(c0).requires_grad_(True), mk(c1).requires_grad_(True)
+    C = c0 + c1
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).cuda(); beta = (0.1 * torch.randn(C, generator=g)).cuda()
+    y, a0, a1 = unet._CatGroupNormAct.apply(x0, x1, gamma, beta, _lib.GN_SILU)
+    w = torch.randn(B, C, H, W, generator=g).cuda().to(dtype); w0 = torch.randn(B, c0, H, W, generator=g).cuda().to(dtype)
+    w1 = torch.randn(B, c1, H, W, generator=g).cuda().to(dtype)
+    g0, g1 = torch.autograd.grad([y, a0, a1], (x0, x1), [w, w0, w1])
+    xr0, xr1 = x0.detach().float().requires_grad_(True), x1.detach().float().requires_grad_(True)
+    yr = _gn_ref(torch.cat([xr0, xr1], 1), gamma, beta, None, None, 1)
+    r0, r1 = torch.autograd.grad(yr, (xr0, xr1), w.float())
+    r0, r1 = r0 + w0.float(), r1 + w1.float()
+    tol = dict(atol=5e-5, rtol=1e-4) if dtype == torch.float32 else dict(atol=3e-2, rtol=2e-2)
+    np.testing.assert_allclose(y.detach().float().cpu().numpy(), yr.detach().cpu().numpy(), **tol)
+    for got, ref in ((g0, r0), (g1, r1)):
+        np.testing.assert_allclose(got.float().cpu().numpy(), ref.cpu().numpy(), atol=tol["atol"] * float(ref.abs().max()), rtol=tol["rtol"])
+    assert torch.equal(a0.detach(), x0.detach()) and torch.equal(a1.detach(), x1.detach())
+
+
+def test_bias_add_three_inputs():
+    from nhmc_b200 import unet
+    g = torch.Generator().manual_seed(10)
+    mk = lambda: torch.randn(2, 64, 6, 10, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    a, b, c = mk(), mk(), mk()
+    bias = torch.randn(64, generator=g).cuda()
+    out = unet._BiasAdd.apply(a, b, bias, c)
+    ref = (a.float() + (b.float() + c.float()) + bias[None, :, None, None]).to(torch.bfloat16)
+    assert torch.equal(out.detach(), ref)
+    w = torch.randn_like(out)
+    ga, gb, gc = torch.autograd.grad(out, (a, b, c), w)
+    assert torch.equal(ga, w) and torch.equal(gb, w) and torch.equal(gc, w)
+
+
+def test_unet_virtual_concat_matches_materialised_concat(golden):
+    """The same network with the skip concatenations kept virtual (default at >= 64x64) and fully materialised."""
+    g = golden("unet_small.npz")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd, cfg = _small_model(torch.float32)
+    outs = []
+    for min_pix in (1, 10 ** 9):
+        m.virtual_cat_min_pixels = min_pix
+        x = T(g["x"]).cuda().requires_grad_(True)
+        out = m(x, T(g["t"]).cuda())
+        (gx,) = torch.autograd.grad(out, x, T(g["w"]).cuda())
+        outs.append((out.detach(), gx))
+        np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=1e-4)
+        np.testing.assert_allclose(gx.cpu().numpy(), g["grad_x"], atol=5e-5 * max(1.0, float(np.abs(g["grad_x"]).max())), rtol=1e-3)
