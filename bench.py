@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-in-situ", action="store_true", help="skip the CUPTI breakdown of one step after the timed region")
     ap.add_argument("--profile-kernels", action="store_true", default=True)
     ap.add_argument("--no-graphs", action="store_true", help="run the step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--torch-profile", default="", help="write a torch.profiler kernel table of one step to this file")
@@ -208,10 +209,14 @@ def run_ours(args, rank, world, local_rank):
         kernels.profile_start()
         for _ in range(K):
             step()
-        prof = kernels.profile_stop()
+        prof_sz = kernels.profile_stop(by_size=True)
         smp._graphs = graphs
     else:
-        prof = kernels.profile_stop()
+        prof_sz = kernels.profile_stop(by_size=True)
+    prof = {}
+    for (name, _b), (n, tms, nbytes) in prof_sz.items():
+        a, b_, c = prof.get(name, (0, 0.0, 0))
+        prof[name] = (a + n, b_ + tms, c + nbytes)
     finite = bool(torch.isfinite(smp.x_prop).all() and torch.isfinite(smp.p).all())
 
     if dist is not None:
@@ -222,14 +227,37 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(lt)
         launches = int(lt.item())
 
-    if args.torch_profile and rank == 0:
+    in_situ = None
+    if rank == 0 and not args.no_in_situ:
+        # one graph replay under CUPTI (torch.profiler): device-side duration of every kernel IN SITU (warm L2,
+        # back-to-back launches) -- explains the step; the timed region above ran without any profiler
         from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof_t:
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
             step()
             torch.cuda.synchronize()
-        with open(args.torch_profile, "w") as f:
-            f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
-        prof_t.export_chrome_trace(args.torch_profile + ".trace.json")     # per-launch durations + grid sizes, in situ
+        fam = {}
+        for ev in prof_t.events():
+            if ev.device_type.name != "CUDA" or not ev.name or ev.name.startswith(("Memcpy", "Memset")):
+                continue
+            nm = ev.name
+            if "nhmc::" in nm:
+                key = nm.split("(")[0].replace("void ", "")
+            elif any(t in nm.lower() for t in ("cutlass", "nvjet", "cudnn", "gemm", "nhwcaddpadding")):
+                key = "library conv/gemm (cuDNN, cuBLAS)"
+            else:
+                key = "aten elementwise/copy"
+            n, us = fam.get(key, (0, 0.0))
+            fam[key] = (n + 1, us + ev.device_time)
+        tot = sum(us for _, us in fam.values())
+        if tot > 0:
+            in_situ = {"sum_ms": tot / 1e3, "families": {k: {"launches": n, "ms": us / 1e3} for k, (n, us) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:24]},
+                       "ours_ms": sum(us for k, (_, us) in fam.items() if k.startswith("nhmc::")) / 1e3,
+                       "library_ms": fam.get("library conv/gemm (cuDNN, cuBLAS)", (0, 0.0))[1] / 1e3,
+                       "note": "CUPTI kernel durations of ONE graph-replayed step after the timed region"}
+        if args.torch_profile:
+            with open(args.torch_profile, "w") as f:
+                f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
+            prof_t.export_chrome_trace(args.torch_profile + ".trace.json")     # per-launch durations + grid sizes
 
     # ---- end-to-end: the same step through the public API with HOST buffers ----
     e2e = None
@@ -260,21 +288,46 @@ def run_ours(args, rank, world, local_rank):
         return
     pk = peaks()
     value = world * B * K / (ms / 1e3)
-    # ---- roofline: our dominant kernel family inside the step (GroupNorm epilogue pair, HBM-bound) ----
+    # ---- roofline: our dominant kernel (family, tensor shape) inside the step -- HBM-bound GroupNorm epilogue ----
     kern = {}
     for name, (n, tms, nbytes) in sorted(prof.items()):
         kern[name] = {"calls_per_step": n / K, "ms_per_step": tms / K, "GBps": (nbytes / 1e9) / (tms / 1e3) if tms > 0 else None}
     ours_ms = sum(v["ms_per_step"] for v in kern.values())
-    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     roofline = None
-    if dom:
-        ach = kern[dom]["GBps"]
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"],
-                    "note": "algorithmic bytes (x read + y written; backward: x, dy read + dx written) / CUDA-event time "
-                            "per call, averaged over K steps" + (" (eager pass after the graph-replayed timed region)" if use_graphs else " of the timed region")}
+    if prof_sz:
+        (dname, dbytes), (dn, dms, dtot) = max(prof_sz.items(), key=lambda kv: kv[1][1])
+        ach = (dtot / 1e9) / (dms / 1e3)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")          # dram bytes per call from the committed ncu --set full capture
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get("%s:%d" % (dname, dbytes))
+        roofline = {"kernel": dname, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
+                    "algorithmic_bytes_per_call": int(dbytes), "calls_per_step": dn / K, "us_per_call": dms / dn * 1e3,
+                    "family_all_shapes": {"GBps": kern[dname]["GBps"], "frac": kern[dname]["GBps"] / pk["hbm"], "calls_per_step": kern[dname]["calls_per_step"]},
+                    "note": "dominant (kernel family, tensor shape) of ours by time; algorithmic bytes (forward: x read + y written; backward: "
+                            "x, dy (+ skip gradient) read + dx written) / CUDA-event time per call on the launching stream, averaged over K steps"
+                            + (" (eager pass right after the graph-replayed timed region)" if use_graphs else " of the timed region")
+                            + "; traffic = dram bytes per call from the ncu --set full capture in profiles/ (null if that shape was not captured)"}
     step_ms = ms / K
     unet_tflop = B * 3 * 2 * UNET_FWD_GFLOP / 1e3                       # fwd + input-VJP ~ 2x fwd FLOPs, 3 timesteps
+    # shares of the step: from the in-situ CUPTI durations when available (the eager event times of small kernels
+    # include launch gaps), else from the per-call events
+    sampler_names = ("leapfrog", "ddim_fwd", "ddim_bwd", "begin_iteration", "accept", "commit")
+    sampler_ms = sum(v["ms_per_step"] for k, v in kern.items() if k in sampler_names or k.startswith("op_"))
+    if in_situ:
+        lib_ms, own_ms, src = in_situ["library_ms"], in_situ["ours_ms"], "in situ (CUPTI, one graph-replayed step)"
+        total_ms = in_situ["sum_ms"]
+    else:
+        own_ms, lib_ms, total_ms, src = ours_ms, max(step_ms - ours_ms, 1e-9), step_ms, "CUDA events per call (eager)"
+    shares = {"own_kernels": own_ms / total_ms, "library_conv_gemm": lib_ms / total_ms,
+              "sampler_kernels_proper": sampler_ms / step_ms, "source": src,
+              "note": "own_kernels = every nhmc:: kernel (GroupNorm/softmax/resampling epilogues inside the U-Net included); "
+                      "sampler_kernels_proper = leapfrog + DDIM epilogues + operator loss/adjoint (the non-U-Net time of a leapfrog step)"}
+    unet_rep = {"algorithmic_tflop_per_step": unet_tflop, "library_ms_per_step": lib_ms,
+                "achieved_tflops": unet_tflop / (lib_ms / 1e3), "peak_tflops": pk["bf16"],
+                "tensor_pipe_frac": unet_tflop / (lib_ms / 1e3) / pk["bf16"],
+                "note": "cuDNN/cuBLAS bf16 convolutions and GEMMs (PyTorch call); time = " + src + "; peak = sustained bf16 of MEASURED_PEAKS.json"}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -284,11 +337,9 @@ def run_ours(args, rank, world, local_rank):
                    "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
                    "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
-        "roofline": roofline, "kernels": kern,
-        "non_unet_share": ours_ms / step_ms if step_ms > 0 else None,
-        "unet": {"algorithmic_tflop_per_step": unet_tflop, "achieved_tflops": unet_tflop / ((step_ms - ours_ms) / 1e3),
-                 "peak_tflops": pk["bf16"], "tensor_pipe_frac": unet_tflop / ((step_ms - ours_ms) / 1e3) / pk["bf16"],
-                 "note": "cuDNN/cuBLAS bf16 convolutions (PyTorch call), time = step - our kernels"},
+        "roofline": roofline, "kernels": kern, "in_situ": in_situ,
+        "shares": shares,
+        "unet": unet_rep,
         "finite": finite,
     }
     if not args.no_cpu_baseline and world >= 1:

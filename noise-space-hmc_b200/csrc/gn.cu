@@ -125,6 +125,30 @@ template <typename T> __device__ __forceinline__ float sigmoid_t(float z) {
 template <int MODE, typename T> __device__ __forceinline__ float gn_act(float z) {
   return MODE == NHMC_GN_PLAIN ? z : z * sigmoid_t<T>(z);
 }
+// Channels-last kernels fold the 1/2 of sigmoid(z) = (1 + tanh(z/2))/2 into the per-channel affine for 16-bit
+// activations: the affine yields h = z/2 directly, silu(z) = h + h*tanh(h) is one MUFU + one FMA per element and
+// silu'(z) = 1/2 + (tanh(h) + h*(1 - tanh(h)^2))/2 one MUFU + three FMAs (these kernels run within 2x of the issue
+// limit, so instruction count is bandwidth).  fp32 activations keep the exact sigmoid.
+template <int MODE, typename T> struct AffineHalf { static constexpr bool value = MODE != NHMC_GN_PLAIN && sizeof(T) == 2; };
+template <int MODE, typename T> __device__ __forceinline__ float gn_act_a(float w) {   // w = z/2 if AffineHalf else z
+  if (AffineHalf<MODE, T>::value) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(w));
+    return fmaf(w, t, w);
+  }
+  return MODE == NHMC_GN_PLAIN ? w : w * sigmoidf_fast(w);
+}
+template <int MODE, typename T> __device__ __forceinline__ float gn_dact_a(float w) {
+  if (MODE == NHMC_GN_PLAIN) return 1.0f;
+  if (AffineHalf<MODE, T>::value) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(w));
+    const float u = fmaf(-t, t, 1.0f);
+    return fmaf(0.5f, fmaf(w, u, t), 0.5f);
+  }
+  const float s = sigmoidf_fast(w);
+  return s * (1.0f + w * (1.0f - s));
+}
 template <int MODE, typename T> __device__ __forceinline__ float gn_dact(float z) {  // d act / dz
   if (MODE == NHMC_GN_PLAIN) return 1.0f;
   const float s = sigmoid_t<T>(z);
@@ -225,6 +249,7 @@ template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256, 3)
 gn_nhwc_stats_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
+  constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   extern __shared__ __align__(128) unsigned char dyn[];
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
   const int cvec = a.C / V;
@@ -243,8 +268,8 @@ gn_nhwc_stats_kernel(GnArgs a) {
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
-      ca[i] = rstd * gam * sc;                       // z = ca*x + cb
-      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+      ca[i] = rstd * gam * sc * kAff;                // z = ca*x + cb (z/2 for 16-bit SiLU, see AffineHalf)
+      cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
     }
   }
   const int64_t r_begin = (int64_t)blk * a.rows_per_cta;
@@ -267,7 +292,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
           unpack<T>(rd, dv);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+            const float d = dv[i] * gn_dact_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             s0[i] += d; s1[i] = fmaf(d, xv[i], s1[i]);
           }
         }
@@ -317,6 +342,7 @@ template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256, 3)
 gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
+  constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
@@ -347,8 +373,8 @@ gn_nhwc_apply_kernel(GnArgs a) {
     const float gam = a.gamma[c], bet = a.beta[c];
     const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
     const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
-    ca[i] = rstd * gam * sc;
-    cb[i] = (bet - mean * rstd * gam) * sc + sh;
+    ca[i] = rstd * gam * sc * kAff;
+    cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
     k1[i] = k2[i] = k3[i] = 0.f;
     if (PHASE == 1) {
       // dx = rstd*(du - m1 - u*m2), du = dy*act'(z)*gamma*(1+s), u = (x-mean)*rstd
@@ -377,13 +403,13 @@ gn_nhwc_apply_kernel(GnArgs a) {
         unpack<T>(rx, xv);
         if (PHASE == 0) {
 #pragma unroll
-          for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+          for (int i = 0; i < V; ++i) ov[i] = gn_act_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
         } else {
           float dv[V];
           unpack<T>(rd, dv);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
-            const float d = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+            const float d = dv[i] * gn_dact_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
           }
           if (has_add) {
@@ -513,6 +539,7 @@ template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256, PHASE == 1 ? 3 : 4)
 gn_nhwc_resident_kernel(const GnResArgs r) {
   constexpr int V = VecOf<T>::N;
+  constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
   const GnArgs& a = r.a;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -600,8 +627,8 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
-      ca[i] = rstd * gam * sc;
-      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+      ca[i] = rstd * gam * sc * kAff;
+      cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
     }
     char* dst = reinterpret_cast<char*>(a.out) + base;
 #pragma unroll 4
@@ -611,7 +638,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
         float xv[V], ov[V];
         unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
 #pragma unroll
-        for (int i = 0; i < V; ++i) ov[i] = gn_act<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+        for (int i = 0; i < V; ++i) ov[i] = gn_act_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
         store_vec<T>(reinterpret_cast<T*>(dst + o), ov);
       }
     }
@@ -626,8 +653,8 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
-      ca[i] = rstd * gam * sc;
-      cb[i] = (bet - mean * rstd * gam) * sc + sh;
+      ca[i] = rstd * gam * sc * kAff;
+      cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
     }
     for (unsigned ps = 0; ps < n_pass; ++ps) {
       if (ps % (unsigned)r.chunk_passes == 0) mbar_wait(bars + ps / (unsigned)r.chunk_passes, 0);
@@ -638,7 +665,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
         unpack<T>(*reinterpret_cast<const uint4*>(sd + o), dv);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          dv[i] = dv[i] * gn_dact<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+          dv[i] = dv[i] * gn_dact_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
           s0[i] += dv[i]; s1[i] = fmaf(dv[i], xv[i], s1[i]);
         }
         if (MODE != NHMC_GN_PLAIN) store_vec<T>(reinterpret_cast<T*>(sd + o), dv);   // own 16 bytes: no sync needed

@@ -16,15 +16,21 @@ def profile_start():
     _PROFILE = {}
 
 
-def profile_stop():
-    """Returns {name: (n_calls, total_ms, total_algorithmic_bytes)} (synchronises)."""
+def profile_stop(by_size=False):
+    """Returns {name: (n_calls, total_ms, total_algorithmic_bytes)} (synchronises); with by_size the key is
+    (name, algorithmic_bytes_per_call), i.e. one entry per tensor shape."""
     global _PROFILE
     prof, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
     out = {}
     for name, recs in (prof or {}).items():
-        ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-        out[name] = (len(recs), ms, sum(b for _, _, b in recs))
+        if not by_size:
+            ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+            out[name] = (len(recs), ms, sum(b for _, _, b in recs))
+            continue
+        for s, e, b in recs:
+            n, ms, tot = out.get((name, b), (0, 0.0, 0))
+            out[(name, b)] = (n + 1, ms + s.elapsed_time(e), tot + b)
     return out
 
 
