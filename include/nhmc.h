@@ -194,6 +194,14 @@ int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_prop, const f
                 float* x_keep, float* samples, int sched, int n_slots, int n_chains,
                 int64_t n_per_chain, nhmc_stream_t stream);
 
+/* Optional: keep (loss, gradient) of the CURRENT state per chain so that the
+ * evaluation at the top of each iteration (main_sampling.py:693-695, identical to the last evaluation
+ * of the previous accepted trajectory) is not repeated: accepted chains take the proposal's
+ * g = g_a (+ g_b) and loss, rejected chains keep theirs.  Call after nhmc_accept. */
+int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const float* g_a, const float* g_b,
+                     double* loss_state, const double* loss_prop, int n_chains, int64_t n_per_chain,
+                     nhmc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K9 U-Net epilogues: GroupNorm(32 groups, eps 1e-5, fp32 statistics) fused with its
  * follow-up (nn.py:17-19; unet_ffhq.py:253-257,277-280,319-323,356,683-685).

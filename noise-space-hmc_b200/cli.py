@@ -6,7 +6,7 @@
 
 Unknown flags are ignored like in the reference (`parse_known_args`, main_sampling.py:1031).  Additions:
 `--chains` (independent chains per GPU), `--synthetic` (seeded synthetic ground truth instead of the FFHQ folder),
-`--dtype`, `--cuda_graphs`, `--save_progress`.  Under torchrun, chains are sharded across the GPUs (dist.py).
+`--dtype`, `--cuda_graphs`, `--reuse_gradient`, `--save_progress`.  Under torchrun, chains are sharded across the GPUs (dist.py).
 """
 import argparse
 import math
@@ -49,6 +49,7 @@ def get_parser():
     p.add_argument("--synthetic", action="store_true", help="seeded synthetic ground truth instead of an image folder")
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"], help="score-network compute dtype")
     p.add_argument("--cuda_graphs", action="store_true", help="replay the leapfrog step as CUDA graphs")
+    p.add_argument("--reuse_gradient", action="store_true", help="keep (loss, gradient) of the current state instead of re-evaluating it at the top of each iteration (20 instead of 21 evaluations; main_sampling.py:693-695)")
     p.add_argument("--save_progress", action="store_true", help="PNG of every accepted epoch like the reference (main_sampling.py:735)")
     p.add_argument("--max_iters", type=int, default=None, help="stop after this many HMC iterations (smoke runs)")
     return p
@@ -139,7 +140,8 @@ def sample_image(opt, config, model_config, device):
     out = None
     if n:
         out = sampler.hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
-                          max_iters=opt.max_iters, on_iteration=on_it, cuda_graphs=opt.cuda_graphs)
+                          max_iters=opt.max_iters, on_iteration=on_it, cuda_graphs=opt.cuda_graphs,
+                          reuse_gradient=opt.reuse_gradient)
         out = out[None] if n == 1 else out                                  # [n, S, C, H, W]
     allc = ndist.gather_chains(out, opt.chains) if world > 1 else out
     if rank == 0 and allc is not None and allc.numel():

@@ -94,9 +94,44 @@ commit_kernel(const nhmc_chain* __restrict__ chains, float* __restrict__ x, cons
   }
 }
 
+// the gradient evaluation at the top of every iteration (main_sampling.py:693-695) repeats the last
+// evaluation of the previous ACCEPTED trajectory (same x, same loss, same gradient).  Keeping (loss, g) of the current
+// state per chain makes it 20 instead of 21 evaluations per iteration: accepted chains take the proposal's values.
+__global__ void __launch_bounds__(kThreads)
+commit_grad_kernel(const nhmc_chain* __restrict__ chains, float* __restrict__ g_state, const float* __restrict__ g_a,
+                   const float* __restrict__ g_b, double* __restrict__ loss_state, const double* __restrict__ loss_prop,
+                   int64_t n_vec) {
+  const int b = blockIdx.y;
+  if (!chains[b].accept) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) loss_state[b] = loss_prop[b];
+  float4* gs = reinterpret_cast<float4*>(g_state) + (int64_t)b * n_vec;
+  const float4* ga = reinterpret_cast<const float4*>(g_a) + (int64_t)b * n_vec;
+  const float4* gb = g_b ? reinterpret_cast<const float4*>(g_b) + (int64_t)b * n_vec : nullptr;
+  for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * kThreads) {
+    float4 t = ld_ro(ga + v);
+    if (gb) {   // same rounding as the leapfrog kernel's g_a + g_b
+      const float4 u = ld_ro(gb + v);
+      t.x = __fadd_rn(t.x, u.x); t.y = __fadd_rn(t.y, u.y); t.z = __fadd_rn(t.z, u.z); t.w = __fadd_rn(t.w, u.w);
+    }
+    st_stream(gs + v, t);
+  }
+}
+
 }  // namespace nhmc
 
 using namespace nhmc;
+
+extern "C" int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const float* g_a, const float* g_b,
+                                double* loss_state, const double* loss_prop, int n_chains, int64_t n_per_chain,
+                                nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(chains && g_state && g_a && loss_state && loss_prop && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(n_per_chain > 0 && n_per_chain % 4 == 0, "n_per_chain must be a positive multiple of 4");
+  NHMC_CHECK_ARG(aligned16(g_state) && aligned16(g_a) && (!g_b || aligned16(g_b)), "pointers must be 16-byte aligned");
+  const int64_t n_vec = n_per_chain / 4;
+  dim3 grid(cta_count(n_vec, kThreads * 4, n_chains), n_chains);
+  commit_grad_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(chains, g_state, g_a, g_b, loss_state, loss_prop, n_vec);
+  return NHMC_LAUNCH_CHECK();
+}
 
 extern "C" int nhmc_accept(nhmc_chain* chains, const float* u, double mass, int sched, int n_slots, int n_chains,
                            nhmc_stream_t stream) {

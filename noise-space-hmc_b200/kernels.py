@@ -159,6 +159,16 @@ def _film_stride(scale, shift, channels):
     return scale.stride(0)
 
 
+def commit_grad(chains, g_state, g_a, g_b, loss_state, loss_prop):
+    N = g_state[0].numel()
+    _req(g_state, torch.float32, "g_state"); _req(g_a, torch.float32, "g_a")
+    _req(loss_state, torch.float64, "loss_state"); _req(loss_prop, torch.float64, "loss_prop")
+    if g_b is not None: _req(g_b, torch.float32, "g_b")
+    with _timed("commit", 1, chains.n * N * 4 * (2 + (1 if g_b is not None else 0))):
+        check(lib().nhmc_commit_grad(chains.ptr(), _p(g_state), _p(g_a), _p(g_b), _p(loss_state), _p(loss_prop), chains.n, N,
+                                     _stream()), "nhmc_commit_grad")
+
+
 def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last, in_bias=None):
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]

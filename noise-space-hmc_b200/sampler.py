@@ -116,7 +116,10 @@ class HMCSampler:
     """State + one-iteration stepper shared by hmc() and hmc_latent()."""
 
     def __init__(self, x, evaluator, tau, epsilon, sigma_0, mass=1.0, sched=_lib.SCHED_PIXEL, sigma_y=None,
-                 n_slots=20):
+                 n_slots=20, reuse_gradient=False):
+        """reuse_gradient (opt-in): keep (loss, gradient) of the current state per chain instead
+        of re-evaluating them at the top of every iteration (main_sampling.py:693-695): 20 instead of 21 gradient
+        evaluations per iteration, same values (the reference recomputes exactly what it already had)."""
         self.ev = evaluator
         self.sched, self.mass, self.n_slots = sched, float(mass), n_slots
         self.x = x.detach().clone().float().contiguous()
@@ -132,12 +135,23 @@ class HMCSampler:
         self.u_dev = torch.empty(self.B, dtype=torch.float32, device=dev)
         self.leapfrog_steps_done = 0
         self._graphs = None          # {mode: (CUDAGraph, launches)} once capture_graphs() has run
+        self.reuse_gradient = bool(reuse_gradient)
+        self.g_state = torch.zeros_like(self.x) if self.reuse_gradient else None
+        self.loss_state = torch.zeros(self.B, dtype=torch.float64, device=dev) if self.reuse_gradient else None
+        self._state_valid = False    # (loss_state, g_state) hold the values at self.x
+        self._last = {}              # mode -> (g_a, g_b) of that step variant's evaluation (static buffers under graphs)
 
     # ---- one gradient evaluation + leapfrog kernel, eager or as a replayed CUDA graph -------------------
     def _step_eager(self, mode):
         src = self.x if mode == _lib.LF_FIRST else self.x_prop
         loss, g_a, g_b, _ = self.ev(src)
+        self._last[mode] = (g_a, g_b)
         kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
+
+    def _first_from_state(self):
+        """FIRST step without a gradient evaluation: energies, half kick and first drift from the kept (loss, g)."""
+        kernels.leapfrog(_lib.LF_FIRST, self.x, self.x_prop, self.p, self.g_state, None, self.loss_state, self.chains,
+                         self.mass, self.ws)
 
     def step(self, mode):
         """FIRST: evaluate at x, half kick, first drift (x -> x_prop). MIDDLE/LAST: evaluate at x_prop, kick (+ drift)."""
@@ -181,7 +195,15 @@ class HMCSampler:
         ev, ch, m = self.ev, self.chains, self.mass
         kernels.begin_iteration(ch, self.sched)
         self.p.copy_(p)
-        self.step(_lib.LF_FIRST)                                                 # main_sampling.py:693-702,706
+        if self.reuse_gradient and self._state_valid:
+            self._first_from_state()                                             # no evaluation #0
+        else:
+            self.step(_lib.LF_FIRST)                                             # main_sampling.py:693-702,706
+            if self.reuse_gradient:   # first iteration: every chain's state values come from this evaluation
+                g_a, g_b = self._last[_lib.LF_FIRST]
+                torch.add(g_a, g_b, out=self.g_state) if g_b is not None else self.g_state.copy_(g_a)
+                self.loss_state.copy_(ev.loss)
+                self._state_valid = True
         for l in range(self.L):                                                  # main_sampling.py:704-715
             self.step(_lib.LF_LAST if l == self.L - 1 else _lib.LF_MIDDLE)
         xc = ev.xc
@@ -189,6 +211,9 @@ class HMCSampler:
         self.u_dev.copy_(torch.as_tensor(u, dtype=torch.float32).reshape(self.B), non_blocking=True)
         kernels.accept(ch, self.u_dev, m, self.sched, self.n_slots)              # main_sampling.py:717-749
         kernels.commit(ch, self.x, self.x_prop, xc, self.x_keep, self.samples, self.sched, self.n_slots)
+        if self.reuse_gradient:
+            g_a, g_b = self._last[_lib.LF_LAST]                                  # evaluation at the proposal
+            kernels.commit_grad(ch, self.g_state, g_a, g_b, self.loss_state, ev.loss)
         return xc
 
     def leapfrog_step_host(self, x_host, p_host):
@@ -249,7 +274,7 @@ def _model_of(algo):
 
 
 def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False):
+        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False, reuse_gradient=False):
     """Drop-in for main_sampling.hmc (main_sampling.py:660-774).
 
     x: [B,3,H,W] initial noise; b: fp32 betas [1000]; seq/seq_next: timestep lists; algo: object with
@@ -269,7 +294,8 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
     y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
     m = float(getattr(opt, "m", 1.0))
     ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
-    smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20)
+    smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20,
+                     reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False))
     if cuda_graphs or getattr(opt, "cuda_graphs", False):
         smp.capture_graphs()
     dm, du = _default_draws(m)

@@ -145,6 +145,47 @@ def test_hmc_batched_chains_equal_single_chains(golden):
         np.testing.assert_allclose(st1["H"][0], stb["H"][b], rtol=1e-5)
 
 
+def test_reuse_gradient_skips_evaluation_zero_with_identical_results(golden):
+    """keeping (loss, gradient) of the current state gives the same chain with 20 instead of 21
+    network evaluations per iteration (mixed accepts / rejects across a batch of chains, eager and graph replay)."""
+    from nhmc_b200 import _lib, sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
+    B, n_it = 3, 4
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
+    ps = [torch.randn(B, 3, 32, 32, generator=gen) for _ in range(n_it)]
+    # u = 0 always accepts (unless exp(-dH) underflows to 0), u ~ 1 rejects unless the move is (nearly) downhill
+    us = [torch.tensor([0.0 if (i + b) % 2 == 0 else 0.9999 for b in range(B)]) for i in range(n_it)]
+
+    def run(reuse, graphs):
+        ev = sampler.GradEvaluator(net, steps, op, y.cuda(), x.cuda())
+        smp = sampler.HMCSampler(x.cuda(), ev, 1.0, 0.05, 0.1, sched=_lib.SCHED_PIXEL, reuse_gradient=reuse)
+        if graphs:
+            smp.capture_graphs()
+        n0 = ev.n_net_fwd
+        hist = []
+        for p, u in zip(ps, us):
+            smp.iteration(p.cuda(), u)
+            hist.append(smp.chains.read()["accept"].copy())
+        return smp.x.cpu(), smp.chains.read(), np.stack(hist), ev.n_net_fwd - n0
+
+    xa, sta, ha, na = run(False, False)
+    assert 0 < ha.sum() < ha.size, "the draws should produce both accepts and rejects"
+    for graphs in (False, True):
+        xb, stb, hb, nb = run(True, graphs)
+        assert np.array_equal(ha, hb)
+        assert np.array_equal(sta["epoch"], stb["epoch"]) and np.array_equal(sta["epsilon"], stb["epsilon"])
+        # same arithmetic on the same values; what differs is last-bit nondeterminism of the network's library kernels,
+        # amplified by 80 chaotic leapfrog steps -- hence the north-star image tolerance, not bit equality
+        np.testing.assert_allclose(xb.numpy(), xa.numpy(), atol=1e-3)
+        np.testing.assert_allclose(stb["H"], sta["H"], rtol=1e-4)
+        if not graphs:
+            L = 20
+            assert na == n_it * (L + 1) * 3 and nb == (n_it * L + 1) * 3, (na, nb)
+
+
 def test_no_cpu_fallback():
     import nhmc_b200
     opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=0.1)
