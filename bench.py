@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | hdr | deblur_aniso | phase_retrieval")
+    ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | inpaint_box | hdr | deblur_aniso | deblur_gauss | phase_retrieval | color")
     ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -119,9 +119,15 @@ def make_operator(deg, device):
     from nhmc_b200 import operators as P
     if deg.startswith("sr"):
         return P.SuperResolution(3, 256, int(deg[2:]), device)
+    if "inp" in deg and "box" in deg:
+        return P.Inpainting.box(3, 256, device, left=64, up=64)
     if "inp" in deg:
         torch.manual_seed(5678)
         return P.Inpainting.random(3, 256, device)
+    if "deblur_gauss" in deg:
+        return P.Deblurring(P.gaussian_taps(10.0, half=2), 3, 256, device)
+    if deg == "color":
+        return P.Colorization(256, device)
     if "hdr" in deg:
         return P.HDR(3, 256, device)
     if deg == "deblur_aniso":
@@ -360,9 +366,15 @@ def _cpu_step_fn(deg):
     model = lambda xx, tt: ounet.unet_forward(sd, cfg, xx, tt)
     if deg.startswith("sr"):
         op = oops.SuperResolution(3, 256, int(deg[2:]))
+    elif "inp" in deg and "box" in deg:
+        op = oops.Inpainting.from_missing_indices(3, 256, oops.box_missing_indices(3, 256, 64, 64).numpy())
     elif "inp" in deg:
         torch.manual_seed(5678)
         op = oops.Inpainting(3, 256, oops.random_inpaint_missing_pixels(256))
+    elif "deblur_gauss" in deg:
+        op = oops.Deblurring.from_kernel(oops.gaussian_taps(10.0, half=2), 3, 256)
+    elif deg == "color":
+        op = oops.Colorization(256)
     elif "hdr" in deg:
         op = oops.HDR()
     elif deg == "deblur_aniso":

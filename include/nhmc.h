@@ -134,6 +134,8 @@ int nhmc_ddim_bwd(const float* g_a, const float* g_b, const uint32_t* mask, floa
 #define NHMC_OP_HDR 2      /* Hfuncs.py:406-445  */
 #define NHMC_OP_DEBLUR2D 3 /* Hfuncs.py:448-523  */
 #define NHMC_OP_PHASE 4    /* Hfuncs.py:318-366 + fastmri_utils.py:67-114 */
+#define NHMC_OP_DENOISE 5  /* Hfuncs.py:157-177  (H = identity)                */
+#define NHMC_OP_COLOR 6    /* Hfuncs.py:655-695  (per-pixel weighted grey value) */
 
 typedef struct nhmc_op {
   int32_t kind;
@@ -149,11 +151,14 @@ typedef struct nhmc_op {
   const int32_t* kept_pix;    /* inpaint: [n_kept] ascending pixel indices                   */
   const int32_t* pix_to_kept; /* inpaint: [D*D] rank among kept pixels, -1 if dropped        */
   const float* U1;            /* deblur2d: [D,D] row-major, as Hfuncs.Deblurring2D.U_small1  */
+                              /* (Gaussian `Deblurring`, Hfuncs.py:236-316: U1 = U2, V1 = V2) */
   const float* V1;
   const float* U2;
   const float* V2;
   const float* gain;          /* deblur2d: [C,D,D] spectral gain D_c (SURVEY.md headline 6)  */
   const float* gain_pinv;     /* deblur2d: [C,D,D] 1/D_c where non-zero else 0               */
+  float coef[12];             /* color: [0..2] forward weights w_c (y = sum_c w_c x_c),      */
+                              /*        [3..5] adjoint weights, [6..8] pseudo-inverse weights */
 } nhmc_op;
 
 /* measurement elements per chain (M) for this operator */

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 F32, BF16, F16 = 0, 1, 2
 LF_FIRST, LF_MIDDLE, LF_LAST = 0, 1, 2
 SCHED_PIXEL, SCHED_LATENT = 0, 1
-OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE = 0, 1, 2, 3, 4
+OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE, OP_DENOISE, OP_COLOR = 0, 1, 2, 3, 4, 5, 6
 GN_PLAIN, GN_SILU, GN_FILM_SILU = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
@@ -27,7 +27,7 @@ class OpDesc(C.Structure):
                 ("n_kept", C.c_int32), ("pad", C.c_int32), ("no_clamp", C.c_int32), ("reserved", C.c_int32),
                 ("kept_pix", C.c_void_p), ("pix_to_kept", C.c_void_p),
                 ("U1", C.c_void_p), ("V1", C.c_void_p), ("U2", C.c_void_p), ("V2", C.c_void_p),
-                ("gain", C.c_void_p), ("gain_pinv", C.c_void_p)]
+                ("gain", C.c_void_p), ("gain_pinv", C.c_void_p), ("coef", C.c_float * 12)]
 
 
 def build(verbose=False):

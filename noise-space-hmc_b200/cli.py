@@ -67,17 +67,25 @@ def prepare_measurement(opt, config, device):
     deg, C, D = opt.deg, config.data.channels, config.data.image_size
     if "sr" in deg and not deg.startswith("sr_bicubic"):
         H = P.SuperResolution(C, D, int(deg[2:]), device)
-    elif "inp" in deg and "box" not in deg:
+    elif "inp" in deg and "box" in deg:
+        H = P.Inpainting.box(C, D, device)                         # two random.randint(16, 112) draws (:292-293)
+    elif "inp" in deg:
         H = P.Inpainting.random(C, D, device)                      # torch.randperm on the global CPU generator (:302)
+    elif "deblur_gauss" in deg:
+        H = P.Deblurring(P.gaussian_taps(10.0, half=2), C, D, device)        # 5 taps, sigma 10 (:307-312)
     elif "phase" in deg:
         H = P.PhaseRetrievalOperator(2.0, device, C, D)
     elif "hdr" in deg:
         H = P.HDR(C, D, device)
     elif deg == "deblur_aniso":
         H = P.Deblurring2D(P.gaussian_taps(1.0), P.gaussian_taps(20.0), C, D, device)
+    elif deg == "color":
+        H = P.Colorization(D, device)
+    elif deg in ("deno", "denoise", "denoising"):                  # Hfuncs.Denoising; the reference's driver has no --deg for it
+        H = P.Denoising(C, D, device)
     else:
         raise SystemExit("ERROR: degradation type %r is not on the accelerated hmc path "
-                         "(supported: inpaint_random, sr<r>, deblur_aniso, hdr, phase_retrieval)" % deg)
+                         "(supported: inpaint_random, inpaint_box, sr<r>, deblur_aniso, deblur_gauss, hdr, phase_retrieval, color, deno)" % deg)
     opt.sigma_0 = 2 * opt.sigma_0
     return H, opt.sigma_0, deg
 

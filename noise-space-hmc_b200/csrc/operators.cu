@@ -225,6 +225,97 @@ hdr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, 
   if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
 }
 
+// =====================================================================================
+// Denoising (H = identity, Hfuncs.py:157-177): same fused pass as HDR without the x/0.5 clip
+// =====================================================================================
+__global__ void __launch_bounds__(kThreads)
+denoise_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                         float* __restrict__ xc_out, int64_t N, double* loss, RedWs ws, int nc) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t n_vec = N / 4;
+  const float4* xb = reinterpret_cast<const float4*>(xh + (int64_t)b * N);
+  const float4* yb = reinterpret_cast<const float4*>(y + (int64_t)b * N);
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
+    const float4 xv = ld_ro(xb + v), yv = ld_ro(yb + v);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+    float gs[4], cs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      cs[j] = clampx(xs[j], nc);
+      const float r = __fsub_rn(ys[j], cs[j]);
+      acc += (double)r * (double)r;
+      gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+    }
+    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+}
+
+// =====================================================================================
+// Colorization (Hfuncs.py:655-695): y[b, pix] = sum_c w_c x[b, c, pix]; H^T r = a_c r; H^+ y = p_c y
+// (w, a, p: products of the 1x3 SVD factors, built by the caller with the reference's torch.svd call)
+// =====================================================================================
+struct Coef3 { float v[3]; };
+__global__ void color_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t P, Coef3 w) {
+  const int b = blockIdx.y;
+  const float* xb = x + (int64_t)b * 3 * P;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+    y[(int64_t)b * P + p] = fmaf(w.v[2], xb[2 * P + p], fmaf(w.v[1], xb[P + p], w.v[0] * xb[p]));
+}
+__global__ void color_adj_kernel(const float* __restrict__ r, float* __restrict__ out, int64_t P, Coef3 a) {
+  const int b = blockIdx.y;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const float v = r[(int64_t)b * P + p];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[((int64_t)b * 3 + c) * P + p] = a.v[c] * v;
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+color_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                       float* __restrict__ xc_out, int64_t P, Coef3 w, Coef3 a, double* loss, RedWs ws, int nc) {
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int64_t n_vec = P / 4;
+  const float* xb = xh + (int64_t)b * 3 * P;
+  double acc = 0.0;
+  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
+    float xs[3][4], cs[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 t = ld_ro(reinterpret_cast<const float4*>(xb + c * P) + v);
+      xs[c][0] = t.x; xs[c][1] = t.y; xs[c][2] = t.z; xs[c][3] = t.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cs[c][j] = clampx(xs[c][j], nc);
+    }
+    const float4 yv = ld_ro(reinterpret_cast<const float4*>(y + (int64_t)b * P) + v);
+    const float ys[4] = {yv.x, yv.y, yv.z, yv.w};
+    float rs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float yh = fmaf(w.v[2], cs[2][j], fmaf(w.v[1], cs[1][j], w.v[0] * cs[0][j]));
+      rs[j] = __fsub_rn(ys[j], yh);
+      acc += (double)rs[j] * (double)rs[j];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gs[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gs[j] = -(2.0f * (a.v[c] * rs[j])) * maskx(xs[c][j], nc);
+      st_stream(reinterpret_cast<float4*>(g + ((int64_t)b * 3 + c) * P) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+      if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + ((int64_t)b * 3 + c) * P) + v, make_float4(cs[c][0], cs[c][1], cs[c][2], cs[c][3]));
+    }
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+}
+static inline Coef3 coef3(const nhmc_op* op, int first) { Coef3 c; for (int i = 0; i < 3; ++i) c.v[i] = op->coef[first + i]; return c; }
+
 static inline int sr_tile_rows(int D, int r) {
   int TR = r;
   while (TR < 16 && TR * 2 <= D) TR *= 2;  // ~1024 float4 per CTA at D = 256
@@ -249,6 +340,11 @@ static int check_op(const nhmc_op* op) {
     case NHMC_OP_PHASE:
       NHMC_CHECK_ARG(op->pad >= 0, "bad pad");
       break;
+    case NHMC_OP_DENOISE:
+      break;
+    case NHMC_OP_COLOR:
+      NHMC_CHECK_ARG(op->channels == 3, "colorization is defined for 3 channels");
+      break;
     default:
       set_error("unknown operator kind %d", op->kind);
       return NHMC_ERR_ARG;
@@ -269,6 +365,8 @@ extern "C" int64_t nhmc_op_meas_size(const nhmc_op* op) {
     case NHMC_OP_HDR: return C * D * D;
     case NHMC_OP_DEBLUR2D: return C * D * D;
     case NHMC_OP_PHASE: return C * (D + 2 * op->pad) * (D + 2 * op->pad);
+    case NHMC_OP_DENOISE: return C * D * D;
+    case NHMC_OP_COLOR: return D * D;
     default: return -1;
   }
 }
@@ -308,6 +406,14 @@ extern "C" int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int 
       hdr_fwd_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x, y, total);
       break;
     }
+    case NHMC_OP_DENOISE: {
+      const int64_t total = (int64_t)n_chains * C * P;
+      copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x, y, total);
+      break;
+    }
+    case NHMC_OP_COLOR:
+      color_fwd_kernel<<<dim3(cta_count(P, kThreads, n_chains), n_chains), kThreads, 0, st>>>(x, y, P, coef3(op, 0));
+      break;
     case NHMC_OP_DEBLUR2D: {
       NHMC_CHECK_ARG(workspace, "workspace required");
       char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
@@ -339,6 +445,12 @@ static int adjoint_or_pinv(const nhmc_op* op, const float* r, float* out, int n_
     case NHMC_OP_HDR:
       if (!pinv) { set_error("hdr is non-linear: no adjoint; use nhmc_op_loss_grad"); return NHMC_ERR_UNSUPPORTED; }
       copy_kernel<<<cta_count((int64_t)n_chains * N, kThreads * 4, 1), kThreads, 0, st>>>(r, out, (int64_t)n_chains * N);
+      break;
+    case NHMC_OP_DENOISE:
+      copy_kernel<<<cta_count((int64_t)n_chains * N, kThreads * 4, 1), kThreads, 0, st>>>(r, out, (int64_t)n_chains * N);
+      break;
+    case NHMC_OP_COLOR:
+      color_adj_kernel<<<dim3(cta_count(P, kThreads, n_chains), n_chains), kThreads, 0, st>>>(r, out, P, coef3(op, pinv ? 6 : 3));
       break;
     case NHMC_OP_DEBLUR2D: {
       NHMC_CHECK_ARG(workspace, "workspace required");
@@ -400,6 +512,18 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
       NHMC_CHECK_ARG(N % 4 == 0 && aligned16(y), "N must be a multiple of 4");
       dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
       hdr_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, N, loss, ws, op->no_clamp);
+      break;
+    }
+    case NHMC_OP_DENOISE: {
+      NHMC_CHECK_ARG(N % 4 == 0 && aligned16(y), "N must be a multiple of 4");
+      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      denoise_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, N, loss, ws, op->no_clamp);
+      break;
+    }
+    case NHMC_OP_COLOR: {
+      NHMC_CHECK_ARG(P % 4 == 0 && aligned16(y), "img_dim^2 must be a multiple of 4");
+      dim3 grid(cta_count(P / 4, kThreads, n_chains), n_chains);
+      color_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, P, coef3(op, 0), coef3(op, 3), loss, ws, op->no_clamp);
       break;
     }
     case NHMC_OP_DEBLUR2D:

@@ -124,11 +124,28 @@ class Inpainting(Operator):
         self.desc.pix_to_kept = self.pix_to_kept.data_ptr()
 
     @classmethod
+    def box(cls, channels, img_dim, device, left=None, up=None, size=128):
+        """Box inpainting (main_sampling.py:290-299); left/up default to the reference's random.randint(16, 112) draws."""
+        import random
+        left = random.randint(16, 112) if left is None else left
+        up = random.randint(16, 112) if up is None else up
+        return cls(channels, img_dim, box_missing_indices(channels, img_dim, left, up, size), device)
+
+    @classmethod
     def random(cls, channels, img_dim, device, frac=0.92):
         """main_sampling.py:302-305: randperm on the global CPU generator, first 92 % of the pixels dropped."""
         missing_r = channels * torch.randperm(img_dim ** 2)[: int(img_dim ** 2 * frac)].long()
         missing = torch.cat([missing_r + c for c in range(channels)], dim=0)
         return cls(channels, img_dim, missing, device)
+
+
+def box_missing_indices(channels, img_dim, left, up, size=128):
+    """main_sampling.py:290-299 (`inp` + `box` in --deg): a size x size box whose first image row is `left` and first
+    column is `up` (the reference's names), as channel-interleaved indices (3*pix + c), ascending.  The reference
+    draws left, up = random.randint(16, 112) twice from python's `random` (seeded with --seed)."""
+    m = torch.zeros(img_dim, img_dim, channels)
+    m[left:left + size, up:up + size, :] = 1.0
+    return torch.nonzero(m.view(-1)).squeeze(1)
 
 
 class SuperResolution(Operator):
@@ -210,6 +227,50 @@ class Deblurring2D(Operator):
         d.gain, d.gain_pinv = self.gain.data_ptr(), self.gain_pinv.data_ptr()
 
 
+class Deblurring(Deblurring2D):
+    """Separable (Gaussian / uniform) deblurring, Hfuncs.py:236-316: the same spectral form as Deblurring2D with one
+    1-D kernel on both axes -- Y_c = U (G_c .* (V^T X_c V)) U^T -- including the same tiled-singulars quirk
+    (`singulars()` = `_singulars.repeat(1, 3)`, :293-294, against the channel-interleaved `Vt`, :266-272)."""
+
+    def __init__(self, kernel, channels, img_dim, device, tables=None, zero=3e-2):
+        if tables is not None:
+            U, V, s_sorted, perm = tables
+            tables = (U, V, U, V, s_sorted, perm)
+        super().__init__(kernel, kernel, channels, img_dim, device, tables=tables, zero=zero)
+        self.U_small, self.V_small = self.U_small1, self.V_small1
+
+
+class Denoising(Operator):
+    """H = identity on the CHW-flattened image (Hfuncs.py:157-177)."""
+    kind = _lib.OP_DENOISE
+
+
+class Colorization(Operator):
+    """y[b, pix] = grey value of the pixel (Hfuncs.py:655-695): H = U S V^T of the 1x3 matrix [0.3333, 0.3334, 0.3333]
+    applied per pixel.  The three weight triples handed to the kernels are products of the SVD factors, which are
+    built with the reference's own torch.svd call (or taken from a reference object)."""
+    kind = _lib.OP_COLOR
+
+    def __init__(self, img_dim, device, factors=None):
+        super().__init__(3, img_dim, device)
+        if factors is None:
+            Hs = torch.Tensor([[0.3333, 0.3334, 0.3333]])
+            U, S, V = torch.svd(Hs, some=False)
+        else:
+            U, S, V = [torch.as_tensor(t).detach().cpu().float() for t in factors]
+        self.U_small, self.singulars_small, self.V_small = U.to(self.device), S.to(self.device), V.to(self.device)
+        u, sv = float(U[0, 0]), float(S[0])
+        v0 = [float(V[c, 0]) for c in range(3)]
+        f32 = lambda t: float(np.float32(t))
+        for c in range(3):
+            self.desc.coef[c] = f32(np.float32(u) * (np.float32(sv) * np.float32(v0[c])))            # H:   U (s (V^T x)_0)
+            self.desc.coef[3 + c] = f32(np.float32(v0[c]) * (np.float32(sv) * np.float32(u)))        # H^T: V (s (U^T r))
+            self.desc.coef[6 + c] = f32(np.float32(v0[c]) * (np.float32(u) / np.float32(sv)))        # H^+: V ((U^T y) / s)
+
+    def meas_shape(self, B):
+        return (B, self.img_dim ** 2)
+
+
 class PhaseRetrievalOperator(Operator):
     """y = |fft2c(pad(x, 64))| (Hfuncs.py:318-366, fastmri_utils.py:67-89); image-shaped measurement."""
     kind = _lib.OP_PHASE
@@ -242,6 +303,14 @@ def from_reference(H_funcs, channels, img_dim, device):
         return Deblurring2D(None, None, H_funcs.channels, H_funcs.img_dim, device,
                             tables=(H_funcs.U_small1, H_funcs.V_small1, H_funcs.U_small2, H_funcs.V_small2,
                                     H_funcs._singulars, H_funcs._perm))
+    if name == "Deblurring" or (hasattr(H_funcs, "U_small") and hasattr(H_funcs, "_perm") and hasattr(H_funcs, "singulars_small")
+                                and not hasattr(H_funcs, "small_dim") and tuple(H_funcs.U_small.shape) == (img_dim, img_dim)):
+        return Deblurring(None, H_funcs.channels, H_funcs.img_dim, device,
+                          tables=(H_funcs.U_small, H_funcs.V_small, H_funcs._singulars, H_funcs._perm))
+    if name == "Colorization" or hasattr(H_funcs, "Vt_small"):
+        return Colorization(H_funcs.img_dim, device, factors=(H_funcs.U_small, H_funcs.singulars_small, H_funcs.V_small))
+    if name == "Denoising":
+        return Denoising(channels, img_dim, device)
     if hasattr(H_funcs, "ratio") and hasattr(H_funcs, "y_dim") and hasattr(H_funcs, "V_small"):
         return SuperResolution(H_funcs.channels, H_funcs.img_dim, H_funcs.ratio, device)
     if name == "HDR":
@@ -250,4 +319,4 @@ def from_reference(H_funcs, channels, img_dim, device):
         op = PhaseRetrievalOperator(2.0, device, channels, img_dim)
         op.pad = int(H_funcs.pad); op.desc.pad = op.pad
         return op
-    raise _lib.NhmcError("operator %s is not on the accelerated path (inpaint, sr, hdr, deblur_aniso, phase)" % name)
+    raise _lib.NhmcError("operator %s is not on the accelerated path (inpaint, sr, hdr, deblur_aniso, deblur_gauss, phase, color, deno)" % name)

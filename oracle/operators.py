@@ -231,6 +231,80 @@ class Deblurring2D(_Base):
         return (V1 @ (Dinv * T) @ V2.t()).reshape(B, -1)
 
 
+def deblur1d_tables(kernel, img_dim, zero=3e-2):
+    """SVD tables of the separable `Deblurring` (Hfuncs.py:245-262): (U, V, singulars_sorted, perm)."""
+    U, s, V = torch.svd(band_matrix(kernel, img_dim), some=False)
+    s = s.clone()
+    s[s < zero] = 0
+    ss = torch.matmul(s.reshape(img_dim, 1), s.reshape(1, img_dim)).reshape(img_dim ** 2)
+    s_sorted, perm = ss.sort(descending=True)
+    return U, V, s_sorted, perm
+
+
+class Deblurring(Deblurring2D):
+    """Separable deblurring (`deblur_gauss`, Hfuncs.py:236-316): Deblurring2D with the same factors on both axes;
+    `singulars()` (:293-294) tiles exactly as Deblurring2D's does, so the same D_c gain applies."""
+
+    def __init__(self, channels, img_dim, U, V, s_sorted, perm):
+        super().__init__(channels, img_dim, U, V, U, V, s_sorted, perm)
+
+    @classmethod
+    def from_kernel(cls, kernel, channels, img_dim):
+        return cls(channels, img_dim, *deblur1d_tables(kernel, img_dim))
+
+
+# --------------------------------------------------------------------------------------
+# Denoising (identity): Hfuncs.py:157-177
+# --------------------------------------------------------------------------------------
+class Denoising(_Base):
+    def H(self, x):
+        return x.reshape(x.shape[0], -1)
+
+    def Ht(self, r):
+        return r.reshape(r.shape[0], -1)
+
+    def H_pinv(self, y):
+        return y.reshape(y.shape[0], -1)
+
+
+# --------------------------------------------------------------------------------------
+# Colorization: Hfuncs.py:655-695
+# --------------------------------------------------------------------------------------
+class Colorization(_Base):
+    """y[b, pix] = U00 * s0 * sum_c V[c,0] x[b,c,pix]: `Vt` (:672-679) rotates every pixel's RGB needle by V^T and
+    stores component-major, `H` keeps the first D*D entries (component 0) times the single singular value, `U` is the
+    1x1 factor.  H^T r = V[:,0] s0 U00 r, H^+ y = V[:,0] U00 y / s0."""
+
+    def __init__(self, img_dim, U=None, S=None, V=None):
+        self.img_dim = img_dim
+        if U is None:
+            U, S, V = torch.svd(torch.Tensor([[0.3333, 0.3334, 0.3333]]), some=False)
+        self.u, self.s, self.v0 = U[0, 0], S[0], V[:, 0]
+
+    def H(self, x):
+        B = x.shape[0]
+        xf = x.reshape(B, 3, -1)
+        v0 = self.v0.to(x.dtype)
+        return self.u.to(x.dtype) * (self.s.to(x.dtype) * (v0[None, :, None] * xf).sum(1))
+
+    def Ht(self, r):
+        B = r.shape[0]
+        k = (self.v0 * self.s * self.u).to(r.dtype)
+        return (k[None, :, None] * r.reshape(B, 1, -1)).reshape(B, -1)
+
+    def H_pinv(self, y):
+        B = y.shape[0]
+        k = (self.v0 * self.u / self.s).to(y.dtype)
+        return (k[None, :, None] * y.reshape(B, 1, -1)).reshape(B, -1)
+
+
+def box_missing_indices(channels, img_dim, left, up, size=128):
+    """main_sampling.py:290-299: channel-interleaved indices (3*pix + c) of a size x size box at rows left.., cols up.."""
+    m = torch.zeros(img_dim, img_dim, channels)
+    m[left:left + size, up:up + size, :] = 1.0
+    return torch.nonzero(m.view(-1)).squeeze(1)
+
+
 # --------------------------------------------------------------------------------------
 # Phase retrieval: Hfuncs.py:318-366, fft2_m Hfuncs.py:8-12, fft2c_new fastmri_utils.py:67-89
 # --------------------------------------------------------------------------------------

@@ -138,6 +138,42 @@ def gold_operators():
          s_head=Hd256._singulars[:16])
 
 
+# ---------------------------------------------------------------------------- operators, next rows
+def gold_operators_ext():
+    """deblur_gauss, color, deno and box inpainting, recorded from the reference's own Hfuncs classes."""
+    rec = {}
+    D, B = 32, 2
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(B, 3, D, D, generator=g) * 0.8
+
+    # Gaussian deblurring: kernel exactly as main_sampling.py:307-312
+    sigma = 10
+    pdf = lambda v: torch.exp(torch.Tensor([-0.5 * (v / sigma) ** 2]))
+    kernel = torch.Tensor([pdf(-2), pdf(-1), pdf(0), pdf(1), pdf(2)])
+    Hg = Hfuncs.Deblurring(kernel / kernel.sum(), 3, D, "cpu")
+    for k in ("U_small", "V_small", "_singulars", "_perm"):
+        rec["dgauss_tab_" + k.strip("_")] = getattr(Hg, k)
+    rec["dgauss_kernel"] = kernel / kernel.sum()
+    _op_record("dgauss", Hg, x, rec)
+
+    Hc = Hfuncs.Colorization(D, "cpu")
+    for k in ("U_small", "singulars_small", "V_small"):
+        rec["color_tab_" + k] = getattr(Hc, k)
+    _op_record("color", Hc, x, rec)
+
+    _op_record("deno", Hfuncs.Denoising(3, D, "cpu"), x, rec)
+
+    # box inpainting: the index construction of main_sampling.py:290-299 at D = 32 with a 16 x 16 box
+    left, up, size = 5, 9, 16
+    missing = torch.zeros([D, D, 3])
+    missing[left:left + size, up:up + size, :] = 1.0
+    missing = torch.nonzero(missing.view(-1).long()).squeeze()
+    rec["box_missing"] = missing
+    rec["box_geom"] = np.array([left, up, size])
+    _op_record("box", Hfuncs.Inpainting(3, D, missing, "cpu"), x, rec)
+    save("operators_ext.npz", **rec)
+
+
 # ---------------------------------------------------------------------------- DDIM epilogue
 def gold_ddim():
     net = TinyEpsNet()
@@ -327,6 +363,6 @@ def gold_hmc_latent_trace():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "ddim", "unet", "hmc_trace", "hmc_latent_trace"]
+    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "operators_ext", "ddim", "unet", "hmc_trace", "hmc_latent_trace"]
     for w in which:
         globals()["gold_" + w]()

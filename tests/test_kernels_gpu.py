@@ -189,6 +189,90 @@ def test_operator_vs_golden_and_oracle(nb, golden, name):
         assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
 
 
+def _ops_ext_from_golden(g, D=32):
+    from nhmc_b200 import operators as P
+    tabs = [T(g["dgauss_tab_" + k]) for k in ("U_small", "V_small", "singulars", "perm")]
+    fac = [T(g["color_tab_" + k]) for k in ("U_small", "singulars_small", "V_small")]
+    return {
+        "dgauss": (P.Deblurring(None, 3, D, "cuda", tables=tabs), oops.Deblurring(3, D, *tabs)),
+        "color": (P.Colorization(D, "cuda", factors=fac), oops.Colorization(D, *fac)),
+        "deno": (P.Denoising(3, D, "cuda"), oops.Denoising()),
+        "box": (P.Inpainting(3, D, T(g["box_missing"]), "cuda"), oops.Inpainting.from_missing_indices(3, D, g["box_missing"])),
+    }
+
+
+@pytest.mark.parametrize("name", ["dgauss", "color", "deno", "box"])
+def test_next_row_operator_vs_golden_and_oracle(nb, golden, name):
+    """SURVEY.md 8f N4 operators through the C ABI against the reference's recorded outputs and the oracle."""
+    g = golden("operators_ext.npz")
+    op, oop = _ops_ext_from_golden(g)[name]
+    x, y = T(g[name + "_x"]), T(g[name + "_y"])
+    B = x.shape[0]
+    exact = name in ("deno", "box")
+    tol = dict(atol=0, rtol=0) if exact else dict(atol=3e-5, rtol=2e-5)
+    Hx = op.H(dev(x.clamp(-1, 1))).cpu()
+    np.testing.assert_allclose(Hx.numpy(), g[name + "_Hx"].reshape(Hx.shape), **tol)
+    loss, grad, xc = op.loss_grad(dev(x), dev(y))
+    torch.cuda.synchronize()
+    assert torch.equal(xc.cpu(), x.clamp(-1, 1))
+    np.testing.assert_allclose(loss.sum().item(), float(g[name + "_loss"]), rtol=2e-5)
+    _, oloss = oop.residual(x, y)
+    np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=1e-12 if exact else 2e-5)
+    scale = max(1.0, float(np.abs(g[name + "_grad"]).max()))
+    np.testing.assert_allclose(grad.cpu().numpy(), g[name + "_grad"], atol=0 if exact else 3e-5 * scale, rtol=0 if exact else 2e-5)
+    pinv = op.H_pinv(dev(y)).cpu()
+    np.testing.assert_allclose(pinv.reshape(g[name + "_pinv"].shape).numpy(), g[name + "_pinv"],
+                               atol=5e-4 if name == "dgauss" else (0 if exact else 2e-6), rtol=1e-4 if name == "dgauss" else 0)
+    r = torch.randn(op.meas_shape(B), generator=torch.Generator().manual_seed(1))
+    Ht = op.Ht(dev(r)).cpu()
+    np.testing.assert_allclose(Ht.numpy(), oop.Ht(r).reshape(Ht.shape).numpy(), atol=3e-5, rtol=2e-5)
+    lhs = float((op.H(dev(x)).cpu().double() * r.double()).sum()); rhs = float((x.reshape(B, -1).double() * Ht.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
+
+
+def test_next_row_operators_full_size_and_from_reference(nb):
+    """FFHQ-256 shapes of the N4 operators (loss / gradient vs the oracle) and construction from duck-typed
+    reference objects (`from_reference` reads the attributes the reference's classes expose)."""
+    import types
+    from nhmc_b200 import operators as P
+    D, B = 256, 2
+    g = torch.Generator().manual_seed(19)
+    x = torch.randn(B, 3, D, D, generator=g) * 0.8
+    x_true = torch.rand(B, 3, D, D, generator=g) * 2 - 1
+    k5 = P.gaussian_taps(10.0, half=2)
+    dg = P.Deblurring(k5, 3, D, "cuda")
+    ref_like = types.SimpleNamespace(U_small=dg.U_small.cpu(), V_small=dg.V_small.cpu(), _singulars=dg._singulars.cpu(), _perm=dg._perm.cpu(),
+                                     singulars_small=torch.zeros(D), channels=3, img_dim=D)
+    dg2 = P.from_reference(ref_like, 3, D, "cuda")
+    assert isinstance(dg2, P.Deblurring) and torch.equal(dg2.gain, dg.gain)
+    col = P.Colorization(D, "cuda")
+    col2 = P.from_reference(types.SimpleNamespace(U_small=col.U_small.cpu(), singulars_small=col.singulars_small.cpu(), V_small=col.V_small.cpu(),
+                                                  Vt_small=col.V_small.cpu().t(), img_dim=D, channels=3), 3, D, "cuda")
+    assert isinstance(col2, P.Colorization) and list(col2.desc.coef) == list(col.desc.coef)
+    import random
+    random.seed(5678)
+    left, up = random.randint(16, 112), random.randint(16, 112)
+    random.seed(5678)
+    box = P.Inpainting.box(3, D, "cuda")                                   # draws left, up like main_sampling.py:292-293
+    assert box.desc.n_kept == D * D - 128 * 128
+    cases = {
+        "dgauss": (dg, oops.Deblurring(3, D, dg.U_small.cpu(), dg.V_small.cpu(), dg._singulars.cpu(), dg._perm.cpu())),
+        "color": (col, oops.Colorization(D, col.U_small.cpu(), col.singulars_small.cpu(), col.V_small.cpu())),
+        "deno": (P.Denoising(3, D, "cuda"), oops.Denoising()),
+        "box": (box, oops.Inpainting.from_missing_indices(3, D, oops.box_missing_indices(3, D, left, up).numpy())),
+    }
+    for name, (op, oop) in cases.items():
+        y = oop.H(x_true); y = y + 0.1 * torch.randn(y.shape, generator=g)
+        Hx = op.H(dev(x_true)).cpu()
+        np.testing.assert_allclose(Hx.numpy(), oop.H(x_true).reshape(Hx.shape).numpy(), atol=5e-5, rtol=2e-5, err_msg=name)
+        loss, grad, xc = op.loss_grad(dev(x), dev(y))
+        _, oloss = oop.residual(x, y)
+        np.testing.assert_allclose(loss.cpu().numpy(), oloss.numpy(), rtol=2e-5, err_msg=name)
+        ograd = oop.grad(x, y)
+        np.testing.assert_allclose(grad.cpu().numpy(), ograd.numpy(), atol=5e-5 * max(1.0, float(ograd.abs().max())), rtol=2e-5, err_msg=name)
+        assert float(grad.cpu()[x.abs() > 1].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("kind", ["inp", "sr4", "sr16", "hdr", "deblur", "phase"])
 def test_operator_full_size(nb, kind):
     """FFHQ-256 shapes (BASELINE configs 1-3), B = 2 chains: loss/gradient against the oracle + properties."""

@@ -75,6 +75,43 @@ def test_operators_match_reference(golden):
                                    atol=5e-4 if name == "deblur" else 2e-5, rtol=1e-4, err_msg=name)
 
 
+def _make_ops_ext(g):
+    D = 32
+    return {
+        "dgauss": oops.Deblurring(3, D, T(g["dgauss_tab_U_small"]), T(g["dgauss_tab_V_small"]), T(g["dgauss_tab_singulars"]),
+                                  T(g["dgauss_tab_perm"])),
+        "color": oops.Colorization(D, T(g["color_tab_U_small"]), T(g["color_tab_singulars_small"]), T(g["color_tab_V_small"])),
+        "deno": oops.Denoising(),
+        "box": oops.Inpainting.from_missing_indices(3, D, g["box_missing"]),
+    }
+
+
+def test_next_row_operators_match_reference(golden):
+    """deblur_gauss, color, deno, box inpainting against the reference's own H / autograd / H_pinv."""
+    g = golden("operators_ext.npz")
+    for name, op in _make_ops_ext(g).items():
+        x, y = T(g[name + "_x"]), T(g[name + "_y"])
+        Hx = op.H(x.clamp(-1, 1))
+        np.testing.assert_allclose(Hx.numpy(), g[name + "_Hx"], atol=2e-5, rtol=1e-5, err_msg=name)
+        r, loss = op.residual(x, y)
+        np.testing.assert_allclose(loss.sum().item(), float(g[name + "_loss"]), rtol=2e-5, err_msg=name)
+        grad = op.grad(x, y)
+        scale = np.abs(g[name + "_grad"]).max()
+        np.testing.assert_allclose(grad.numpy(), g[name + "_grad"], atol=2e-5 * max(1.0, scale), err_msg=name)
+        pinv = op.H_pinv(y)
+        np.testing.assert_allclose(pinv.reshape(g[name + "_pinv"].shape).numpy(), g[name + "_pinv"],
+                                   atol=5e-4 if name == "dgauss" else 2e-5, rtol=1e-4, err_msg=name)
+    # table / index construction restated
+    U, V, s, perm = oops.deblur1d_tables(T(g["dgauss_kernel"]), 32)
+    assert np.array_equal(s.numpy(), g["dgauss_tab_singulars"]) and np.array_equal(perm.numpy(), g["dgauss_tab_perm"])
+    assert np.array_equal(U.numpy(), g["dgauss_tab_U_small"])
+    assert np.array_equal(oops.gaussian_taps(10.0, half=2).numpy(), g["dgauss_kernel"])          # main_sampling.py:307-312
+    left, up, size = [int(v) for v in g["box_geom"]]
+    assert np.array_equal(oops.box_missing_indices(3, 32, left, up, size).numpy(), g["box_missing"])
+    Uc, Sc, Vc = torch.svd(torch.Tensor([[0.3333, 0.3334, 0.3333]]), some=False)
+    np.testing.assert_allclose(oops.Colorization(32).H(T(g["color_x"]).clamp(-1, 1)).numpy(), g["color_Hx"], atol=1e-6)
+
+
 def test_deblur_tables_rebuild(golden):
     """Our restatement of the band matrix + SVD table construction reproduces the reference's tables."""
     g = golden("operators.npz")
