@@ -161,6 +161,8 @@ typedef struct nhmc_op {
                               /*        [3..5] adjoint weights, [6..8] pseudo-inverse weights */
 } nhmc_op;
 
+size_t nhmc_sizeof_op(void);
+
 /* measurement elements per chain (M) for this operator */
 int64_t nhmc_op_meas_size(const nhmc_op* op);
 size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains);

@@ -45,6 +45,7 @@ _SIGS = {
     "nhmc_version": (C.c_int, []),
     "nhmc_last_error": (C.c_char_p, []),
     "nhmc_sizeof_chain": (C.c_size_t, []),
+    "nhmc_sizeof_op": (C.c_size_t, []),
     "nhmc_begin_iteration": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nhmc_leapfrog_workspace_bytes": (C.c_size_t, [C.c_int]),
     "nhmc_leapfrog": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -25,4 +25,5 @@ extern "C" {
 int nhmc_version(void) { return 100; }
 const char* nhmc_last_error(void) { return nhmc::g_err; }
 size_t nhmc_sizeof_chain(void) { return sizeof(nhmc_chain); }
+size_t nhmc_sizeof_op(void) { return sizeof(nhmc_op); }
 }
