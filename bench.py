@@ -397,7 +397,18 @@ def _cpu_step_fn(deg):
     return step
 
 
+def _use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 for its workers; the CPU arm is to use every host core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if n > torch.get_num_threads():
+        torch.set_num_threads(n)
+
+
 def cpu_baseline(deg, steps_timed=1, warm=1):
+    _use_all_host_threads()
     step = _cpu_step_fn(deg)
     cores = torch.get_num_threads()
     for _ in range(warm):
@@ -418,6 +429,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     K, W = args.steps, args.warmup
+    _use_all_host_threads()
     step = _cpu_step_fn(args.deg)
     cores = torch.get_num_threads()
     budget_s = 240.0
