@@ -219,8 +219,10 @@ int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const float* g_a,
  * f32/bf16/f16; gamma/beta fp32 [C]; scale/shift fp32 rows of C values, sample b at
  * scale + b*film_stride (FiLM only; film_stride 0 means C: this lets both point into one
  * [B, 2C] embedding projection, unet_ffhq.py:319-321, without a split copy); in_bias fp32 [C] or
- * NULL: the tensor that is normalised is x + in_bias[c] (the bias of the convolution that
- * produced x, folded in here instead of a separate broadcast-add pass).
+ * NULL: the tensor that is normalised is x + in_bias[b*in_bias_stride + c] -- the bias of the
+ * convolution that produced x (in_bias_stride 0: one vector for all samples) and, for ResBlocks
+ * without scale-shift norm (ldm openaimodel.py:267-276), the per-sample embedding projection
+ * (in_bias_stride >= C), folded in here instead of a separate broadcast-add pass.
  * stats_out: fp32 [B, G, 2] (mean, rstd) saved for the backward.
  * ---------------------------------------------------------------------------------------- */
 #define NHMC_GN_PLAIN 0
@@ -230,7 +232,7 @@ int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const float* g_a,
 #define NHMC_LAYOUT_NHWC 1
 int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
                 const float* beta, const float* scale, const float* shift, int64_t film_stride,
-                const float* in_bias, float* stats_out,
+                const float* in_bias, int64_t in_bias_stride, float* stats_out,
                 int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream);
 /* dx (and optionally dscale/dshift [B,C] fp32) given dy; weights are frozen on this path, so
  * no dgamma/dbeta.  dx_add (nullable, same dtype/layout as dx, channels-last only): a tensor added to
@@ -244,7 +246,8 @@ int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const f
  * the algorithmic bytes.  Otherwise a statistics kernel + an apply kernel (two reads). */
 int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                 const float* gamma, const float* beta, const float* scale, const float* shift,
-                int64_t film_stride, const float* in_bias, const float* stats, float* dscale, float* dshift,
+                int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats,
+                float* dscale, float* dshift,
                 const void* dx_add, int batch, int channels, int64_t hw, int groups,
                 nhmc_stream_t stream);
 /* 0 unless a per-sample barrier of the shared-memory-resident GroupNorm path ever timed out on the
@@ -297,6 +300,17 @@ int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows,
  * skip 1x1 convolution applied block-wise to a virtual concatenation.  channels-last rows, out may alias a. */
 int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c3, const float* bias, void* out,
                   int64_t rows, int channels, nhmc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Latent path, first stage: nearest-codebook lookup of the VQ-f4 autoencoder
+ * (VQModelInterface.decode -> taming VectorQuantizer2.forward, ldm/models/autoencoder.py:274-282):
+ * zq[b,:,p] = z + (e - z) with e = codebook[argmin_k |z[b,:,p] - e_k|^2] (the reference's straight-through
+ * form, equal to e up to fp32 rounding), first minimum wins.  z, zq: fp32 [B, dim, pixels]
+ * (NCHW); codebook fp32 [n_codes, dim]; idx_out int32 [B, pixels] or NULL.  The gradient is
+ * straight-through (identity), so no backward entry point exists.
+ * ---------------------------------------------------------------------------------------- */
+int nhmc_vq_nearest(const float* z, const float* codebook, float* zq, int32_t* idx_out, int batch,
+                    int dim, int64_t pixels, int n_codes, nhmc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -99,7 +99,9 @@ struct GnArgs {
   // writes dx / reads add per block (out, out1 / add, add1; add and add1 are independently nullable)
   const void* x1; void* out1; const void* add1; int c_split;
   const float* gamma; const float* beta; const float* scale; const float* shift;  // scale/shift: [B,C] fp32 or null
-  const float* in_bias;  // [C] fp32 or null: the normalised tensor is x + in_bias[c] (conv bias folded in)
+  const float* in_bias;  // fp32 or null: the normalised tensor is x + in_bias[b*in_bias_stride + c] (conv bias, and for
+                         // the additive-embedding ResBlock variant the per-sample embedding, folded in)
+  int64_t in_bias_stride;  // 0: one [C] vector shared by all samples
   float* stats;      // [B][G][2]: fwd (mean, rstd)
   float* bstats;     // [B][G][2]: bwd (sum du / n, sum du*u / n)
   double* partials;  // [B][kGnMaxBlocks][G][2]
@@ -252,6 +254,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   extern __shared__ __align__(128) unsigned char dyn[];
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
+  const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
@@ -263,7 +266,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
@@ -297,13 +300,13 @@ gn_nhwc_stats_kernel(GnArgs a) {
           }
         }
       });
-  if (PHASE == 0 && a.in_bias) {
+  if (PHASE == 0 && in_bias) {
     // statistics of x + bias from the raw sums: this thread saw `cnt` pixels of each of its channels
     const int64_t span = r_end - r_begin - prow;
     const int64_t cnt = span > 0 ? (span + rows - 1) / rows : 0;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const float bia = a.in_bias[c0 + i];
+      const float bia = in_bias[c0 + i];
       s1[i] = s1[i] + 2.0f * bia * s0[i] + (float)cnt * bia * bia;
       s0[i] = s0[i] + (float)cnt * bia;
     }
@@ -312,7 +315,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
@@ -344,6 +347,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
+  const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, prow = threadIdx.x / cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
@@ -369,7 +373,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     const int c = c0 + i, g = c / Cg;
-    const float mean = g_mean[g] - (a.in_bias ? a.in_bias[c] : 0.0f), rstd = g_rstd[g];
+    const float mean = g_mean[g] - (a.in_bias ? in_bias[c] : 0.0f), rstd = g_rstd[g];
     const float gam = a.gamma[c], bet = a.beta[c];
     const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
     const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
@@ -555,6 +559,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
   }
   __syncthreads();
   const int b = (int)(s_lid / (unsigned int)r.nb), blk = (int)(s_lid % (unsigned int)r.nb);
+  const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int cvec = a.C / V;
   const int cv = threadIdx.x % cvec, rows = blockDim.x / cvec;
   const int c0 = cv * V;
@@ -597,11 +602,11 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
         for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
       }
     }
-    if (a.in_bias) {
+    if (in_bias) {
       const float cnt = my_off < total ? (float)((total - my_off + pass_bytes - 1) / pass_bytes) : 0.f;
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const float bia = a.in_bias[c0 + i];
+        const float bia = in_bias[c0 + i];
         s1[i] = s1[i] + 2.0f * bia * s0[i] + cnt * bia * bia;
         s0[i] = s0[i] + cnt * bia;
       }
@@ -623,7 +628,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = g_c0[g] - (a.in_bias ? a.in_bias[c] : 0.0f), rstd = g_c1[g];
+      const float mean = g_c0[g] - (a.in_bias ? in_bias[c] : 0.0f), rstd = g_c1[g];
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
@@ -648,7 +653,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float gam = a.gamma[c], bet = a.beta[c];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
@@ -675,7 +680,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
       const int c = c0 + i, g = c / Cg;
-      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? a.in_bias[c] : 0.0f);
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (a.in_bias ? in_bias[c] : 0.0f);
       const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
       const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
       const float cgm = a.gamma[c] * sc;             // du = d * gamma * (1+scale); u = (x-mean)*rstd
@@ -734,6 +739,7 @@ template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256)
 gn_nchw_kernel(GnArgs a) {
   const int g = blockIdx.x, b = blockIdx.y;
+  const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int Cg = a.C / a.G;
   const int64_t n = (int64_t)Cg * a.HW;
   const int64_t base = ((int64_t)b * a.C + (int64_t)g * Cg) * a.HW;
@@ -746,7 +752,7 @@ gn_nchw_kernel(GnArgs a) {
   if (PHASE == 0) {
     double s[2] = {0.0, 0.0};
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
+      const float v = Elem<T>::to_f(xb[i]) + (a.in_bias ? in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       s[0] += v; s[1] += (double)v * v;
     }
     block_sum<double, 2>(s, red);
@@ -771,14 +777,14 @@ gn_nchw_kernel(GnArgs a) {
   if (PHASE == 0) {
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      const float bia = a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f;
+      const float bia = a.in_bias ? in_bias[g * Cg + (int)(i / a.HW)] : 0.0f;
       ob[i] = Elem<T>::from_f(gn_act<MODE, T>(fmaf(ca, Elem<T>::to_f(xb[i]) + bia, cb)));
     }
   } else {
     double s[2] = {0.0, 0.0};
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
+      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       s[0] += du; s[1] += (double)du * (double)((xv - mean) * rstd);
     }
@@ -788,7 +794,7 @@ gn_nchw_kernel(GnArgs a) {
     const float m1 = bc[0], m2 = bc[1];
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
       float ca, cb, cgm; coef(g * Cg + (int)(i / a.HW), ca, cb, cgm);
-      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? a.in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
+      const float xv = Elem<T>::to_f(xb[i]) + (a.in_bias ? in_bias[g * Cg + (int)(i / a.HW)] : 0.0f);
       const float du = Elem<T>::to_f(dyb[i]) * gn_dact<MODE, T>(fmaf(ca, xv, cb)) * cgm;
       const float u = (xv - mean) * rstd;
       ob[i] = Elem<T>::from_f(rstd * (du - m1 - u * m2));
@@ -994,13 +1000,13 @@ using namespace nhmc;
 
 extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
                            const float* beta, const float* scale, const float* shift, int64_t film_stride, const float* in_bias,
-                           float* stats_out, int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
+                           int64_t in_bias_stride, float* stats_out, int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(stats_out, "stats_out required");
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
-  a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.stats = stats_out;
+  a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.in_bias_stride = in_bias_stride; a.stats = stats_out;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
   a.film_stride = film_stride > 0 ? film_stride : channels;
   NHMC_CHECK_ARG(a.film_stride >= channels, "film_stride must be >= channels");
@@ -1009,7 +1015,8 @@ extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void*
 
 extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                            const float* gamma, const float* beta, const float* scale, const float* shift,
-                           int64_t film_stride, const float* in_bias, const float* stats, float* dscale, float* dshift, const void* dx_add, int batch,
+                           int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats, float* dscale,
+                           float* dshift, const void* dx_add, int batch,
                            int channels, int64_t hw, int groups, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(dy && stats, "dy and stats required");
@@ -1019,7 +1026,7 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
-  a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias;
+  a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.in_bias_stride = in_bias_stride;
   a.stats = const_cast<float*>(stats);
   a.bstats = s.bstats;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;

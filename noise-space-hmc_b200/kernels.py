@@ -169,6 +169,15 @@ def commit_grad(chains, g_state, g_a, g_b, loss_state, loss_prop):
                                      _stream()), "nhmc_commit_grad")
 
 
+def _in_bias_stride(in_bias, channels):
+    """in_bias: fp32 [C] (shared) or [B, C] (per sample, e.g. conv bias + embedding projection)."""
+    if in_bias is None or in_bias.dim() == 1:
+        return 0
+    if in_bias.dtype != torch.float32 or in_bias.dim() != 2 or in_bias.shape[1] != channels or in_bias.stride(1) != 1:
+        raise _lib.NhmcError("in_bias must be fp32 [C] or [B, C] with unit stride along C")
+    return in_bias.stride(0)
+
+
 def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_last, in_bias=None):
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]
@@ -176,7 +185,7 @@ def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_l
     with _timed("gn_fwd", 1, 2 * x.numel() * x.element_size()):
         check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
                                 _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc), _p(in_bias),
-                                _p(stats), B, Cc, hw, groups, float(eps), _stream()), "nhmc_gn_fwd")
+                                _in_bias_stride(in_bias, Cc), _p(stats), B, Cc, hw, groups, float(eps), _stream()), "nhmc_gn_fwd")
 
 
 def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None, dx_add=None):
@@ -186,7 +195,8 @@ def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_l
     with _timed("gn_bwd", 1, (3 + (1 if dx_add is not None else 0)) * x.numel() * x.element_size()):
         check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
                                 _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc),
-                                _p(in_bias), _p(stats), 0, 0, _p(dx_add), B, Cc, hw, groups, _stream()), "nhmc_gn_bwd")
+                                _p(in_bias), _in_bias_stride(in_bias, Cc), _p(stats), 0, 0, _p(dx_add), B, Cc, hw, groups,
+                                _stream()), "nhmc_gn_bwd")
 
 
 def gn_check():
@@ -258,3 +268,12 @@ def gn_cat_bwd(mode, x0, x1, dy, dx0, dx1, gamma, beta, scale, shift, stats, gro
         check(lib().nhmc_gn_cat_bwd(mode, _DT[x0.dtype], _p(x0), _p(x1), c0, c1, _p(dy), _p(dx0), _p(dx1), _p(gamma), _p(beta),
                                     _p(scale), _p(shift), _film_stride(scale, shift, c0 + c1), _p(stats), _p(add0), _p(add1),
                                     B, hw, groups, _stream()), "nhmc_gn_cat_bwd")
+
+
+def vq_nearest(z, codebook, zq, idx=None):
+    """z, zq: fp32 [B, D, H, W] contiguous; codebook fp32 [K, D]; idx int32 [B, H*W] or None."""
+    _req(z, torch.float32, "z"); _req(zq, torch.float32, "zq"); _req(codebook, torch.float32, "codebook")
+    B, D = z.shape[0], z.shape[1]
+    P = z[0, 0].numel()
+    with _timed("vq_nearest", 1, 2 * z.numel() * 4):
+        check(lib().nhmc_vq_nearest(_p(z), _p(codebook), _p(zq), _p(idx), B, D, P, codebook.shape[0], _stream()), "nhmc_vq_nearest")

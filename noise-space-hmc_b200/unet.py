@@ -40,13 +40,13 @@ class _GroupNormAct(torch.autograd.Function):
     """y = act(GN32(x) [*(1+scale)+shift]); saves x and the per-group (mean, rstd) only."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias):
+    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias, eps=GN_EPS):
         cl = _is_channels_last(x)
         if not cl and not x.is_contiguous():
             x = x.contiguous()
         y = torch.empty_like(x)
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
-        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, GN_EPS, cl, in_bias)
+        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, eps, cl, in_bias)
         ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
         ctx.mode, ctx.cl = mode, cl
         return y
@@ -57,7 +57,7 @@ class _GroupNormAct(torch.autograd.Function):
         dy = dy.contiguous(memory_format=torch.channels_last) if ctx.cl else dy.contiguous()
         dx = torch.empty_like(x)
         kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, ctx.cl, in_bias)
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 class _CatGroupNormAct(torch.autograd.Function):
@@ -118,11 +118,11 @@ class _GroupNormActSkip(torch.autograd.Function):
     kernel (dx_add) instead of leaving autograd a separate read-read-write accumulation pass."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias):
+    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias, eps=GN_EPS):
         x = _cl(x)
         y = torch.empty_like(x)
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
-        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, GN_EPS, True, in_bias)
+        kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, eps, True, in_bias)
         ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
         ctx.mode = mode
         return y, x.view_as(x)
@@ -131,13 +131,13 @@ class _GroupNormActSkip(torch.autograd.Function):
     def backward(ctx, dy, dskip):
         x, gamma, beta, scale, shift, stats, in_bias = ctx.saved_tensors
         if dy is None:
-            return dskip, None, None, None, None, None, None
+            return dskip, None, None, None, None, None, None, None
         dy = _cl(dy)
         if dskip is not None:
             dskip = _cl(dskip)
         dx = torch.empty_like(x)
         kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias, dx_add=dskip)
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 class _AvgPool2(torch.autograd.Function):
@@ -219,10 +219,11 @@ class _BiasAdd(torch.autograd.Function):
 
 
 def group_norm_act(x, norm, mode, scale=None, shift=None, in_bias=None):
-    """act(GN32(x + in_bias[c]) ...): in_bias folds the bias of the convolution that produced x."""
+    """act(GN32(x + in_bias) ...): in_bias ([C], or [B, C] per sample) folds the bias of the convolution that produced
+    x and, for ResBlocks without scale-shift norm, the embedding projection."""
     if not x.is_cuda:
         raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
-    return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode, in_bias)
+    return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode, in_bias, getattr(norm, "eps", GN_EPS))
 
 
 def group_norm_act_skip(x, norm, mode):
@@ -231,7 +232,7 @@ def group_norm_act_skip(x, norm, mode):
         raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
     if x.dim() != 4 or x.shape[1] % (4 if x.dtype == torch.float32 else 8):
         return group_norm_act(x, norm, mode), x
-    return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None)
+    return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None, getattr(norm, "eps", GN_EPS))
 
 
 def _conv_nobias(conv, x):
@@ -244,10 +245,11 @@ def _conv_nobias(conv, x):
 class _Norm(nn.Module):
     """Parameter holder for GroupNorm32 (nn.py:17-19): fp32 affine, never cast with the rest of the net."""
 
-    def __init__(self, channels):
+    def __init__(self, channels, eps=GN_EPS):
         super().__init__()
         self.weight = nn.Parameter(torch.ones(channels))
         self.bias = nn.Parameter(torch.zeros(channels))
+        self.eps = eps
 
     def _apply(self, fn, recurse=True):
         super()._apply(fn, recurse)
@@ -300,8 +302,8 @@ class ResBlock(nn.Module):
         if self.film:
             scale, shift = e[:, : self.out_channels], e[:, self.out_channels:]       # strided views, no split copies
             h = group_norm_act(h, self.out_layers[0], _lib.GN_FILM_SILU, scale, shift, in_bias=b1)
-        else:
-            h = group_norm_act(h + (e + b1).to(h.dtype)[:, :, None, None], self.out_layers[0], _lib.GN_SILU)
+        else:   # h + emb_out (openaimodel.py:274-276): folded into the norm as a per-sample bias, no broadcast-add pass
+            h = group_norm_act(h, self.out_layers[0], _lib.GN_SILU, in_bias=(e + b1).contiguous())
         h = _conv_nobias(self.out_layers[3], h)
         if xs is not None:                       # skip 1x1 conv of cat([xa, xb]) = conv(xa, W[:, :c0]) + conv(xb, W[:, c0:])
             w0, w1 = self._split_skip_weights(xs[0].shape[1])
@@ -330,6 +332,28 @@ class ResBlock(nn.Module):
             cache = (b.detach().float().contiguous(), b_out.contiguous())
             self._bias_cache = cache
         return cache
+
+
+class Downsample(nn.Module):
+    """3x3 stride-2 convolution (ldm/modules/diffusionmodules/openaimodel.py:134-160, use_conv=True); key `op`."""
+
+    def __init__(self, channels, out_channels=None):
+        super().__init__()
+        self.op = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.op(x)
+
+
+class Upsample(nn.Module):
+    """nearest x2 (our channels-last kernel) + 3x3 convolution (openaimodel.py:91-118, use_conv=True); key `conv`."""
+
+    def __init__(self, channels, out_channels=None):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, out_channels or channels, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(_Upsample2.apply(x))
 
 
 class AttentionBlock(nn.Module):
@@ -375,8 +399,6 @@ class UNetModel(nn.Module):
                  channel_mult=(1, 2, 4, 8), num_heads=1, num_head_channels=-1, use_scale_shift_norm=False,
                  resblock_updown=False, dtype=torch.bfloat16):
         super().__init__()
-        if not resblock_updown:
-            raise NotImplementedError("only the resblock_updown=True variant (ffhq_10m) is on the accelerated path")
         self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
         self.out_channels, self.compute_dtype = out_channels, dtype
         self.virtual_cat_min_pixels = 64 * 64      # skip concatenations at >= this many pixels stay virtual
@@ -396,7 +418,7 @@ class UNetModel(nn.Module):
                 self.input_blocks.append(_Seq(*layers))
                 chans.append(ch)
             if level != len(channel_mult) - 1:
-                self.input_blocks.append(_Seq(ResBlock(ch, E, ch, down=True, **rb)))
+                self.input_blocks.append(_Seq(ResBlock(ch, E, ch, down=True, **rb) if resblock_updown else Downsample(ch)))
                 chans.append(ch)
                 ds *= 2
         self.middle_block = _Seq(ResBlock(ch, E, **rb), AttentionBlock(ch, **at), ResBlock(ch, E, **rb))
@@ -408,7 +430,7 @@ class UNetModel(nn.Module):
                 if ds in attention_resolutions:
                     layers.append(AttentionBlock(ch, **at))
                 if level and i == num_res_blocks:
-                    layers.append(ResBlock(ch, E, ch, up=True, **rb))
+                    layers.append(ResBlock(ch, E, ch, up=True, **rb) if resblock_updown else Upsample(ch))
                     ds //= 2
                 self.output_blocks.append(_Seq(*layers))
         self.out = nn.Sequential(_Norm(ch), nn.Identity(), nn.Conv2d(int(channel_mult[0] * model_channels), out_channels, 3, padding=1))

@@ -362,7 +362,74 @@ def gold_hmc_latent_trace():
          samples=out.detach(), seed=np.array(778))
 
 
+# ---------------------------------------------------------------------------- latent model family
+def gold_latent_models():
+    """The reference's own latent U-Net (ldm openaimodel.UNetModel) and VQ decoder (ldm model.Decoder) at a small
+    configuration with seeded weights: forward outputs, and for the first stage the decode output and its gradient
+    with respect to z through post_quant_conv + decoder (straight-through over the nearest-code lookup).
+    taming's VectorQuantizer2 is not vendored upstream: its lookup is restated inline (argmin of
+    sum z^2 + sum e^2 - 2 z.e, first minimum) -- that boundary is un-pinned."""
+    import types as _t
+    class _Any(_t.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            return lambda *a, **kw: 0.0
+    for n in ("omegaconf", "pytorch_lightning", "pytorch_lightning.utilities", "pytorch_lightning.utilities.distributed",
+              "taming", "taming.modules", "taming.modules.vqvae", "taming.modules.vqvae.quantize"):
+        if n not in sys.modules:
+            try:
+                __import__(n)
+            except Exception:
+                sys.modules[n] = _Any(n)
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel as RefUNet
+    from ldm.modules.diffusionmodules.model import Decoder as RefDecoder
+    from oracle.latent_fill import SMALL_UNET, SMALL_FIRST_STAGE, seeded_fill
+    rec = {}
+    g = torch.Generator().manual_seed(51)
+    # --- latent U-Net
+    uc = dict(SMALL_UNET); uc["attention_resolutions"] = list(uc["attention_resolutions"]); uc["channel_mult"] = list(uc["channel_mult"])
+    net = RefUNet(**uc).eval()
+    sd = seeded_fill({k: v.shape for k, v in net.state_dict().items()}, seed=4321)
+    net.load_state_dict(sd)
+    x = torch.randn(2, 3, 16, 16, generator=g)
+    t = torch.tensor([750.0, 250.0])
+    with torch.no_grad():
+        rec["unet_out"] = net(x, t)
+    rec["unet_x"], rec["unet_t"] = x, t
+    rec["unet_keys"] = np.array(list(sd.keys()))
+    # --- first stage decode
+    fs = SMALL_FIRST_STAGE
+    dd = dict(fs["ddconfig"]); dd["ch_mult"] = tuple(dd["ch_mult"]); dd["attn_resolutions"] = list(dd["attn_resolutions"])
+    dec = RefDecoder(**dd).eval()
+    pq = torch.nn.Conv2d(fs["embed_dim"], dd["z_channels"], 1)
+    shapes = {"quantize.embedding.weight": (fs["n_embed"], fs["embed_dim"]), "post_quant_conv.weight": pq.weight.shape,
+              "post_quant_conv.bias": pq.bias.shape}
+    shapes.update({"decoder." + k: v.shape for k, v in dec.state_dict().items()})
+    sd2 = seeded_fill(shapes, seed=8765)
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd2.items() if k.startswith("decoder.")})
+    with torch.no_grad():
+        pq.weight.copy_(sd2["post_quant_conv.weight"]); pq.bias.copy_(sd2["post_quant_conv.bias"])
+    E = sd2["quantize.embedding.weight"]
+    z = (torch.randn(2, 3, 8, 8, generator=g) * 0.8).requires_grad_(True)
+    zf = z.permute(0, 2, 3, 1).reshape(-1, 3)
+    d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(E ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, E.t())
+    idx = torch.argmin(d, dim=1)
+    zq = E[idx].view(2, 8, 8, 3)
+    zq = z.permute(0, 2, 3, 1) + (zq - z.permute(0, 2, 3, 1)).detach()
+    zq = zq.permute(0, 3, 1, 2).contiguous()
+    out = dec(pq(zq))
+    w = torch.randn(out.shape, generator=g)
+    (gz,) = torch.autograd.grad(out, z, w)
+    rec.update(dec_z=z.detach(), dec_idx=idx.view(2, 64), dec_zq=zq.detach(), dec_out=out.detach(), dec_w=w, dec_grad_z=gz,
+               dec_keys=np.array(list(sd2.keys())))
+    # second-nearest margin: how close the lookup is to a tie (for the un-pinned boundary's tolerance)
+    d2 = d.detach().clone(); d2[torch.arange(d2.shape[0]), idx] = float("inf")
+    rec["dec_margin"] = (d2.min(1).values - d.detach().min(1).values).min()
+    save("latent_models.npz", **rec)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "operators_ext", "ddim", "unet", "hmc_trace", "hmc_latent_trace"]
+    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "operators_ext", "ddim", "unet", "hmc_trace", "hmc_latent_trace", "latent_models"]
     for w in which:
         globals()["gold_" + w]()
