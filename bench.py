@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | inpaint_box | hdr | deblur_aniso | deblur_gauss | phase_retrieval | color")
     ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
+    ap.add_argument("--workload", default="pixel", choices=["pixel", "latent"], help="pixel: --algo hmc (BASELINE config[1], the metric's configuration); latent: --algo hmc_latent on the ffhq_latent architecture (BASELINE config[4])")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -147,22 +148,39 @@ def run_ours(args, rank, world, local_rank):
     B, K, W = args.chains, args.steps, max(args.warmup, 3)
 
     torch.manual_seed(1234)
-    model = unet.create_model(**FFHQ, dtype=dtype)
-    unet.randomize_zero_tensors(model, seed=1234)
-    model.prepare(dev)
+    latent_wl = args.workload == "latent"
     op = make_operator(args.deg, dev)
     gen = torch.Generator().manual_seed(5678 + rank)
     x_orig = torch.rand(B, 3, 256, 256, generator=gen) * 2 - 1
     sigma_0 = 0.1                                                                 # --sigma_0 0.05, doubled
     y = op.H(x_orig.to(dev))
     y = y + sigma_0 * torch.randn(y.shape, generator=gen).to(dev)
-    x0 = torch.randn(B, 3, 256, 256, generator=gen)
-    betas = torch.from_numpy(schedule.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
-    steps = schedule.ddim_steps(schedule.alpha_table(betas), SEQ, SEQ_NEXT)
-    ev = sampler.GradEvaluator(model, steps, op, y, x0.to(dev))
-    smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
-    kernels.begin_iteration(smp.chains, _lib.SCHED_PIXEL)                          # sigma_y for epoch 0
-    smp.p.copy_(torch.randn(B, 3, 256, 256, generator=gen).to(dev))
+    if not latent_wl:
+        model = unet.create_model(**FFHQ, dtype=dtype)
+        unet.randomize_zero_tensors(model, seed=1234)
+        model.prepare(dev)
+        state_shape = (B, 3, 256, 256)
+        x0 = torch.randn(state_shape, generator=gen)
+        betas = torch.from_numpy(schedule.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
+        steps = schedule.ddim_steps(schedule.alpha_table(betas), SEQ, SEQ_NEXT)
+        ev = sampler.GradEvaluator(model, steps, op, y, x0.to(dev))
+        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
+        sched_kind = _lib.SCHED_PIXEL
+    else:
+        from nhmc_b200 import latent
+        ldm = latent.create_latent_model(dtype=dtype)                             # ffhq_latent (config_ffhq_latent.yml)
+        unet.randomize_zero_tensors(ldm, seed=1234)
+        ldm.prepare(dev)
+        op.set_clamp(False)                                                       # main_sampling_latent.py:651
+        state_shape = (B, 3, 64, 64)
+        x0 = torch.randn(state_shape, generator=gen)
+        steps = schedule.ddim_steps(schedule.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev), SEQ, SEQ_NEXT)
+        ev = sampler.GradEvaluator(lambda z, t: ldm.apply_model(z, t, None), steps, op, y, x0.to(dev), net_grad=False,
+                                   decode=ldm.differentiable_decode_first_stage)
+        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_LATENT, sigma_y=0.5, n_slots=10)
+        sched_kind = _lib.SCHED_LATENT
+    kernels.begin_iteration(smp.chains, sched_kind)                                # sigma_y for epoch 0
+    smp.p.copy_(torch.randn(state_shape, generator=gen).to(dev))
     smp.step(_lib.LF_FIRST)
     use_graphs = not args.no_graphs
     if use_graphs:
@@ -268,7 +286,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end-to-end: the same step through the public API with HOST buffers ----
     e2e = None
     if not args.no_e2e:
-        xh = torch.empty(B, 3, 256, 256).pin_memory(); ph = torch.empty(B, 3, 256, 256).pin_memory()
+        xh = torch.empty(state_shape).pin_memory(); ph = torch.empty(state_shape).pin_memory()
         xh.copy_(smp.x_prop); ph.copy_(smp.p)
         for _ in range(2):
             smp.leapfrog_step_host(xh, ph)
@@ -316,7 +334,10 @@ def run_ours(args, rank, world, local_rank):
                             + (" (eager pass right after the graph-replayed timed region)" if use_graphs else " of the timed region")
                             + "; traffic = dram bytes per call from the ncu --set full capture in profiles/ (null if that shape was not captured)"}
     step_ms = ms / K
-    unet_tflop = B * 3 * 2 * UNET_FWD_GFLOP / 1e3                       # fwd + input-VJP ~ 2x fwd FLOPs, 3 timesteps
+    if latent_wl:   # 3 latent U-Net forwards (no VJP: eps carries no gradient) + decoder forward and VJP
+        unet_tflop = B * (3 * 202.4 + 2 * 670.8) / 1e3
+    else:
+        unet_tflop = B * 3 * 2 * UNET_FWD_GFLOP / 1e3                   # fwd + input-VJP ~ 2x fwd FLOPs, 3 timesteps
     # shares of the step: from the in-situ CUPTI durations when available (the eager event times of small kernels
     # include launch gaps), else from the per-call events
     sampler_names = ("leapfrog", "ddim_fwd", "ddim_bwd", "begin_iteration", "accept", "commit")
@@ -338,8 +359,10 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 sampler state / %s score network" % args.dtype, "data": "synthetic",
-        "config": {"workload": "FFHQ-256 %s HMC, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, "
-                               "random-init ffhq_10m U-Net (BASELINE config[1])" % (args.deg, B),
+        "config": {"workload": ("FFHQ-256 %s hmc_latent, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05 sigma_y=0.5, "
+                                "random-init ffhq_latent (VQ-f4 + latent U-Net) architecture (BASELINE config[4])" if latent_wl else
+                                "FFHQ-256 %s HMC, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, "
+                                "random-init ffhq_10m U-Net (BASELINE config[1])") % (args.deg, B),
                    "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
                    "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,

@@ -51,6 +51,7 @@ def get_parser():
     p.add_argument("--cuda_graphs", action="store_true", help="replay the leapfrog step as CUDA graphs")
     p.add_argument("--reuse_gradient", action="store_true", help="keep (loss, gradient) of the current state instead of re-evaluating it at the top of each iteration (20 instead of 21 evaluations; main_sampling.py:693-695)")
     p.add_argument("--save_progress", action="store_true", help="PNG of every accepted epoch like the reference (main_sampling.py:735)")
+    p.add_argument("--ldm_ckpt", type=str, default="", help="hmc_latent: LatentDiffusion checkpoint (model.ckpt); random init if absent")
     p.add_argument("--max_iters", type=int, default=None, help="stop after this many HMC iterations (smoke runs)")
     return p
 
@@ -111,10 +112,45 @@ def _load_images(opt, config, n, generator):
     return torch.stack(ims)
 
 
+def _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_funcs, sigma_0, x_orig, y_0, cgen, mom, uni, on_it):
+    """--algo hmc_latent (main_sampling_latent.py:354-570): chains live in the 3 x 64 x 64 latent space of the
+    `ffhq_latent` model; the collected latents are decoded with decode_first_stage (:473)."""
+    from . import latent
+    n = a1 - a0
+    dtype = torch.bfloat16 if getattr(opt, "dtype", "bf16") == "bf16" else torch.float32
+    ldm = latent.create_latent_model(model_config or None, dtype=dtype, ckpt_path=getattr(opt, "ldm_ckpt", ""))
+    from . import unet as _unet
+    _unet.randomize_zero_tensors(ldm)          # random-init runs: zero-initialised output convs would make eps == 0
+    ldm.prepare(device)
+    hz = config.data.image_size // 4
+    z = torch.stack([torch.randn(3, hz, hz, device=device, generator=g_) for g_ in cgen]) if n else torch.zeros(0, 3, hz, hz, device=device)
+    seq, seq_next = schedule.timestep_sequence(opt.num_timesteps, opt.timesteps)
+    algo = types.SimpleNamespace(model=ldm, H_funcs=H_funcs, sigma_0=sigma_0, cls_fn=None)
+    out = None
+    if n:
+        lat = sampler.hmc_latent(z, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
+                                 max_iters=opt.max_iters, on_iteration=on_it, image_size=config.data.image_size)
+        lat = [lat] if n == 1 else lat
+        out = [ldm.decode_first_stage(l_).float() if l_.numel() else torch.zeros(0, 3, config.data.image_size, config.data.image_size, device=device)
+               for l_ in lat]
+        S = min(o.shape[0] for o in out)
+        out = torch.stack([o[:S] for o in out]) if S else None
+    allc = ndist.gather_chains(out, opt.chains) if (world > 1 and out is not None) else out
+    if rank == 0 and allc is not None and allc.numel():
+        img = ((allc + 1) / 2).clamp(0, 1)
+        orig = ((x_orig[0] + 1) / 2).clamp(0, 1)
+        psnr = 10 * torch.log10(1 / ((img - orig) ** 2).mean(dim=(2, 3, 4)))
+        print("Total Average PSNR: %.3f" % float(psnr.mean()))
+        print("Number of samples: %d chains x %d" % (img.shape[0], img.shape[1]))
+        torch.save(allc.cpu(), os.path.join(opt.image_folder, "hmc_latent_samples.pt"))
+    return allc
+
+
 def sample_image(opt, config, model_config, device):
     rank, world, local_rank = ndist.init_from_env()
     H_funcs, sigma_0, deg = prepare_measurement(opt, config, device)
-    model = init_model(opt, config, model_config, device)
+    latent_mode = opt.algo == "hmc_latent"
+    model = None if latent_mode else init_model(opt, config, model_config, device)
     betas = schedule.get_beta_schedule(beta_schedule=config.diffusion.beta_schedule, beta_start=config.diffusion.beta_start,
                                        beta_end=config.diffusion.beta_end,
                                        num_diffusion_timesteps=config.diffusion.num_diffusion_timesteps)
@@ -145,6 +181,8 @@ def sample_image(opt, config, model_config, device):
             for j in np.nonzero(st["accept"])[0]:
                 tvu.save_image(((xc[j] + 1) / 2).clamp(0, 1), os.path.join(opt.image_folder, "hmc_c%d_%d.png" % (a0 + j, st["epoch"][j])))
 
+    if latent_mode:
+        return _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_funcs, sigma_0, x_orig, y_0, cgen, mom, uni, on_it)
     out = None
     if n:
         out = sampler.hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
@@ -163,18 +201,20 @@ def sample_image(opt, config, model_config, device):
     return allc
 
 
-def main(argv=None):
+def main(argv=None, latent=False):
     parser = get_parser()
+    if latent:                                   # main_sampling_latent.py:828-830: epsilon defaults to 0.1 there
+        parser.set_defaults(epsilon=0.1, dataset="ffhq_latent")
     opt, _unknown = parser.parse_known_args(argv)
-    if opt.algo != "hmc":
-        raise SystemExit("this driver implements --algo hmc (got %r)" % opt.algo)
+    if opt.algo not in ("hmc", "hmc_latent") or (opt.algo == "hmc_latent") != bool(latent):
+        raise SystemExit("main_sampling.py implements --algo hmc, main_sampling_latent.py --algo hmc_latent (got %r)" % opt.algo)
     if not torch.cuda.is_available():
         raise SystemExit("a CUDA device (sm_100a) is required: there is no CPU fallback")
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     opt.config = os.path.join(here, "configs", "config_{}.yml".format(opt.dataset))
     with open(opt.config) as f:
         cfg = yaml.safe_load(f)
-    model_config = cfg["model"]
+    model_config = cfg.get("model_params") if latent else cfg["model"]
     config = dict2namespace(cfg)
     torch.manual_seed(opt.seed); np.random.seed(opt.seed); random.seed(opt.seed)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -61,7 +61,7 @@ def test_group_norm_epilogue(dtype, cl, mode, shape):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("rows,cols", [(64, 256), (37, 64), (8, 1024), (5, 4096), (3, 100)])
+@pytest.mark.parametrize("rows,cols", [(64, 256), (37, 64), (8, 1024), (5, 4096), (3, 100), (9, 512), (4, 6000), (2, 8192), (3, 9000), (2, 1022)])
 def test_softmax_epilogue(dtype, rows, cols):
     from nhmc_b200 import kernels
     g = torch.Generator().manual_seed(2)
