@@ -66,7 +66,10 @@ def dict2namespace(config):
 def prepare_measurement(opt, config, device):
     """Operator for --deg (main_sampling.py:261-351); doubles opt.sigma_0 like the reference (:348)."""
     deg, C, D = opt.deg, config.data.channels, config.data.image_size
-    if "sr" in deg and not deg.startswith("sr_bicubic"):
+    if deg.startswith("sr_bicubic"):
+        factor = int(deg[10:])
+        H = P.SRConv(P.bicubic_taps(factor), C, D, device, stride=factor)            # main_sampling.py:265-284
+    elif "sr" in deg:
         H = P.SuperResolution(C, D, int(deg[2:]), device)
     elif "inp" in deg and "box" in deg:
         H = P.Inpainting.box(C, D, device)                         # two random.randint(16, 112) draws (:292-293)
@@ -86,7 +89,7 @@ def prepare_measurement(opt, config, device):
         H = P.Denoising(C, D, device)
     else:
         raise SystemExit("ERROR: degradation type %r is not on the accelerated hmc path "
-                         "(supported: inpaint_random, inpaint_box, sr<r>, deblur_aniso, deblur_gauss, hdr, phase_retrieval, color, deno)" % deg)
+                         "(supported: inpaint_random, inpaint_box, sr<r>, sr_bicubic<r>, deblur_aniso, deblur_gauss, hdr, phase_retrieval, color, deno)" % deg)
     opt.sigma_0 = 2 * opt.sigma_0
     return H, opt.sigma_0, deg
 

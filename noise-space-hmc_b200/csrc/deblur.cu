@@ -19,11 +19,11 @@ enum { EPI_NONE = 0, EPI_GAIN = 1, EPI_RESID = 2, EPI_GRAD = 3 };
 struct GemmArgs {
   const float* A; int64_t sA; int lda_m, lda_k;   // A(m,k) = A[mat*sA + m*lda_m + k*lda_k]
   const float* B; int64_t sB; int ldb_k, ldb_n;   // B(k,n) = B[mat*sB + k*ldb_k + n*ldb_n]
-  float* C; int64_t sC;                           // C(m,n) = C[mat*sC + m*D + n]
-  int D, channels;
-  const float* gain;   // [channels][D][D]             (EPI_GAIN)
-  const float* y;      // [mats][D][D] measurement      (EPI_RESID)
-  const float* xhat;   // [mats][D][D] unclamped image  (EPI_GRAD)
+  float* C; int64_t sC;                           // C(m,n) = C[mat*sC + m*N + n]
+  int M, N, K, channels;                          // C is M x N, the contraction runs over K
+  const float* gain;   // [channels][M][N]             (EPI_GAIN)
+  const float* y;      // [mats][M][N] measurement      (EPI_RESID)
+  const float* xhat;   // [mats][M][N] unclamped image  (EPI_GRAD)
   double* loss;        // [chains]                      (EPI_RESID)
   int no_clamp;        // skip the final clip and its mask (latent path)
   RedWs ws;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
 gemm_kernel(GemmArgs a) {
   __shared__ __align__(16) float As[TK][TM + 4];
   __shared__ __align__(16) float Bs[TK][TN + 4];
-  const int D = a.D;
+  const int M = a.M, N = a.N, K = a.K;
   const int mat = blockIdx.z;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -46,18 +46,18 @@ gemm_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < D; k0 += TK) {
+  for (int k0 = 0; k0 < K; k0 += TK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;
       int m, k;
       if (a.lda_k == 1) { k = idx & (TK - 1); m = idx >> 4; } else { m = idx & (TM - 1); k = idx >> 6; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < D && gk < D) ? __ldg(Ab + (int64_t)gm * a.lda_m + (int64_t)gk * a.lda_k) : 0.f;
+      As[k][m] = (gm < M && gk < K) ? __ldg(Ab + (int64_t)gm * a.lda_m + (int64_t)gk * a.lda_k) : 0.f;
       int n, kb;
       if (a.ldb_n == 1) { n = idx & (TN - 1); kb = idx >> 6; } else { kb = idx & (TK - 1); n = idx >> 4; }
       const int gn = n0 + n, gkb = k0 + kb;
-      float v = (gn < D && gkb < D) ? __ldg(Bb + (int64_t)gkb * a.ldb_k + (int64_t)gn * a.ldb_n) : 0.f;
+      float v = (gn < N && gkb < K) ? __ldg(Bb + (int64_t)gkb * a.ldb_k + (int64_t)gn * a.ldb_n) : 0.f;
       if (CLAMP_B && !a.no_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
       Bs[kb][n] = v;
     }
@@ -83,16 +83,16 @@ gemm_kernel(GemmArgs a) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int gn = n0 + tx * 4 + j;
-      if (gm < D && gn < D) {
-        const int64_t off = (int64_t)gm * D + gn;
+      if (gm < M && gn < N) {
+        const int64_t off = (int64_t)gm * N + gn;
         float v = acc[i][j];
-        if (EPI == EPI_GAIN) v *= __ldg(a.gain + (int64_t)c * D * D + off);
+        if (EPI == EPI_GAIN) v *= __ldg(a.gain + (int64_t)c * M * N + off);
         if (EPI == EPI_RESID) {
-          v = __fsub_rn(__ldg(a.y + (int64_t)mat * D * D + off), v);
+          v = __fsub_rn(__ldg(a.y + (int64_t)mat * M * N + off), v);
           lsum += (double)v * (double)v;
         }
         if (EPI == EPI_GRAD) {
-          const float xh = __ldg(a.xhat + (int64_t)mat * D * D + off);
+          const float xh = __ldg(a.xhat + (int64_t)mat * M * N + off);
           v = -(2.0f * v) * ((a.no_clamp || (xh >= -1.0f && xh <= 1.0f)) ? 1.0f : 0.0f);
         }
         a.C[(int64_t)mat * a.sC + off] = v;
@@ -116,22 +116,21 @@ struct Mats { const float *U1, *V1, *U2, *V2; };
 // out = L' * X * R' with elementwise epilogue; L', R' given by (pointer, transposed?)
 template <int EPI, bool CLAMP>
 static void launch(GemmArgs a, int mats, cudaStream_t st) {
-  const int t = (a.D + TM - 1) / TM;
-  gemm_kernel<EPI, CLAMP><<<dim3(t, t, mats), 256, 0, st>>>(a);
+  gemm_kernel<EPI, CLAMP><<<dim3((a.N + TN - 1) / TN, (a.M + TM - 1) / TM, mats), 256, 0, st>>>(a);
 }
 
 static GemmArgs left(const float* M, bool trans, const float* X, float* out, int D, int C) {
   GemmArgs a{};
   a.A = M; a.sA = 0; a.lda_m = trans ? 1 : D; a.lda_k = trans ? D : 1;
   a.B = X; a.sB = (int64_t)D * D; a.ldb_k = D; a.ldb_n = 1;
-  a.C = out; a.sC = (int64_t)D * D; a.D = D; a.channels = C;
+  a.C = out; a.sC = (int64_t)D * D; a.M = a.N = a.K = D; a.channels = C;
   return a;
 }
 static GemmArgs right(const float* X, const float* M, bool trans, float* out, int D, int C) {
   GemmArgs a{};
   a.A = X; a.sA = (int64_t)D * D; a.lda_m = D; a.lda_k = 1;
   a.B = M; a.sB = 0; a.ldb_k = trans ? 1 : D; a.ldb_n = trans ? D : 1;
-  a.C = out; a.sC = (int64_t)D * D; a.D = D; a.channels = C;
+  a.C = out; a.sC = (int64_t)D * D; a.M = a.N = a.K = D; a.channels = C;
   return a;
 }
 
@@ -193,6 +192,79 @@ int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, floa
   launch<EPI_NONE, false>(left(op->V1, false, t1, t0, D, C), mats, st);
   GemmArgs g8 = right(t0, op->V2, true, g, D, C); g8.xhat = x_hat; g8.no_clamp = op->no_clamp;
   launch<EPI_GRAD, false>(g8, mats, st);
+  if (xc_out) {
+    const int64_t total = (int64_t)mats * D * D;
+    clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
+// =====================================================================================
+// Separable matrix operator Y_c = L X_c L^T (bicubic "SRConv", Hfuncs.py:527-607): in the reference's SVD form
+// H = U S V^T with the permutation of :558-559 this is L = U_small diag(s) V_small[:, :d]^T, a d x D matrix
+// (d = D / stride) applied on both sides; H^T R = L^T R L, H^+ Y = P Y P^T with P = V_small[:, :d] diag(1/s) U_small^T.
+// L and P are built by the caller from the reference's own SVD factors.  Same fp32 SIMT GEMM as above, rectangular.
+// =====================================================================================
+// out[mats][M x N] = Lm(M x K) * X[mats][K x N]          (Lm given row-major [rows x cols], optionally transposed)
+static GemmArgs left_rect(const float* Lm, int rows, int cols, bool trans, const float* X, float* out, int N, int C) {
+  GemmArgs a{};
+  const int M = trans ? cols : rows, K = trans ? rows : cols;
+  a.A = Lm; a.sA = 0; a.lda_m = trans ? 1 : cols; a.lda_k = trans ? cols : 1;
+  a.B = X; a.sB = (int64_t)K * N; a.ldb_k = N; a.ldb_n = 1;
+  a.C = out; a.sC = (int64_t)M * N; a.M = M; a.N = N; a.K = K; a.channels = C;
+  return a;
+}
+// out[mats][M x N] = X[mats][M x K] * Rm(K x N)
+static GemmArgs right_rect(const float* X, int M, const float* Rm, int rows, int cols, bool trans, float* out, int C) {
+  GemmArgs a{};
+  const int K = trans ? cols : rows, N = trans ? rows : cols;
+  a.A = X; a.sA = (int64_t)M * K; a.lda_m = K; a.lda_k = 1;
+  a.B = Rm; a.sB = 0; a.ldb_k = trans ? 1 : cols; a.ldb_n = trans ? cols : 1;
+  a.C = out; a.sC = (int64_t)M * N; a.M = M; a.N = N; a.K = K; a.channels = C;
+  return a;
+}
+
+size_t sepmat_workspace_bytes(const nhmc_op* op, int n_chains) {
+  const size_t D = op->img_dim, d = op->img_dim / op->ratio, mats = (size_t)n_chains * op->channels;
+  return (2 * mats * d * D + mats * d * d) * sizeof(float) + 256;
+}
+
+int sepmat_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
+  const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
+  float* t0 = reinterpret_cast<float*>(ws);                                       // [mats][d x D]
+  launch<EPI_NONE, false>(left_rect(op->U1, d, D, false, x, t0, D, C), mats, st);             // L X
+  launch<EPI_NONE, false>(right_rect(t0, d, op->U1, d, D, true, y, C), mats, st);             // (L X) L^T
+  return NHMC_LAUNCH_CHECK();
+}
+
+int sepmat_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
+  const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
+  float* t0 = reinterpret_cast<float*>(ws);                                       // [mats][D x d]
+  if (!pinv) {
+    launch<EPI_NONE, false>(left_rect(op->U1, d, D, true, r, t0, d, C), mats, st);             // L^T R
+    launch<EPI_NONE, false>(right_rect(t0, D, op->U1, d, D, false, out, C), mats, st);         // (L^T R) L
+  } else {
+    launch<EPI_NONE, false>(left_rect(op->V1, D, d, false, r, t0, d, C), mats, st);            // P Y
+    launch<EPI_NONE, false>(right_rect(t0, D, op->V1, D, d, true, out, C), mats, st);          // (P Y) P^T
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
+int sepmat_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
+                     int n_chains, void* workspace, cudaStream_t st) {
+  const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
+  NHMC_CHECK_ARG(((d + TM - 1) / TM) * ((d + TN - 1) / TN) * C <= kMaxBlocksPerChain, "measurement too large for the loss reduction");
+  const RedWs rw = red_ws(workspace, n_chains);
+  float* t0 = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));   // [mats][d x D]
+  float* t1 = t0 + (size_t)mats * d * D;                                               // [mats][D x d]
+  float* rr = t1 + (size_t)mats * d * D;                                               // [mats][d x d]
+  GemmArgs g1 = left_rect(op->U1, d, D, false, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
+  launch<EPI_NONE, true>(g1, mats, st);                                                // L clamp(X)
+  GemmArgs g2 = right_rect(t0, d, op->U1, d, D, true, rr, C); g2.y = y; g2.loss = loss; g2.ws = rw;
+  launch<EPI_RESID, false>(g2, mats, st);                                              // R = y - (L X) L^T, loss
+  launch<EPI_NONE, false>(left_rect(op->U1, d, D, true, rr, t1, d, C), mats, st);      // L^T R
+  GemmArgs g4 = right_rect(t1, D, op->U1, d, D, false, g, C); g4.xhat = x_hat; g4.no_clamp = op->no_clamp;
+  launch<EPI_GRAD, false>(g4, mats, st);                                               // -2 (L^T R L) .* mask
   if (xc_out) {
     const int64_t total = (int64_t)mats * D * D;
     clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);

@@ -240,6 +240,67 @@ class Deblurring(Deblurring2D):
         self.U_small, self.V_small = self.U_small1, self.V_small1
 
 
+def bicubic_taps(factor, a=-0.5):
+    """The 4*factor bicubic taps of main_sampling.py:266-281 (float64 numpy, normalised, then float32 and normalised again)."""
+    def bk(x):
+        x = abs(x)
+        if x <= 1:
+            return (a + 2) * x ** 3 - (a + 3) * x ** 2 + 1
+        if 1 < x < 2:
+            return a * x ** 3 - 5 * a * x ** 2 + 8 * a * x - 4 * a
+        return 0
+    k = np.zeros((factor * 4))
+    for i in range(factor * 4):
+        k[i] = bk((1 / factor) * (i - np.floor(factor * 4 / 2) + 0.5))
+    k = k / np.sum(k)
+    kernel = torch.from_numpy(k).float()
+    return kernel / kernel.sum()
+
+
+def _srconv_matrix(kernel, img_dim, stride):
+    """1-D strided convolution matrix with reflective padding (Hfuncs.py:541-551)."""
+    k = torch.as_tensor(kernel).detach().cpu().float()
+    small = img_dim // stride
+    Hs = torch.zeros(small, img_dim)
+    half = k.shape[0] // 2
+    for i in range(stride // 2, img_dim + stride // 2, stride):
+        for j in range(i - half, i + half):
+            je = j
+            if je < 0:
+                je = -je - 1
+            if je >= img_dim:
+                je = (img_dim - 1) - (je - img_dim)
+            Hs[i // stride, je] += k[j - i + half]
+    return Hs
+
+
+class SRConv(Operator):
+    """Convolution-based (bicubic) super-resolution, Hfuncs.py:527-607: Y_c = L X_c L^T with L = U_small diag(s)
+    V_small[:, :d]^T (d = D / stride; the permutation of :558-559 selects the leading d x d block of V^T X V),
+    H^T R = L^T R L, H^+ Y = P Y P^T with P = V_small[:, :d] diag(1/s) U_small^T.  L and P are formed once from the SVD
+    factors (the reference's own torch.svd call, or taken from a reference object)."""
+    kind = _lib.OP_SEPMAT
+    loss_grad_launches = 5
+
+    def __init__(self, kernel, channels, img_dim, device, stride=1, factors=None, zero=3e-2):
+        super().__init__(channels, img_dim, device)
+        self.ratio, self.small_dim = int(stride), img_dim // int(stride)
+        if factors is None:
+            U, S, V = torch.svd(_srconv_matrix(kernel, img_dim, self.ratio), some=False)
+            S = S.clone()
+            S[S < zero] = 0
+        else:
+            U, S, V = [torch.as_tensor(t).detach().cpu().float() for t in factors]
+        d = self.small_dim
+        Sinv = torch.where(S != 0, 1.0 / torch.where(S != 0, S, torch.ones_like(S)), torch.zeros_like(S))
+        Vd = V[:, :d]
+        self.U_small, self.singulars_small, self.V_small = U.to(self.device), S.to(self.device), V.to(self.device)
+        self.L = ((U * S[None, :]) @ Vd.t()).contiguous().to(self.device)            # [d, D]
+        self.P = ((Vd * Sinv[None, :]) @ U.t()).contiguous().to(self.device)         # [D, d]
+        self.desc.ratio = self.ratio
+        self.desc.U1, self.desc.V1 = self.L.data_ptr(), self.P.data_ptr()
+
+
 class Denoising(Operator):
     """H = identity on the CHW-flattened image (Hfuncs.py:157-177)."""
     kind = _lib.OP_DENOISE
@@ -307,6 +368,9 @@ def from_reference(H_funcs, channels, img_dim, device):
                                 and not hasattr(H_funcs, "small_dim") and tuple(H_funcs.U_small.shape) == (img_dim, img_dim)):
         return Deblurring(None, H_funcs.channels, H_funcs.img_dim, device,
                           tables=(H_funcs.U_small, H_funcs.V_small, H_funcs._singulars, H_funcs._perm))
+    if name == "SRConv" or (hasattr(H_funcs, "small_dim") and hasattr(H_funcs, "U_small") and hasattr(H_funcs, "singulars_small")):
+        return SRConv(None, H_funcs.channels, H_funcs.img_dim, device, stride=H_funcs.ratio,
+                      factors=(H_funcs.U_small, H_funcs.singulars_small, H_funcs.V_small))
     if name == "Colorization" or hasattr(H_funcs, "Vt_small"):
         return Colorization(H_funcs.img_dim, device, factors=(H_funcs.U_small, H_funcs.singulars_small, H_funcs.V_small))
     if name == "Denoising":

@@ -298,6 +298,76 @@ class Colorization(_Base):
         return (k[None, :, None] * y.reshape(B, 1, -1)).reshape(B, -1)
 
 
+# --------------------------------------------------------------------------------------
+# Convolution-based (bicubic) super-resolution: Hfuncs.py:527-607, kernel main_sampling.py:266-284
+# --------------------------------------------------------------------------------------
+def bicubic_taps(factor, a=-0.5):
+    def bk(x):
+        x = abs(x)
+        if x <= 1:
+            return (a + 2) * x ** 3 - (a + 3) * x ** 2 + 1
+        if 1 < x < 2:
+            return a * x ** 3 - 5 * a * x ** 2 + 8 * a * x - 4 * a
+        return 0
+    k = np.zeros((factor * 4))
+    for i in range(factor * 4):
+        k[i] = bk((1 / factor) * (i - np.floor(factor * 4 / 2) + 0.5))
+    k = k / np.sum(k)
+    kernel = torch.from_numpy(k).float()
+    return kernel / kernel.sum()
+
+
+def srconv_matrix(kernel, img_dim, stride):
+    """Hfuncs.py:541-551: strided 1-D convolution matrix [D/stride, D] with reflective padding."""
+    small = img_dim // stride
+    Hs = torch.zeros(small, img_dim)
+    half = kernel.shape[0] // 2
+    for i in range(stride // 2, img_dim + stride // 2, stride):
+        for j in range(i - half, i + half):
+            je = j
+            if je < 0:
+                je = -je - 1
+            if je >= img_dim:
+                je = (img_dim - 1) - (je - img_dim)
+            Hs[i // stride, je] += kernel[j - i + half]
+    return Hs
+
+
+class SRConv(_Base):
+    """Y_c = L X_c L^T, L = U diag(s) V[:, :d]^T: `Vt` (:571-578) forms V^T X V and moves its leading d x d block (the
+    `_perm` of :558-559) to the front, `singulars()` (:598-599) scales coefficient (i, j) by s_i s_j for every channel,
+    `U` (:580-588) maps back with U . U^T."""
+
+    def __init__(self, channels, img_dim, stride, U, S, V):
+        self.channels, self.img_dim, self.d = channels, img_dim, img_dim // stride
+        Vd = V[:, :self.d]
+        Sinv = torch.where(S != 0, 1.0 / torch.where(S != 0, S, torch.ones_like(S)), torch.zeros_like(S))
+        self.L = (U * S[None, :]) @ Vd.t()
+        self.P = (Vd * Sinv[None, :]) @ U.t()
+
+    @classmethod
+    def from_kernel(cls, kernel, channels, img_dim, stride, zero=3e-2):
+        U, S, V = torch.svd(srconv_matrix(kernel, img_dim, stride), some=False)
+        S = S.clone()
+        S[S < zero] = 0
+        return cls(channels, img_dim, stride, U, S, V)
+
+    def H(self, x):
+        B = x.shape[0]
+        L = self.L.to(x.dtype)
+        return (L @ x.reshape(B, self.channels, self.img_dim, self.img_dim) @ L.t()).reshape(B, -1)
+
+    def Ht(self, r):
+        B = r.shape[0]
+        L = self.L.to(r.dtype)
+        return (L.t() @ r.reshape(B, self.channels, self.d, self.d) @ L).reshape(B, -1)
+
+    def H_pinv(self, y):
+        B = y.shape[0]
+        P = self.P.to(y.dtype)
+        return (P @ y.reshape(B, self.channels, self.d, self.d) @ P.t()).reshape(B, -1)
+
+
 def box_missing_indices(channels, img_dim, left, up, size=128):
     """main_sampling.py:290-299: channel-interleaved indices (3*pix + c) of a size x size box at rows left.., cols up.."""
     m = torch.zeros(img_dim, img_dim, channels)

@@ -163,6 +163,27 @@ def gold_operators_ext():
 
     _op_record("deno", Hfuncs.Denoising(3, D, "cpu"), x, rec)
 
+    # bicubic SRConv: kernel exactly as main_sampling.py:266-284 (factor 4)
+    factor = 4
+    def bicubic_kernel(x_, a=-0.5):
+        if abs(x_) <= 1:
+            return (a + 2) * abs(x_) ** 3 - (a + 3) * abs(x_) ** 2 + 1
+        elif 1 < abs(x_) and abs(x_) < 2:
+            return a * abs(x_) ** 3 - 5 * a * abs(x_) ** 2 + 8 * a * abs(x_) - 4 * a
+        else:
+            return 0
+    kk = np.zeros((factor * 4))
+    for i in range(factor * 4):
+        x_ = (1 / factor) * (i - np.floor(factor * 4 / 2) + 0.5)
+        kk[i] = bicubic_kernel(x_)
+    kk = kk / np.sum(kk)
+    kern = torch.from_numpy(kk).float()
+    Hb = Hfuncs.SRConv(kern / kern.sum(), 3, D, "cpu", stride=factor)
+    for k in ("U_small", "singulars_small", "V_small"):
+        rec["srbic_tab_" + k] = getattr(Hb, k)
+    rec["srbic_kernel"] = kern / kern.sum()
+    _op_record("srbic", Hb, x, rec)
+
     # box inpainting: the index construction of main_sampling.py:290-299 at D = 32 with a 16 x 16 box
     left, up, size = 5, 9, 16
     missing = torch.zeros([D, D, 3])

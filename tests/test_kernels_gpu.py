@@ -198,10 +198,12 @@ def _ops_ext_from_golden(g, D=32):
         "color": (P.Colorization(D, "cuda", factors=fac), oops.Colorization(D, *fac)),
         "deno": (P.Denoising(3, D, "cuda"), oops.Denoising()),
         "box": (P.Inpainting(3, D, T(g["box_missing"]), "cuda"), oops.Inpainting.from_missing_indices(3, D, g["box_missing"])),
+        "srbic": (P.SRConv(None, 3, D, "cuda", stride=4, factors=[T(g["srbic_tab_" + k]) for k in ("U_small", "singulars_small", "V_small")]),
+                  oops.SRConv(3, D, 4, *[T(g["srbic_tab_" + k]) for k in ("U_small", "singulars_small", "V_small")])),
     }
 
 
-@pytest.mark.parametrize("name", ["dgauss", "color", "deno", "box"])
+@pytest.mark.parametrize("name", ["dgauss", "color", "deno", "box", "srbic"])
 def test_next_row_operator_vs_golden_and_oracle(nb, golden, name):
     """SURVEY.md 8f N4 operators through the C ABI against the reference's recorded outputs and the oracle."""
     g = golden("operators_ext.npz")
@@ -261,6 +263,12 @@ def test_next_row_operators_full_size_and_from_reference(nb):
         "deno": (P.Denoising(3, D, "cuda"), oops.Denoising()),
         "box": (box, oops.Inpainting.from_missing_indices(3, D, oops.box_missing_indices(3, D, left, up).numpy())),
     }
+    srb = P.SRConv(P.bicubic_taps(4), 3, D, "cuda", stride=4)                     # --deg sr_bicubic4 (main_sampling.py:265-284)
+    assert srb.meas_shape(B) == (B, 3 * 64 * 64)
+    cases["srbic"] = (srb, oops.SRConv(3, D, 4, srb.U_small.cpu(), srb.singulars_small.cpu(), srb.V_small.cpu()))
+    srb2 = P.from_reference(types.SimpleNamespace(U_small=srb.U_small.cpu(), singulars_small=srb.singulars_small.cpu(), V_small=srb.V_small.cpu(),
+                                                  small_dim=64, ratio=4, channels=3, img_dim=D), 3, D, "cuda")
+    assert isinstance(srb2, P.SRConv) and torch.equal(srb2.L, srb.L)
     for name, (op, oop) in cases.items():
         y = oop.H(x_true); y = y + 0.1 * torch.randn(y.shape, generator=g)
         Hx = op.H(dev(x_true)).cpu()

@@ -83,6 +83,7 @@ def _make_ops_ext(g):
         "color": oops.Colorization(D, T(g["color_tab_U_small"]), T(g["color_tab_singulars_small"]), T(g["color_tab_V_small"])),
         "deno": oops.Denoising(),
         "box": oops.Inpainting.from_missing_indices(3, D, g["box_missing"]),
+        "srbic": oops.SRConv(3, D, 4, T(g["srbic_tab_U_small"]), T(g["srbic_tab_singulars_small"]), T(g["srbic_tab_V_small"])),
     }
 
 
@@ -108,6 +109,9 @@ def test_next_row_operators_match_reference(golden):
     assert np.array_equal(oops.gaussian_taps(10.0, half=2).numpy(), g["dgauss_kernel"])          # main_sampling.py:307-312
     left, up, size = [int(v) for v in g["box_geom"]]
     assert np.array_equal(oops.box_missing_indices(3, 32, left, up, size).numpy(), g["box_missing"])
+    assert np.array_equal(oops.bicubic_taps(4).numpy(), g["srbic_kernel"])                        # main_sampling.py:266-284
+    Ub, Sb, Vb = torch.svd(oops.srconv_matrix(T(g["srbic_kernel"]), 32, 4), some=False)
+    assert np.array_equal(Ub.numpy(), g["srbic_tab_U_small"]) and np.array_equal(Vb.numpy(), g["srbic_tab_V_small"])
     Uc, Sc, Vc = torch.svd(torch.Tensor([[0.3333, 0.3334, 0.3333]]), some=False)
     np.testing.assert_allclose(oops.Colorization(32).H(T(g["color_x"]).clamp(-1, 1)).numpy(), g["color_Hx"], atol=1e-6)
 
