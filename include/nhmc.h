@@ -136,6 +136,7 @@ int nhmc_ddim_bwd(const float* g_a, const float* g_b, const uint32_t* mask, floa
 #define NHMC_OP_PHASE 4    /* Hfuncs.py:318-366 + fastmri_utils.py:67-114 */
 #define NHMC_OP_DENOISE 5  /* Hfuncs.py:157-177  (H = identity)                */
 #define NHMC_OP_COLOR 6    /* Hfuncs.py:655-695  (per-pixel weighted grey value) */
+#define NHMC_OP_CS 8       /* Hfuncs.py:611-651  (Walsh-Hadamard compressive sensing: kept_pix = pixel permutation, n_kept = D*D/ratio) */
 #define NHMC_OP_SEPMAT 7   /* Hfuncs.py:527-607  (SRConv: Y_c = L X_c L^T, L = [D/ratio, D] in U1, P = [D, D/ratio] in V1) */
 
 typedef struct nhmc_op {

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 F32, BF16, F16 = 0, 1, 2
 LF_FIRST, LF_MIDDLE, LF_LAST = 0, 1, 2
 SCHED_PIXEL, SCHED_LATENT = 0, 1
-OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE, OP_DENOISE, OP_COLOR, OP_SEPMAT = 0, 1, 2, 3, 4, 5, 6, 7
+OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE, OP_DENOISE, OP_COLOR, OP_SEPMAT, OP_CS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 GN_PLAIN, GN_SILU, GN_FILM_SILU = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 

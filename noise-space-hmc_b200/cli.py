@@ -85,11 +85,13 @@ def prepare_measurement(opt, config, device):
         H = P.Deblurring2D(P.gaussian_taps(1.0), P.gaussian_taps(20.0), C, D, device)
     elif deg == "color":
         H = P.Colorization(D, device)
+    elif deg.startswith("cs"):
+        H = P.WalshHadamardCS.random(C, D, int(deg[2:]), device)                     # main_sampling.py:322-325
     elif deg in ("deno", "denoise", "denoising"):                  # Hfuncs.Denoising; the reference's driver has no --deg for it
         H = P.Denoising(C, D, device)
     else:
         raise SystemExit("ERROR: degradation type %r is not on the accelerated hmc path "
-                         "(supported: inpaint_random, inpaint_box, sr<r>, sr_bicubic<r>, deblur_aniso, deblur_gauss, hdr, phase_retrieval, color, deno)" % deg)
+                         "(supported: inpaint_random, inpaint_box, sr<r>, sr_bicubic<r>, cs<r>, deblur_aniso, deblur_gauss, hdr, phase_retrieval, color, deno)" % deg)
     opt.sigma_0 = 2 * opt.sigma_0
     return H, opt.sigma_0, deg
 

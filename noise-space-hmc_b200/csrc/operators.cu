@@ -19,6 +19,10 @@ int sepmat_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_
 int sepmat_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t, bool pinv);
 int sepmat_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
 size_t sepmat_workspace_bytes(const nhmc_op*, int);
+int cs_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int cs_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int cs_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
+size_t cs_workspace_bytes(const nhmc_op*, int);
 int phase_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int phase_pinv(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int phase_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
@@ -347,6 +351,9 @@ static int check_op(const nhmc_op* op) {
     case NHMC_OP_SEPMAT:
       NHMC_CHECK_ARG(op->ratio > 0 && op->img_dim % op->ratio == 0 && op->U1, "separable operator needs ratio | img_dim and the L matrix");
       break;
+    case NHMC_OP_CS:
+      NHMC_CHECK_ARG(op->n_kept >= 0 && (op->n_kept == 0 || op->kept_pix) && (int64_t)op->n_kept <= (int64_t)op->img_dim * op->img_dim, "compressive sensing needs the pixel permutation (kept_pix) and n_kept <= D*D");
+      break;
     case NHMC_OP_DENOISE:
       break;
     case NHMC_OP_COLOR:
@@ -374,6 +381,7 @@ extern "C" int64_t nhmc_op_meas_size(const nhmc_op* op) {
     case NHMC_OP_PHASE: return C * (D + 2 * op->pad) * (D + 2 * op->pad);
     case NHMC_OP_DENOISE: return C * D * D;
     case NHMC_OP_COLOR: return D * D;
+    case NHMC_OP_CS: return (int64_t)op->n_kept * C;
     case NHMC_OP_SEPMAT: return op->ratio > 0 ? C * (D / op->ratio) * (D / op->ratio) : -1;
     default: return -1;
   }
@@ -385,6 +393,7 @@ extern "C" size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains) {
   base = (base + 255) & ~(size_t)255;
   if (op->kind == NHMC_OP_DEBLUR2D) return base + deblur_workspace_bytes(op, n_chains);
   if (op->kind == NHMC_OP_SEPMAT) return base + sepmat_workspace_bytes(op, n_chains);
+  if (op->kind == NHMC_OP_CS) return base + cs_workspace_bytes(op, n_chains);
   if (op->kind == NHMC_OP_PHASE) return base + phase_workspace_bytes(op, n_chains);
   return base;
 }
@@ -438,6 +447,11 @@ extern "C" int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int 
       char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
       return sepmat_forward(op, x, y, n_chains, ws, st);
     }
+    case NHMC_OP_CS: {
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return cs_forward(op, x, y, n_chains, ws, st);
+    }
   }
   return NHMC_LAUNCH_CHECK();
 }
@@ -471,6 +485,11 @@ static int adjoint_or_pinv(const nhmc_op* op, const float* r, float* out, int n_
       NHMC_CHECK_ARG(!pinv || op->gain_pinv, "gain_pinv table missing");
       char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
       return deblur_adjoint(op, r, out, n_chains, ws, st, pinv);
+    }
+    case NHMC_OP_CS: {   // all singular values are 1: H^+ = H^T
+      NHMC_CHECK_ARG(workspace, "workspace required");
+      char* ws = (char*)workspace + ((red_ws_bytes(n_chains) + 255) & ~(size_t)255);
+      return cs_adjoint(op, r, out, n_chains, ws, st);
     }
     case NHMC_OP_SEPMAT: {
       NHMC_CHECK_ARG(workspace, "workspace required");
@@ -550,6 +569,8 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
       return deblur_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
     case NHMC_OP_SEPMAT:
       return sepmat_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
+    case NHMC_OP_CS:
+      return cs_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
     case NHMC_OP_PHASE:
       (void)extra;
       return phase_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);

@@ -301,6 +301,28 @@ class SRConv(Operator):
         self.desc.U1, self.desc.V1 = self.L.data_ptr(), self.P.data_ptr()
 
 
+class WalshHadamardCS(Operator):
+    """Walsh-Hadamard compressive sensing, Hfuncs.py:611-651 (--deg cs<ratio>): y[b, k*C + c] = FWHT(x_c)[perm[k]] / D for
+    the first D*D/ratio entries of a pixel permutation; all singular values are 1, so H^+ = H^T = FWHT(scatter(.))."""
+    kind = _lib.OP_CS
+    loss_grad_launches = 7
+
+    def __init__(self, channels, img_dim, ratio, perm, device):
+        super().__init__(channels, img_dim, device)
+        self.ratio = int(ratio)
+        self.perm = torch.as_tensor(perm).to(self.device).long()
+        assert self.perm.numel() == img_dim ** 2
+        self._perm32 = self.perm.to(torch.int32).contiguous()
+        self.desc.ratio = self.ratio
+        self.desc.n_kept = img_dim ** 2 // self.ratio
+        self.desc.kept_pix = self._perm32.data_ptr()
+
+    @classmethod
+    def random(cls, channels, img_dim, ratio, device):
+        """main_sampling.py:322-325: torch.randperm(D*D) drawn on the DEVICE generator."""
+        return cls(channels, img_dim, ratio, torch.randperm(img_dim ** 2, device=device), device)
+
+
 class Denoising(Operator):
     """H = identity on the CHW-flattened image (Hfuncs.py:157-177)."""
     kind = _lib.OP_DENOISE
@@ -371,6 +393,8 @@ def from_reference(H_funcs, channels, img_dim, device):
     if name == "SRConv" or (hasattr(H_funcs, "small_dim") and hasattr(H_funcs, "U_small") and hasattr(H_funcs, "singulars_small")):
         return SRConv(None, H_funcs.channels, H_funcs.img_dim, device, stride=H_funcs.ratio,
                       factors=(H_funcs.U_small, H_funcs.singulars_small, H_funcs.V_small))
+    if name == "WalshHadamardCS" or (hasattr(H_funcs, "perm") and hasattr(H_funcs, "fwht")):
+        return WalshHadamardCS(H_funcs.channels, H_funcs.img_dim, H_funcs.ratio, H_funcs.perm, device)
     if name == "Colorization" or hasattr(H_funcs, "Vt_small"):
         return Colorization(H_funcs.img_dim, device, factors=(H_funcs.U_small, H_funcs.singulars_small, H_funcs.V_small))
     if name == "Denoising":
@@ -383,4 +407,4 @@ def from_reference(H_funcs, channels, img_dim, device):
         op = PhaseRetrievalOperator(2.0, device, channels, img_dim)
         op.pad = int(H_funcs.pad); op.desc.pad = op.pad
         return op
-    raise _lib.NhmcError("operator %s is not on the accelerated path (inpaint, sr, hdr, deblur_aniso, deblur_gauss, phase, color, deno)" % name)
+    raise _lib.NhmcError("operator %s is not on the accelerated path (inpaint, sr, hdr, deblur_aniso, deblur_gauss, sr_bicubic, cs, phase, color, deno)" % name)

@@ -368,6 +368,46 @@ class SRConv(_Base):
         return (P @ y.reshape(B, self.channels, self.d, self.d) @ P.t()).reshape(B, -1)
 
 
+# --------------------------------------------------------------------------------------
+# Walsh-Hadamard compressive sensing: Hfuncs.py:611-651
+# --------------------------------------------------------------------------------------
+def fwht(x, img_dim):
+    """Natural-order fast Walsh-Hadamard transform over the flattened D*D pixels of every channel, divided by D
+    (Hfuncs.py:613-622); the same butterfly order as the reference, so fp32 results are bit-identical."""
+    B, C = x.shape[0], x.shape[1]
+    a = x.reshape(B, C, img_dim ** 2)
+    h = 1
+    while h < img_dim ** 2:
+        a = a.reshape(B, C, -1, h * 2)
+        lo, hi = a[:, :, :, :h], a[:, :, :, h:2 * h]
+        a = torch.cat([lo + hi, lo - hi], dim=3)
+        h *= 2
+    return a.reshape(B, C, img_dim ** 2) / img_dim
+
+
+class WalshHadamardCS(_Base):
+    """y[b, k*C + c] = fwht(x)[b, c, perm[k]], k < D*D/ratio (`Vt` :631-632 + the truncation in `H`, Hfuncs.py:65-71)."""
+
+    def __init__(self, channels, img_dim, ratio, perm):
+        self.channels, self.img_dim, self.ratio = channels, img_dim, ratio
+        self.perm = torch.as_tensor(perm).long()
+        self.n = img_dim ** 2 // ratio
+
+    def H(self, x):
+        B = x.shape[0]
+        t = fwht(x.reshape(B, self.channels, self.img_dim, self.img_dim), self.img_dim)
+        return t[:, :, self.perm[: self.n]].permute(0, 2, 1).reshape(B, -1)
+
+    def Ht(self, r):
+        B = r.shape[0]
+        temp = torch.zeros(B, self.channels, self.img_dim ** 2, dtype=r.dtype)
+        temp[:, :, self.perm[: self.n]] = r.reshape(B, self.n, self.channels).permute(0, 2, 1)
+        return fwht(temp, self.img_dim).reshape(B, -1)
+
+    def H_pinv(self, y):
+        return self.Ht(y)
+
+
 def box_missing_indices(channels, img_dim, left, up, size=128):
     """main_sampling.py:290-299: channel-interleaved indices (3*pix + c) of a size x size box at rows left.., cols up.."""
     m = torch.zeros(img_dim, img_dim, channels)

@@ -184,6 +184,12 @@ def gold_operators_ext():
     rec["srbic_kernel"] = kern / kern.sum()
     _op_record("srbic", Hb, x, rec)
 
+    # Walsh-Hadamard compressive sensing (main_sampling.py:322-325), ratio 4
+    pg = torch.Generator().manual_seed(31)
+    perm = torch.randperm(D ** 2, generator=pg)
+    rec["cs_perm"] = perm
+    _op_record("cs", Hfuncs.WalshHadamardCS(3, D, 4, perm, "cpu"), x, rec)
+
     # box inpainting: the index construction of main_sampling.py:290-299 at D = 32 with a 16 x 16 box
     left, up, size = 5, 9, 16
     missing = torch.zeros([D, D, 3])

@@ -84,6 +84,7 @@ def _make_ops_ext(g):
         "deno": oops.Denoising(),
         "box": oops.Inpainting.from_missing_indices(3, D, g["box_missing"]),
         "srbic": oops.SRConv(3, D, 4, T(g["srbic_tab_U_small"]), T(g["srbic_tab_singulars_small"]), T(g["srbic_tab_V_small"])),
+        "cs": oops.WalshHadamardCS(3, D, 4, g["cs_perm"]),
     }
 
 
