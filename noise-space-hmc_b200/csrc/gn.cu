@@ -478,9 +478,21 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 // Group totals of per-channel partial sums (s0, s1) of this CTA -> g_acc[g][0..1] (fp64), then -- when the
 // sample spans several CTAs -- through the global accumulators and the per-sample barrier.  Ends with the
 // sample-wide totals in g_acc, visible to every thread.
-template <int V>
+// cluster helpers: hardware barrier across the CTAs of a thread-block cluster and reads of a peer CTA's shared memory
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ double ld_dsmem_f64(const double* local_smem, unsigned rank) {
+  unsigned addr = smem_u32(local_smem), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(rank));
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+template <int V, bool CLUSTER>
 __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (&s1)[V], const GnResArgs& r, int b,
-                                             int c0, int cvec, int rows, float4* part, double (*g_acc)[2]) {
+                                             int c0, int cvec, int rows, float4* part, double (*g_acc)[2],
+                                             double (*g_part)[2]) {
   const GnArgs& a = r.a;
   const int Cg = a.C / a.G;
   const int g0 = c0 / Cg;
@@ -502,7 +514,9 @@ __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (
         t0 += (double)(j ? t.z : t.x); t1 += (double)(j ? t.w : t.y);
       }
     }
-    if (r.nb > 1) {
+    if (CLUSTER) {
+      g_part[g][0] = t0; g_part[g][1] = t1;        // read by every CTA of the cluster through DSMEM
+    } else if (r.nb > 1) {
       atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
       atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
       __threadfence();
@@ -511,6 +525,21 @@ __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (
     }
   }
   __syncthreads();
+  if (CLUSTER) {
+    // one sample = one thread-block cluster: hardware barrier, then every CTA sums the nb partials of each group
+    // in rank order out of its peers' shared memory -- no global atomics, no spinning, deterministic
+    cluster_arrive();
+    cluster_wait();
+    if (threadIdx.x < a.G) {
+      const int g = threadIdx.x;
+      double t0 = 0.0, t1 = 0.0;
+      for (int k = 0; k < r.nb; ++k) { t0 += ld_dsmem_f64(&g_part[g][0], (unsigned)k); t1 += ld_dsmem_f64(&g_part[g][1], (unsigned)k); }
+      g_acc[g][0] = t0; g_acc[g][1] = t1;
+    }
+    cluster_arrive();        // peers may exit (and release their shared memory) only after everybody has read: waited at kernel end
+    __syncthreads();
+    return;
+  }
   if (r.nb > 1) {
     if (threadIdx.x == 0) {
       atomicAdd(r.arrive + b, 1u);
@@ -539,7 +568,7 @@ __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (
 }
 
 // PHASE 0: y = act(gn(x + in_bias));  PHASE 1: dx = gn_bwd(dy) (+ add)
-template <typename T, int MODE, int PHASE>
+template <typename T, int MODE, int PHASE, bool CLUSTER>
 __global__ void __launch_bounds__(256, PHASE == 1 ? 3 : 4)
 gn_nhwc_resident_kernel(const GnResArgs r) {
   constexpr int V = VecOf<T>::N;
@@ -551,9 +580,11 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
   __shared__ float4 part[256];
   __shared__ double g_acc[32][2];      // the resident path takes G <= 32 (static shared memory is part of the budget)
   __shared__ float g_c0[32], g_c1[32];
+  __shared__ double g_part[CLUSTER ? 32 : 1][2];
   __shared__ unsigned int s_lid;
   if (threadIdx.x == 0) {
-    s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
+    // cluster launch: sample = cluster index, CTA of the sample = rank in the cluster (grid is [B * nb], cluster [nb])
+    s_lid = CLUSTER ? blockIdx.x : atomicInc(r.ticket, r.total_ctas - 1u);
     for (int k = 0; k < kResChunks; ++k) mbar_init(bars + k, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -611,7 +642,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
         s0[i] = s0[i] + cnt * bia;
       }
     }
-    group_totals<V>(s0, s1, r, b, c0, cvec, rows, part, g_acc);
+    group_totals<V, CLUSTER>(s0, s1, r, b, c0, cvec, rows, part, g_acc, g_part);
     if (threadIdx.x < a.G) {
       const int g = threadIdx.x;
       const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
@@ -689,7 +720,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
       s1[i] = cgm * rstd * (t1 - mean * t0);
       k1[i] = rstd * cgm; k2[i] = mean; k3[i] = rstd;   // finished below once the group means are known
     }
-    group_totals<V>(s0, s1, r, b, c0, cvec, rows, part, g_acc);
+    group_totals<V, CLUSTER>(s0, s1, r, b, c0, cvec, rows, part, g_acc, g_part);
     if (threadIdx.x < a.G) {
       const int g = threadIdx.x;
       const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
@@ -730,6 +761,7 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
       }
     }
   }
+  if (CLUSTER) cluster_wait();    // every peer has finished reading this CTA's partial sums
 }
 
 // ============================== NCHW =========================================================
@@ -849,6 +881,11 @@ static DevInfo dev_info() {
   return d;
 }
 
+static int g_cluster_mode = -1;    // NHMC_GN_CLUSTER=0 / nhmc_gn_set_resident(1) keep the global-barrier resident kernel only
+static int cluster_mode() {
+  if (g_cluster_mode < 0) { const char* e = getenv("NHMC_GN_CLUSTER"); g_cluster_mode = (e && e[0] == '0') ? 0 : 1; }
+  return g_cluster_mode;
+}
 static int g_resident_mode = -1;   // NHMC_GN_RESIDENT=0 / nhmc_gn_set_resident(0) force the two-kernel path (A/B measurements, tests)
 static int resident_mode() {
   if (g_resident_mode < 0) { const char* e = getenv("NHMC_GN_RESIDENT"); g_resident_mode = (e && e[0] == '0') ? 0 : 1; }
@@ -867,7 +904,7 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     if ((cv * V + V - 1) / Cg - (cv * V) / Cg > 1) return NHMC_ERR_UNSUPPORTED;   // a thread may span at most 2 groups
   const DevInfo d = dev_info();
   if (!d.ok) return NHMC_ERR_UNSUPPORTED;
-  auto kern = gn_nhwc_resident_kernel<T, MODE, PHASE>;
+  auto kern = gn_nhwc_resident_kernel<T, MODE, PHASE, false>;
   static int static_smem = -1;   // per instantiation
   if (static_smem < 0) {
     cudaFuncAttributes fa;
@@ -879,7 +916,50 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
   }
   const int64_t row_bytes = (int64_t)a0.C * sizeof(T);
   const int64_t pass_bytes = (int64_t)threads * 16;
-  // Single wave only: every CTA of the launch must be on the chip at once (k CTAs per SM).  Larger tensors go
+  // (a) One sample per thread-block cluster (<= 8 CTAs, the portable limit): the per-sample reduction runs over
+  // distributed shared memory behind the hardware cluster barrier -- no global atomics, no ticket, no spinning.
+  // Taken whenever a sample's slab fits in 8 CTAs' shared memory (the 8x8 .. 32x32 maps at FFHQ-256).
+  if (cluster_mode()) {
+    auto ckern = gn_nhwc_resident_kernel<T, MODE, PHASE, true>;
+    static int c_static = -1;
+    if (c_static < 0) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, ckern) == cudaSuccess &&
+          cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess)
+        c_static = (int)fa.sharedSizeBytes;
+      else { cudaGetLastError(); c_static = 1 << 30; }
+    }
+    const int64_t sample_bytes = a0.HW * row_bytes;
+    const int64_t limit = ((int64_t)(d.smem_optin - c_static) / NSRC) & ~(int64_t)127;
+    int64_t nb = (sample_bytes + 32767) / 32768;                    // ~32 KiB of input per CTA ...
+    if (nb > 8) nb = 8;                                             // ... but at most 8 CTAs per sample
+    if (nb < 1) nb = 1;
+    int64_t rows_per_cta = (a0.HW + nb - 1) / nb;
+    nb = (a0.HW + rows_per_cta - 1) / rows_per_cta;
+    if (limit > 0 && rows_per_cta * row_bytes <= limit) {
+      const int64_t slab = ((rows_per_cta * row_bytes + 127) / 128) * 128;
+      GnResArgs r{};
+      r.a = a0;
+      r.a.rows_per_cta = rows_per_cta;
+      r.nb = (int)nb;
+      const int64_t n_pass = (rows_per_cta * row_bytes + pass_bytes - 1) / pass_bytes;
+      r.chunk_passes = (int)((n_pass + kResChunks - 1) / kResChunks);
+      r.total_ctas = (unsigned int)(nb * batch);
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(r.total_ctas); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)slab * NSRC; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)nb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      int n_clusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&n_clusters, ckern, &cfg) == cudaSuccess && n_clusters >= 1) {
+        if (int e = cuda_status(cudaLaunchKernelEx(&cfg, ckern, r), "cluster launch")) return e;
+        return NHMC_OK;
+      }
+      cudaGetLastError();
+    }
+  }
+  // (b) Single wave only: every CTA of the launch must be on the chip at once (k CTAs per SM).  Larger tensors go
   // through the statistics + apply kernels, whose second read is served by the L2 for what still fits there
   // (measured in situ: the resident scheme loses once a launch needs several waves, because the per-sample
   // barrier then serialises load -> reduce -> store phases that the two-kernel path overlaps).
@@ -1089,7 +1169,10 @@ extern "C" int nhmc_gn_check(void) {
 }
 
 extern "C" int nhmc_gn_set_resident(int on) {
-  const int prev = resident_mode();
+  // 0: statistics + apply kernels only; 1: + resident kernel with the global per-sample barrier; 2 (default): + the
+  // thread-block-cluster variant for samples that fit in 8 CTAs
+  const int prev = resident_mode() ? (cluster_mode() ? 2 : 1) : 0;
   g_resident_mode = on ? 1 : 0;
+  g_cluster_mode = on >= 2 ? 1 : 0;
   return prev;
 }
