@@ -270,9 +270,10 @@ int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* x1, int c0,
                     const void* add1, int batch, int64_t hw, int groups, nhmc_stream_t stream);
 int nhmc_gn_check(void);
 /* Channels-last execution paths: 0 = statistics + apply kernels only; 1 = + the shared-memory-resident
- * single kernel with a global per-sample barrier; 2 (default) = + its thread-block-cluster variant (one
- * sample per cluster of <= 8 CTAs, reduction over distributed shared memory).  Returns the previous
- * setting.  For A/B measurements and tests. */
+ * single kernel with a global per-sample barrier; 2 = + its thread-block-cluster variant (one sample per
+ * cluster of <= 8 CTAs, reduction over distributed shared memory); 3 (default) = + the resident-by-
+ * channel-slice kernel for tensors beyond one wave (units of whole groups, >= 2 units on the chip at
+ * once, x and dy read once).  Returns the previous setting.  For A/B measurements and tests. */
 int nhmc_gn_set_resident(int on);
 
 /* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of

@@ -211,19 +211,23 @@ __device__ __forceinline__ SegSel seg_select(const void* x1, int c_split, int C,
 // earlier mbarrier/TMA shared-memory ring topped out at ~4.5 TB/s (59 % issue slots busy on ring bookkeeping,
 // 57 % DRAM throughput).  TMA stays where it buys something: the resident kernel below, which needs the slab in
 // shared memory anyway.
-template <int NSRC, int NX, typename Body>
+template <int NSRC, int NX, bool REV, typename Body>
 __device__ __forceinline__ void stream_rows(const RowPtr x, const RowPtr d, const RowPtr (&ex)[NX], int64_t r_begin,
                                             int64_t r_end, int prow, int rows, Body body) {
   constexpr int U = NSRC == 2 ? 4 : 8;
   const int64_t r0 = r_begin + prow;
   const int n = r_end > r0 ? (int)((r_end - r0 + rows - 1) / rows) : 0;      // rows this thread visits
-  const char* px = x.p + r0 * x.stride;
-  const char* pd = NSRC == 2 ? d.p + r0 * d.stride : nullptr;
-  const int64_t sx = (int64_t)rows * x.stride, sd = (int64_t)rows * d.stride;
+  // REV: last row first (so that a re-read starts on what the previous kernel touched last).  Measured on B200: no gain
+  // for the apply kernels (the L2 does not behave like an LRU over a 268 MB stream), so both kernels walk forwards.
+  const int64_t first = REV ? r0 + (int64_t)(n > 0 ? n - 1 : 0) * rows : r0;
+  const int64_t dir = REV ? -1 : 1;
+  const char* px = x.p + first * x.stride;
+  const char* pd = NSRC == 2 ? d.p + first * d.stride : nullptr;
+  const int64_t sx = dir * rows * x.stride, sd = dir * rows * d.stride;
   char* pe[NX];
   int64_t se[NX];
 #pragma unroll
-  for (int i = 0; i < NX; ++i) { pe[i] = ex[i].p + r0 * ex[i].stride; se[i] = (int64_t)rows * ex[i].stride; }
+  for (int i = 0; i < NX; ++i) { pe[i] = ex[i].p + first * ex[i].stride; se[i] = dir * rows * ex[i].stride; }
   for (int k = 0; k < n; k += U) {
     uint4 vx[U], vd[U];
 #pragma unroll
@@ -283,7 +287,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
   // PHASE 1 accumulates t0 = sum dy*act'(z), t1 = sum dy*act'(z)*x per channel; the per-channel
   // affine (gamma(1+s), mean, rstd) is applied once after the loop.
   const RowPtr none[1] = {{nullptr, 0}};
-  stream_rows<PHASE == 1 ? 2 : 1, 1>(xr, dr, none, r_begin, r_end, prow, rows,
+  stream_rows<PHASE == 1 ? 2 : 1, 1, false>(xr, dr, none, r_begin, r_end, prow, rows,
       [&](const uint4& rx, const uint4& rd, char* const (&)[1]) {
         float xv[V];
         unpack<T>(rx, xv);
@@ -401,7 +405,7 @@ gn_nhwc_apply_kernel(GnArgs a) {
   const void* addp = sel.second ? a.add1 : a.add;
   const bool has_add = PHASE == 1 && addp != nullptr;
   const RowPtr extra[2] = {orow, row_ptr<T>(addp, sel.width, sel.cc, first)};
-  stream_rows<PHASE == 1 ? 2 : 1, 2>(xr, dr, extra, r_begin, r_end, prow, rows,
+  stream_rows<PHASE == 1 ? 2 : 1, 2, false>(xr, dr, extra, r_begin, r_end, prow, rows,
       [&](const uint4& rx, const uint4& rd, char* const (&ep)[2]) {
         float xv[V], ov[V];
         unpack<T>(rx, xv);
@@ -764,6 +768,273 @@ gn_nhwc_resident_kernel(const GnResArgs r) {
   if (CLUSTER) cluster_wait();    // every peer has finished reading this CTA's partial sums
 }
 
+// ============================== channels-last, resident by channel slice ======================
+// Tensors too large for the single-wave resident kernel (the 128x128 / 256x256 maps) are cut into UNITS = (sample,
+// slice of whole groups): groups are independent, so a slice of C/cs channels is a GroupNorm problem of its own.
+// A unit is sized so that at least two units sit on the chip at once (each on its own set of SMs, one CTA per SM,
+// ~220 KB of shared memory): while one unit waits on its barrier and writes its result, the next ones are loading,
+// so HBM never idles, and -- unlike the statistics + apply pair -- x (and dy) are read exactly ONCE.  Rows of a slice
+// are not contiguous in memory (stride C), so the loads are per-thread 16-byte cp.async copies (8 lanes cover a
+// 128-byte segment); a thread only ever touches the bytes it copied itself, hence no block barriers in the hot loops.
+// Units take their index from the start-order ticket (same forward-progress argument as above); bounded spin.
+struct GnSliceArgs {
+  GnArgs a;
+  int cs;                   // slices per sample
+  int Cs;                   // channels per slice (multiple of C/G and of the vector width)
+  int nb;                   // CTAs per unit
+  int64_t rows_per_cta;
+  int chunk_passes;         // passes per cp.async commit group (4 groups)
+  unsigned int total_ctas;
+  unsigned int* ticket; unsigned int* arrive; unsigned int* done; unsigned int* err;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kSliceThreads = 256;   // 3 CTAs per SM (24 warps): the backward is within 2x of the issue limit, occupancy matters
+
+template <typename T, int MODE, int PHASE>
+__global__ void __launch_bounds__(kSliceThreads, 3)
+gn_nhwc_slice_kernel(const GnSliceArgs r) {
+  constexpr int V = VecOf<T>::N;
+  constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
+  constexpr int NSRC = PHASE == 1 ? 2 : 1;
+  const GnArgs& a = r.a;
+  extern __shared__ __align__(128) unsigned char dyn[];
+  __shared__ float4 part[kSliceThreads];
+  __shared__ double g_acc[32][2];
+  __shared__ float g_c0[32], g_c1[32];
+  __shared__ unsigned int s_lid;
+  if (threadIdx.x == 0) s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
+  __syncthreads();
+  const int unit = (int)(s_lid / (unsigned int)r.nb), blk = (int)(s_lid % (unsigned int)r.nb);
+  const int b = unit / r.cs, sl = unit % r.cs;
+  const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
+  const int cvec = r.Cs / V;                                   // vectors per row of the slice
+  const int cv = threadIdx.x % cvec, rows = blockDim.x / cvec;
+  const int c0 = sl * r.Cs + cv * V;                           // first channel of this thread (absolute)
+  const int Cg = a.C / a.G;
+  const int g_first = (sl * r.Cs) / Cg, g_count = r.Cs / Cg;   // groups of this slice
+  const int64_t r_begin = (int64_t)blk * r.rows_per_cta;
+  int64_t r_end = r_begin + r.rows_per_cta; if (r_end > a.HW) r_end = a.HW;
+  const int n_rows = r_end > r_begin ? (int)(r_end - r_begin) : 0;
+  const int64_t row_stride = (int64_t)a.C * sizeof(T);
+  const int prow = threadIdx.x / cvec;
+  const int64_t gbase = ((int64_t)b * a.HW + r_begin + prow) * row_stride + (int64_t)c0 * sizeof(T);   // this thread's first row
+  const int n_mine = n_rows > prow ? (n_rows - prow + rows - 1) / rows : 0;     // rows this thread owns: prow, prow+rows, ...
+  const unsigned pass_bytes = blockDim.x * 16u;
+  const unsigned slab = (unsigned)((((r.rows_per_cta + rows - 1) / rows) * (int64_t)pass_bytes + 127) / 128 * 128);
+  unsigned char* sx = dyn;
+  unsigned char* sd = dyn + slab;
+  const char* xg = reinterpret_cast<const char*>(a.x) + gbase;
+  const char* dg = PHASE == 1 ? reinterpret_cast<const char*>(a.dy) + gbase : nullptr;
+  const unsigned my_off = threadIdx.x * 16u;
+  // ---- issue every copy of this thread, four commit groups
+  {
+    int k = 0;
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {
+      const int k_end = (grp + 1) * r.chunk_passes < n_mine ? (grp + 1) * r.chunk_passes : n_mine;
+      for (; k < k_end; ++k) {
+        const int64_t go = (int64_t)(k * rows) * row_stride;
+        cp_async16(sx + (unsigned)k * pass_bytes + my_off, xg + go);
+        if (NSRC == 2) cp_async16(sd + (unsigned)k * pass_bytes + my_off, dg + go);
+      }
+      cp_async_commit();
+    }
+  }
+  float s0[V], s1[V], ca[V], cb[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s0[i] = 0.f; s1[i] = 0.f; ca[i] = 0.f; cb[i] = 0.f; }
+  if (PHASE == 1) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (in_bias ? in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
+      ca[i] = rstd * gam * sc * kAff;
+      cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
+    }
+  }
+  // ---- pass 1 over the landed chunks (own bytes only: no block barrier)
+  auto pass1 = [&](int k_lo, int k_hi) {
+    for (int k = k_lo; k < k_hi; ++k) {
+      const unsigned o = (unsigned)k * pass_bytes + my_off;
+      float xv[V];
+      unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+      if (PHASE == 0) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) { s0[i] += xv[i]; s1[i] = fmaf(xv[i], xv[i], s1[i]); }
+      } else {
+        float dv[V];
+        unpack<T>(*reinterpret_cast<const uint4*>(sd + o), dv);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          dv[i] = dv[i] * gn_dact_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+          s0[i] += dv[i]; s1[i] = fmaf(dv[i], xv[i], s1[i]);
+        }
+        if (MODE != NHMC_GN_PLAIN) store_vec<T>(reinterpret_cast<T*>(sd + o), dv);
+      }
+    }
+  };
+  {
+    const int cp = r.chunk_passes;
+    auto hi = [&](int g) { return (g + 1) * cp < n_mine ? (g + 1) * cp : n_mine; };
+    cp_async_wait<3>(); pass1(0, hi(0));
+    cp_async_wait<2>(); pass1(hi(0), hi(1));
+    cp_async_wait<1>(); pass1(hi(1), hi(2));
+    cp_async_wait<0>(); pass1(hi(2), n_mine);
+  }
+  if (PHASE == 0 && in_bias) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float bia = in_bias[c0 + i];
+      s1[i] = s1[i] + 2.0f * bia * s0[i] + (float)n_mine * bia * bia;
+      s0[i] = s0[i] + (float)n_mine * bia;
+    }
+  }
+  float k1[V], k2[V], k3[V];
+  if (PHASE == 1) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, g = c / Cg;
+      const float mean = a.stats[((int64_t)b * a.G + g) * 2] - (in_bias ? in_bias[c] : 0.0f);
+      const float rstd = a.stats[((int64_t)b * a.G + g) * 2 + 1];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float cgm = a.gamma[c] * sc;
+      const float t0 = s0[i], t1 = s1[i];
+      s0[i] = cgm * t0;
+      s1[i] = cgm * rstd * (t1 - mean * t0);
+      k1[i] = rstd * cgm; k2[i] = mean; k3[i] = rstd;
+    }
+  }
+  // ---- per-CTA group partials -> global fp64 accumulators -> unit barrier -> unit totals
+  {
+    const int g0 = c0 / Cg;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if ((c0 + i) / Cg == g0) { q.x += s0[i]; q.y += s1[i]; } else { q.z += s0[i]; q.w += s1[i]; }
+    }
+    part[threadIdx.x] = q;
+    __syncthreads();
+    if ((int)threadIdx.x < g_count) {
+      const int g = g_first + threadIdx.x;
+      const int cl = g * Cg - sl * r.Cs;                        // first channel of the group, slice-relative
+      const int cv_lo = cl / V, cv_hi = (cl + Cg - 1) / V;
+      double t0 = 0.0, t1 = 0.0;
+      for (int v = cv_lo; v <= cv_hi; ++v) {
+        const int j = g - (sl * r.Cs + v * V) / Cg;
+        for (int pr = 0; pr < rows; ++pr) {
+          const float4 t = part[pr * cvec + v];
+          t0 += (double)(j ? t.z : t.x); t1 += (double)(j ? t.w : t.y);
+        }
+      }
+      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
+      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
+      __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(r.arrive + unit, 1u);
+      const long long t_start = clock64();
+      while (ld_acquire_u32(r.arrive + unit) < (unsigned int)r.nb) {
+        __nanosleep(64);
+        if (clock64() - t_start > (1ll << 31)) { atomicExch(r.err, 1u); break; }
+      }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < g_count) {
+      const int g = g_first + threadIdx.x;
+      g_acc[threadIdx.x][0] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2);
+      g_acc[threadIdx.x][1] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const bool last = atomicInc(r.done + unit, (unsigned int)(r.nb - 1)) == (unsigned int)(r.nb - 1);
+      if (last) {
+        for (int g = g_first; g < g_first + g_count; ++g) { a.partials[((int64_t)b * 64 + g) * 2] = 0.0; a.partials[((int64_t)b * 64 + g) * 2 + 1] = 0.0; }
+        r.arrive[unit] = 0u;
+      }
+    }
+  }
+  const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
+  if ((int)threadIdx.x < g_count) {
+    const int gl = threadIdx.x, g = g_first + gl;
+    if (PHASE == 0) {
+      const double m = g_acc[gl][0] * inv_n;
+      double var = g_acc[gl][1] * inv_n - m * m; if (var < 0.0) var = 0.0;
+      g_c0[gl] = (float)m; g_c1[gl] = (float)(1.0 / sqrt(var + (double)a.eps));
+      if (blk == 0) {
+        a.stats[((int64_t)b * a.G + g) * 2] = g_c0[gl];
+        a.stats[((int64_t)b * a.G + g) * 2 + 1] = g_c1[gl];
+      }
+    } else {
+      g_c0[gl] = (float)(g_acc[gl][0] * inv_n); g_c1[gl] = (float)(g_acc[gl][1] * inv_n);
+    }
+  }
+  __syncthreads();
+  char* og = reinterpret_cast<char*>(a.out) + gbase;
+  if (PHASE == 0) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = c0 + i, gl = c / Cg - g_first;
+      const float mean = g_c0[gl] - (in_bias ? in_bias[c] : 0.0f), rstd = g_c1[gl];
+      const float gam = a.gamma[c], bet = a.beta[c];
+      const float sc = (MODE == NHMC_GN_FILM_SILU) ? 1.0f + a.scale[(int64_t)b * a.film_stride + c] : 1.0f;
+      const float sh = (MODE == NHMC_GN_FILM_SILU) ? a.shift[(int64_t)b * a.film_stride + c] : 0.0f;
+      ca[i] = rstd * gam * sc * kAff;
+      cb[i] = ((bet - mean * rstd * gam) * sc + sh) * kAff;
+    }
+#pragma unroll 4
+    for (int k = 0; k < n_mine; ++k) {
+      float xv[V], ov[V];
+      unpack<T>(*reinterpret_cast<const uint4*>(sx + (unsigned)k * pass_bytes + my_off), xv);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov[i] = gn_act_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
+      store_vec<T>(reinterpret_cast<T*>(og + (int64_t)(k * rows) * row_stride), ov);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int gl = (c0 + i) / Cg - g_first;
+      const float m1 = g_c0[gl], m2 = g_c1[gl], mean = k2[i], rstd = k3[i];
+      k2[i] = -rstd * rstd * m2;
+      k3[i] = -rstd * m1 + rstd * rstd * m2 * mean;
+    }
+    const char* ag = a.add ? reinterpret_cast<const char*>(a.add) + gbase : nullptr;
+    constexpr int U = 4;
+    for (int k0 = 0; k0 < n_mine; k0 += U) {
+      uint4 av[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        av[u] = make_uint4(0, 0, 0, 0);
+        if (ag && k0 + u < n_mine) av[u] = ld_raw(ag + (int64_t)((k0 + u) * rows) * row_stride);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u;
+        if (k < n_mine) {
+          const unsigned o = (unsigned)k * pass_bytes + my_off;
+          float xv[V], dv[V], ov[V], ad[V];
+          unpack<T>(*reinterpret_cast<const uint4*>(sx + o), xv);
+          unpack<T>(*reinterpret_cast<const uint4*>(sd + o), dv);
+          unpack<T>(av[u], ad);
+#pragma unroll
+          for (int i = 0; i < V; ++i) ov[i] = fmaf(k1[i], dv[i], fmaf(k2[i], xv[i], k3[i])) + ad[i];
+          store_vec<T>(reinterpret_cast<T*>(og + (int64_t)(k * rows) * row_stride), ov);
+        }
+      }
+    }
+  }
+}
+
 // ============================== NCHW =========================================================
 // One CTA per (sample, group): the group is a contiguous slab of Cg*HW elements (<= 1 MB at FFHQ-256),
 // read twice by the same CTA so the second read is an L2 hit.
@@ -995,6 +1266,84 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
   return NHMC_ERR_UNSUPPORTED;
 }
 
+static int g_slice_mode = -1;      // NHMC_GN_SLICE: 0 off (default: measured slower in situ than statistics + apply), 1 backward only, 2 backward + large forward tensors
+static int slice_mode() {
+  if (g_slice_mode < 0) { const char* e = getenv("NHMC_GN_SLICE"); g_slice_mode = e ? atoi(e) : 0; }
+  return g_slice_mode;
+}
+
+// Resident-by-channel-slice kernel for tensors that do not fit the single-wave resident kernel.  NHMC_ERR_UNSUPPORTED
+// when the shape cannot be cut into units of which at least two fit on the chip at once.
+template <typename T, int MODE, int PHASE>
+static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaStream_t st) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int NSRC = PHASE == 1 ? 2 : 1;
+  const int mode = slice_mode();
+  if (!resident_mode() || mode == 0 || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  const int64_t row_bytes = (int64_t)a0.C * sizeof(T);
+  const int64_t sample_bytes = a0.HW * row_bytes;
+  if (PHASE == 0 && (mode < 2 || (int64_t)batch * sample_bytes < ((int64_t)200 << 20))) return NHMC_ERR_UNSUPPORTED;
+  const DevInfo d = dev_info();
+  if (!d.ok) return NHMC_ERR_UNSUPPORTED;
+  auto kern = gn_nhwc_slice_kernel<T, MODE, PHASE>;
+  static int static_smem = -1;
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
+      cudaGetLastError(); return NHMC_ERR_UNSUPPORTED;
+    }
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int Cg = a0.C / a0.G;
+  for (int occ = 3; occ >= 1; --occ) {
+    int64_t dyn_limit = d.smem_sm / occ - d.smem_reserved;
+    if (dyn_limit > d.smem_optin) dyn_limit = d.smem_optin;
+    dyn_limit -= static_smem;
+    const int64_t slab_limit = (dyn_limit / NSRC) & ~(int64_t)127;
+    const int64_t slots = (int64_t)occ * d.sms;
+    for (int cs = 1; cs <= 8; cs <<= 1) {
+      if (a0.G % cs || (int64_t)batch * cs > s.batch) continue;
+      const int Cs = a0.C / cs;
+      if (Cs % Cg || Cs % V) continue;
+      const int cvec = Cs / V;
+      if (cvec > kSliceThreads) continue;
+      const int rows = kSliceThreads / cvec, threads = rows * cvec;
+      bool ok = true;
+      for (int cv = 0; cv < cvec && ok; ++cv) ok = ((cv * V + V - 1) / Cg - (cv * V) / Cg) <= 1;   // <= 2 groups per thread
+      if (!ok) continue;
+      const int64_t pass_bytes = (int64_t)threads * 16;
+      const int64_t unit_bytes = sample_bytes / cs;
+      int64_t nb = (unit_bytes + slab_limit - 1) / slab_limit;
+      if (nb < 1) nb = 1;
+      if (nb > slots / 2) continue;                                // at least two units on the chip at once
+      const int64_t U = slots / nb;
+      nb = slots / U;                                              // the resident units cover all slots
+      int64_t rows_per_cta = 0, slab = 0;
+      for (; nb <= slots / 2; ++nb) {
+        rows_per_cta = (a0.HW + nb - 1) / nb;
+        slab = (((rows_per_cta + rows - 1) / rows) * pass_bytes + 127) / 128 * 128;
+        if (slab <= slab_limit) break;
+      }
+      if (nb > slots / 2 || slab > slab_limit) continue;
+      nb = (a0.HW + rows_per_cta - 1) / rows_per_cta;
+      int got = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&got, kern, threads, (size_t)slab * NSRC) != cudaSuccess) { cudaGetLastError(); continue; }
+      if ((int64_t)got * d.sms < 2 * nb) continue;                 // two whole units must be resident
+      GnSliceArgs r{};
+      r.a = a0;
+      r.cs = cs; r.Cs = Cs; r.nb = (int)nb; r.rows_per_cta = rows_per_cta;
+      const int64_t n_pass = (rows_per_cta + rows - 1) / rows;
+      r.chunk_passes = (int)((n_pass + 3) / 4);
+      r.total_ctas = (unsigned int)(nb * batch * cs);
+      r.ticket = s.res + 2; r.err = s.res + 1; r.arrive = s.res + 4; r.done = s.res + 4 + s.batch;
+      kern<<<r.total_ctas, threads, (size_t)slab * NSRC, st>>>(r);
+      return NHMC_LAUNCH_CHECK();
+    }
+  }
+  return NHMC_ERR_UNSUPPORTED;
+}
+
 template <typename T, int MODE, int PHASE>
 static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
@@ -1003,7 +1352,9 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
   if (!a.x1) {
-    const int e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
+    int e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
+    if (e != NHMC_ERR_UNSUPPORTED) return e;
+    e = run_nhwc_slice<T, MODE, PHASE>(a, s, batch, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
   }
   // Two kernels (statistics, apply).  The grid is ONE balanced wave: (CTAs per SM the statistics kernel can keep
@@ -1170,9 +1521,10 @@ extern "C" int nhmc_gn_check(void) {
 
 extern "C" int nhmc_gn_set_resident(int on) {
   // 0: statistics + apply kernels only; 1: + resident kernel with the global per-sample barrier; 2 (default): + the
-  // thread-block-cluster variant for samples that fit in 8 CTAs
-  const int prev = resident_mode() ? (cluster_mode() ? 2 : 1) : 0;
+  // thread-block-cluster variant for samples that fit in 8 CTAs; 3 (default): + the resident-by-channel-slice kernel for large tensors
+  const int prev = resident_mode() ? (cluster_mode() ? (slice_mode() ? 3 : 2) : 1) : 0;
   g_resident_mode = on ? 1 : 0;
   g_cluster_mode = on >= 2 ? 1 : 0;
+  g_slice_mode = on >= 3 ? 2 : 0;
   return prev;
 }

@@ -16,6 +16,25 @@ def profile_start():
     _PROFILE = {}
 
 
+def profile_take():
+    """Stops recording and returns the raw {name: [(start_event, end_event, algorithmic_bytes), ...]} records WITHOUT
+    reading them (for events captured into a CUDA graph: read them with profile_read after each replay)."""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE, None
+    return prof or {}
+
+
+def profile_read(records, into, by_size=True):
+    """Accumulates the current event times of `records` into `into` ({key: (n, ms, bytes)}); synchronises."""
+    torch.cuda.synchronize()
+    for name, recs in records.items():
+        for s, e, b in recs:
+            key = (name, b) if by_size else name
+            n, ms, tot = into.get(key, (0, 0.0, 0))
+            into[key] = (n + 1, ms + s.elapsed_time(e), tot + b)
+    return into
+
+
 def profile_stop(by_size=False):
     """Returns {name: (n_calls, total_ms, total_algorithmic_bytes)} (synchronises); with by_size the key is
     (name, algorithmic_bytes_per_call), i.e. one entry per tensor shape."""
@@ -44,8 +63,11 @@ class _timed:
         global LAUNCHES
         LAUNCHES += self.n
         if _PROFILE is not None:
-            self.s = torch.cuda.Event(enable_timing=True)
-            self.e = torch.cuda.Event(enable_timing=True)
+            # inside a stream capture the events become event-record NODES of the graph (external=True): every
+            # replay re-records them, so per-kernel CUDA-event times can be read in situ after each replay
+            ext = torch.cuda.is_current_stream_capturing()
+            self.s = torch.cuda.Event(enable_timing=True, external=ext)
+            self.e = torch.cuda.Event(enable_timing=True, external=ext)
             self.s.record()
         return self
 

@@ -190,6 +190,24 @@ class HMCSampler:
         self._graphs = graphs
         return self
 
+    def capture_profiled_step(self, mode=_lib.LF_MIDDLE):
+        """One step variant captured as a CUDA graph WITH a pair of timing events around every kernel of ours
+        (event-record nodes).  Returns (graph, records): replay, then kernels.profile_read(records, acc) gives the
+        per-kernel CUDA-event times of that replay -- measured in situ (warm L2, back-to-back launches) on the
+        launching stream.  Sampler state is restored after the capture."""
+        keep = [t.clone() for t in (self.x, self.x_prop, self.p, self.chains.dev)]
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        pool = next(iter(self._graphs.values()))[0].pool() if self._graphs else None
+        kernels.profile_start()
+        with torch.cuda.graph(g, pool=pool):
+            self._step_eager(mode)
+        records = kernels.profile_take()
+        torch.cuda.synchronize()
+        for dst, src in zip((self.x, self.x_prop, self.p, self.chains.dev), keep):
+            dst.copy_(src)
+        return g, records
+
     def iteration(self, p, u):
         """One HMC iteration for every chain. p: momentum draw [B,C,H,W]; u: uniform draws [B]."""
         ev, ch, m = self.ev, self.chains, self.mass

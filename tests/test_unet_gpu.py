@@ -180,7 +180,7 @@ def test_resample_and_split_kernels(dtype):
     assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
 
 
-@pytest.mark.parametrize("resident", [2, 1, 0])
+@pytest.mark.parametrize("resident", [3, 2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("shape", [(8, 128, 128, 128), (3, 384, 64, 64), (2, 256, 256, 256), (5, 1024, 16, 16), (2, 128, 33, 7),
