@@ -134,7 +134,8 @@ def _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_fun
     out = None
     if n:
         lat = sampler.hmc_latent(z, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
-                                 max_iters=opt.max_iters, on_iteration=on_it, image_size=config.data.image_size)
+                                 max_iters=opt.max_iters, on_iteration=on_it, image_size=config.data.image_size,
+                                 reuse_gradient=opt.reuse_gradient)
         lat = [lat] if n == 1 else lat
         out = [ldm.decode_first_stage(l_).float() if l_.numel() else torch.zeros(0, 3, config.data.image_size, config.data.image_size, device=device)
                for l_ in lat]

@@ -325,7 +325,7 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
 
 
 def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-               max_iters=None, on_iteration=None, return_sampler=False, image_size=256):
+               max_iters=None, on_iteration=None, return_sampler=False, image_size=256, reuse_gradient=False):
     """Drop-in for main_sampling_latent.hmc_latent (main_sampling_latent.py:623-762).
 
     algo.model is an LDM object exposing `.apply_model(z,t,None)` (no-grad, ddpm.py:892-893),
@@ -347,7 +347,8 @@ def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum
     ev = GradEvaluator(net, steps, op, y, x.detach().float().contiguous(), net_grad=False,
                        decode=ldm.differentiable_decode_first_stage)
     smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_LATENT,
-                     sigma_y=opt.sigma_y, n_slots=10)
+                     sigma_y=opt.sigma_y, n_slots=10,
+                     reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False))
     dm, du = _default_draws(m)
     _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
     if return_sampler:

@@ -84,6 +84,10 @@ def test_hmc_teacher_forced_against_reference_trace(golden):
             if acc:
                 img = ((xc[0].cpu() + 1) / 2).clamp(0, 1)
                 np.testing.assert_allclose(img.numpy(), g["saved"][n_saved], atol=1e-3)
+                # north star: PSNR of the reconstruction against the ground truth within 0.05 dB of the reference's
+                orig = ((T(g["x_orig"])[0] + 1) / 2).clamp(0, 1)
+                psnr = lambda a: 10 * np.log10(1.0 / float(((a - orig) ** 2).mean()))
+                assert abs(psnr(img) - psnr(T(g["saved"][n_saved]))) < 0.05
                 n_img += 1
         n_saved += acc
         sch.end_iteration(acc)
