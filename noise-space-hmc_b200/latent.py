@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, kernels
-from .unet import (UNetModel, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_nobias, group_norm_act,
+from .unet import (UNetModel, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_bias, _conv_nobias, group_norm_act,
                    group_norm_act_skip)
 
 VQ_GN_EPS = 1e-6          # model.py:37-38 Normalize()
@@ -151,7 +151,7 @@ class _UpsampleConv(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(_Upsample2.apply(x))
+        return _conv_bias(self.conv, _Upsample2.apply(x))
 
 
 class Decoder(nn.Module):
@@ -187,7 +187,7 @@ class Decoder(nn.Module):
         self.conv_out = nn.Conv2d(block_in, out_ch, 3, padding=1)
 
     def forward(self, z):
-        h = self.conv_in(_cl(z))
+        h = _conv_bias(self.conv_in, _cl(z))
         h = self.mid.block_2(self.mid.attn_1(self.mid.block_1(h)))
         for i_level in reversed(range(self.num_resolutions)):
             for i_block in range(self.num_res_blocks + 1):

@@ -239,6 +239,16 @@ def _conv_nobias(conv, x):
     return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
 
 
+def _conv_bias(conv, x):
+    """conv(x) + bias with the bias added by our channels-last kernel: on large maps PyTorch adds a convolution's
+    bias as a separate broadcast TensorIterator pass at ~1.6 TB/s (324 us on the [8,256,256,256] decoder map)."""
+    b32 = getattr(conv, "_bias_f32", None)
+    if b32 is None or b32.device != conv.bias.device:
+        b32 = conv.bias.detach().float().contiguous()
+        conv._bias_f32 = b32
+    return _BiasAdd.apply(_conv_nobias(conv, x), None, b32)
+
+
 # ------------------------------------------------------------------------------------------------
 # blocks (attribute names chosen so that state_dict keys equal the reference's)
 # ------------------------------------------------------------------------------------------------
@@ -342,7 +352,7 @@ class Downsample(nn.Module):
         self.op = nn.Conv2d(channels, out_channels or channels, 3, stride=2, padding=1)
 
     def forward(self, x):
-        return self.op(x)
+        return _conv_bias(self.op, x)
 
 
 class Upsample(nn.Module):
@@ -353,7 +363,7 @@ class Upsample(nn.Module):
         self.conv = nn.Conv2d(channels, out_channels or channels, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(_Upsample2.apply(x))
+        return _conv_bias(self.conv, _Upsample2.apply(x))
 
 
 class AttentionBlock(nn.Module):
@@ -370,17 +380,18 @@ class AttentionBlock(nn.Module):
         T, nh = H * W, self.num_heads
         ch = C // nh
         xn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
-        # channels-last: [B, T, C] views without copies
-        tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)
-        qkv = F.linear(tok, self.qkv.weight[:, :, 0], self.qkv.bias)               # [B, T, 3C]
-        # legacy order (unet_ffhq.py:417): channel = head*(3*ch) + {q,k,v}*ch + c
-        qkv = qkv.view(B, T, nh, 3, ch).permute(3, 0, 2, 1, 4)                       # [3, B, nh, T, ch]
-        q, k, v = qkv[0], qkv[1], qkv[2]
-        logits = torch.matmul(q, k.transpose(-1, -2))                                # [B, nh, T, T]
+        # Every operand below is a VIEW handed to a (strided-)batched GEMM: no permute/contiguous copy anywhere.
+        tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
+        wq = self.qkv.weight[:, :, 0]
+        # qkv in the reference's own layout [B, 3C, T] (unet_ffhq.py:408-417: channel = head*(3*ch) + {q,k,v}*ch + c),
+        # so that q, k, v of all B*nh heads are plain slices with ONE batch stride
+        qkv = torch.baddbmm(self.qkv.bias.view(1, 3 * C, 1), wq.unsqueeze(0).expand(B, 3 * C, C), tok.transpose(1, 2))
+        q, k, v = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)                       # each [B*nh, ch, T]
+        logits = torch.bmm(q.transpose(1, 2), k)                                     # [B*nh, T(q), T(k)]
         probs = _ScaledSoftmax.apply(logits, 1.0 / math.sqrt(ch))
-        a = torch.matmul(probs, v)                                                   # [B, nh, T, ch]
-        a = a.permute(0, 2, 1, 3).reshape(B, T, C)                                   # channel = head*ch + c
-        h = F.linear(a, self.proj_out.weight[:, :, 0], self.proj_out.bias)
+        a = torch.bmm(v, probs.transpose(1, 2)).view(B, C, T)                        # a[b, c, t] = sum_s probs[t, s] v[c, s]
+        wp = self.proj_out.weight[:, :, 0]
+        h = torch.baddbmm(self.proj_out.bias.view(1, 1, C), a.transpose(1, 2), wp.t().unsqueeze(0).expand(B, C, C))   # [B, T, C]
         out = x.permute(0, 2, 3, 1).reshape(B, T, C) + h
         return out.view(B, H, W, C).permute(0, 3, 1, 2)
 
@@ -473,6 +484,8 @@ class UNetModel(nn.Module):
             if isinstance(m, ResBlock):
                 m._bias_cache = None
                 m._skip_split = None
+            if isinstance(m, nn.Conv2d) and hasattr(m, "_bias_f32"):
+                m._bias_f32 = None
         return r
 
     def prepare(self, device="cuda"):
