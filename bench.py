@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | inpaint_box | hdr | deblur_aniso | deblur_gauss | phase_retrieval | color")
     ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
     ap.add_argument("--workload", default="pixel", choices=["pixel", "latent"], help="pixel: --algo hmc (BASELINE config[1], the metric's configuration); latent: --algo hmc_latent on the ffhq_latent architecture (BASELINE config[4])")
+    ap.add_argument("--lanes", type=int, default=1, help="groups of chains evaluated on their own streams (parallel branches of the captured step)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -164,7 +165,7 @@ def run_ours(args, rank, world, local_rank):
         betas = torch.from_numpy(schedule.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)).float()
         steps = schedule.ddim_steps(schedule.alpha_table(betas), SEQ, SEQ_NEXT)
         ev = sampler.GradEvaluator(model, steps, op, y, x0.to(dev))
-        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
+        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL, lanes=args.lanes)
         sched_kind = _lib.SCHED_PIXEL
     else:
         from nhmc_b200 import latent
@@ -177,7 +178,8 @@ def run_ours(args, rank, world, local_rank):
         steps = schedule.ddim_steps(schedule.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev), SEQ, SEQ_NEXT)
         ev = sampler.GradEvaluator(lambda z, t: ldm.apply_model(z, t, None), steps, op, y, x0.to(dev), net_grad=False,
                                    decode=ldm.differentiable_decode_first_stage)
-        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_LATENT, sigma_y=0.5, n_slots=10)
+        smp = sampler.HMCSampler(x0.to(dev), ev, 1.0, 0.05, sigma_0, sched=_lib.SCHED_LATENT, sigma_y=0.5, n_slots=10,
+                                 lanes=args.lanes)
         sched_kind = _lib.SCHED_LATENT
     kernels.begin_iteration(smp.chains, sched_kind)                                # sigma_y for epoch 0
     smp.p.copy_(torch.randn(state_shape, generator=gen).to(dev))
@@ -335,6 +337,10 @@ def run_ours(args, rank, world, local_rank):
                             "x, dy (+ skip gradient) read + dx written) / CUDA-event time per call on the launching stream, averaged over K steps"
                             + (" (event-record nodes in a second capture of the same step, replayed right after the timed region)" if use_graphs else " of the timed region")
                             + "; traffic = dram bytes per call from the ncu --set full capture in profiles/ (null if that shape was not captured)"}
+    # every (kernel family, algorithmic bytes per call) = tensor shape of ours, in situ: where the epilogue time goes
+    by_shape = [{"kernel": nm, "algorithmic_bytes_per_call": int(nb_), "calls_per_step": n / K, "us_per_call": tms / n * 1e3,
+                 "ms_per_step": tms / K, "GBps": (tot / 1e9) / (tms / 1e3) if tms > 0 else None}
+                for (nm, nb_), (n, tms, tot) in sorted(prof_sz.items(), key=lambda kv: -kv[1][1])[:40]]
     step_ms = ms / K
     if latent_wl:   # 3 latent U-Net forwards (no VJP: eps carries no gradient) + decoder forward and VJP
         unet_tflop = B * (3 * 202.4 + 2 * 670.8) / 1e3
@@ -366,12 +372,13 @@ def run_ours(args, rank, world, local_rank):
                                 "FFHQ-256 %s HMC, %d chains per GPU, timesteps=3 tau=1.0 epsilon=0.05 sigma_0=0.05, "
                                 "random-init ffhq_10m U-Net (BASELINE config[1])") % (args.deg, B),
                    "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
-                   "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs},
+                   "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs,
+                   "lanes": smp.n_lanes},
         "e2e": e2e,
         # kernels of libnhmc.so launched inside the timed region: exact CUPTI count of one replayed step x K x ranks when the
         # in-situ pass ran, else the python-side count of the C calls (which counts a two-kernel GroupNorm call once)
         "gpu_launches": int(in_situ["ours_launches_per_step"] * K * world) if in_situ else int(launches), "clocks": clk,
-        "roofline": roofline, "kernels": kern, "in_situ": in_situ,
+        "roofline": roofline, "kernels": kern, "kernels_by_shape": by_shape, "in_situ": in_situ,
         "shares": shares,
         "unet": unet_rep,
         "finite": finite,

@@ -275,6 +275,11 @@ int nhmc_gn_check(void);
  * channel-slice kernel for tensors beyond one wave (units of whole groups, >= 2 units on the chip at
  * once, x and dy read once).  Returns the previous setting.  For A/B measurements and tests. */
 int nhmc_gn_set_resident(int on);
+/* Lanes: a host that evaluates groups of chains on n_lanes streams at once (the reference evaluates one chain at a
+ * time, main_sampling.py:704-713; chains are independent) announces which lane the GroupNorm calls that follow
+ * belong to.  Every lane owns its accumulators / tickets, and the single-wave resident kernel sizes itself for
+ * 1/n_lanes of the chip.  Default (0, 1).  At most 8 lanes. */
+int nhmc_gn_set_lane(int lane, int n_lanes);
 
 /* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of
  * logits [rows, T] (dtype f32/bf16/f16), computed in fp32; logits are multiplied by

@@ -40,6 +40,10 @@ class ChainState:
     def ptr(self):
         return self.dev.data_ptr()
 
+    def view(self, start, n):
+        """Chains [start, start + n) of this array as an object the kernel wrappers accept (ptr(), n)."""
+        return _ChainView(self, start, n)
+
     def read(self):
         """Host copy (synchronises)."""
         return self.dev.cpu().numpy().reshape(-1).view(CHAIN_DTYPE).copy()
@@ -47,3 +51,12 @@ class ChainState:
     def write(self, host_state):
         raw = torch.from_numpy(host_state.view(np.uint8).reshape(self.n, CHAIN_DTYPE.itemsize).copy())
         self.dev.copy_(raw)
+
+
+class _ChainView:
+    def __init__(self, parent, start, n):
+        assert 0 <= start and start + n <= parent.n
+        self.parent, self.start, self.n = parent, start, n
+
+    def ptr(self):
+        return self.parent.dev.data_ptr() + self.start * CHAIN_DTYPE.itemsize

@@ -1110,13 +1110,18 @@ gn_nchw_kernel(GnArgs a) {
 // self-resetting, and keeping it here spares every caller a workspace argument on the hottest
 // U-Net path.  (The header's "library allocates nothing" covers tensors; this is documented there.)
 struct GnScratch { double* partials; unsigned int* tickets; float* bstats; unsigned int* res; int batch; };  // res: [ticket, err, pad, pad, arrive[nb], done[nb]]
-static GnScratch g_scratch[16] = {};
+// Lanes: a host that evaluates groups of chains on several streams at once (nhmc_gn_set_lane) gets one scratch set per
+// lane, so concurrent launches never share accumulators / tickets, and the single-wave resident kernel budgets
+// 1/n_lanes of the chip for itself.
+constexpr int kMaxLanes = 8;
+static GnScratch g_scratch[16][kMaxLanes] = {};
+static int g_lane = 0, g_lanes = 1;
 
 static int get_scratch(int batch, int G, GnScratch& out) {
   int dev = 0;
   if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
   if (dev < 0 || dev >= 16) { set_error("device index %d out of range", dev); return NHMC_ERR_ARG; }
-  GnScratch& s = g_scratch[dev];
+  GnScratch& s = g_scratch[dev][g_lane];
   if (s.batch < batch || !s.partials) {
     // grow-only; allocation happens outside any stream capture (first call) -- warm up before capturing
     if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); cudaFree(s.res); }
@@ -1240,7 +1245,8 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     dyn_limit -= static_smem;
     const int64_t slab_limit = (dyn_limit / NSRC) & ~(int64_t)127;
     if (slab_limit < row_bytes) continue;
-    int64_t nb = ((int64_t)k * d.sms) / batch;                    // CTAs per sample that keep the launch in one wave
+    const int64_t slots = ((int64_t)k * d.sms) / g_lanes;         // this lane's share of the chip
+    int64_t nb = slots / batch;                                   // CTAs per sample that keep the launch in one wave
     if (nb < 1) continue;
     int64_t rows_per_cta = (a0.HW + nb - 1) / nb;
     if (rows_per_cta * row_bytes < 8192) rows_per_cta = (8192 + row_bytes - 1) / row_bytes;   // never below 8 KiB per CTA
@@ -1251,7 +1257,7 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     const size_t dyn = (size_t)slab * NSRC;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, dyn) != cudaSuccess) { cudaGetLastError(); continue; }
-    if ((int64_t)occ * d.sms < nb * batch) continue;
+    if (((int64_t)occ * d.sms) / g_lanes < nb * batch) continue;
     GnResArgs r{};
     r.a = a0;
     r.a.rows_per_cta = rows_per_cta;
@@ -1512,10 +1518,20 @@ extern "C" int nhmc_gn_check(void) {
   // 0 = no wait of the resident GroupNorm path ever timed out on the current device (synchronises)
   int dev = 0;
   if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
-  if (dev < 0 || dev >= 16 || !g_scratch[dev].res) return NHMC_OK;
-  unsigned int flag = 0;
-  if (int e = cuda_status(cudaMemcpy(&flag, g_scratch[dev].res + 1, sizeof(flag), cudaMemcpyDeviceToHost), "gn check")) return e;
-  if (flag) { set_error("resident GroupNorm: a per-sample barrier timed out (results of that call are invalid)"); return NHMC_ERR_CUDA; }
+  if (dev < 0 || dev >= 16) return NHMC_OK;
+  for (int lane = 0; lane < kMaxLanes; ++lane) {
+    if (!g_scratch[dev][lane].res) continue;
+    unsigned int flag = 0;
+    if (int e = cuda_status(cudaMemcpy(&flag, g_scratch[dev][lane].res + 1, sizeof(flag), cudaMemcpyDeviceToHost), "gn check")) return e;
+    if (flag) { set_error("resident GroupNorm: a per-sample barrier timed out (results of that call are invalid)"); return NHMC_ERR_CUDA; }
+  }
+  return NHMC_OK;
+}
+
+extern "C" int nhmc_gn_set_lane(int lane, int n_lanes) {
+  // The GroupNorm calls that follow (from any host thread) belong to `lane` of `n_lanes` concurrently running streams.
+  NHMC_CHECK_ARG(n_lanes >= 1 && n_lanes <= kMaxLanes && lane >= 0 && lane < n_lanes, "lane out of range (at most 8 lanes)");
+  g_lane = lane; g_lanes = n_lanes;
   return NHMC_OK;
 }
 

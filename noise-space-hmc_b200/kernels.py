@@ -78,6 +78,17 @@ class _timed:
         return False
 
 
+LANE = 0             # lane (group of chains evaluated on its own stream) the calls that follow belong to
+
+
+def set_lane(lane, n_lanes):
+    """Announce that the calls that follow run on lane `lane` of `n_lanes` concurrent streams: per-lane GroupNorm
+    scratch in the library, per-lane operator workspaces here."""
+    global LANE
+    check(lib().nhmc_gn_set_lane(int(lane), int(n_lanes)), "nhmc_gn_set_lane")
+    LANE = int(lane)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 

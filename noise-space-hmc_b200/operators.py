@@ -45,9 +45,10 @@ class Operator:
         return (B, self.meas_size())
 
     def _workspace(self, B):
-        if B not in self._ws:
-            self._ws[B] = kernels.zeros_workspace(lib().nhmc_op_workspace_bytes(ctypes.byref(self.desc), B), self.device)
-        return self._ws[B]
+        key = (B, kernels.LANE)       # lanes run concurrently: never share reduction scratch between them
+        if key not in self._ws:
+            self._ws[key] = kernels.zeros_workspace(lib().nhmc_op_workspace_bytes(ctypes.byref(self.desc), B), self.device)
+        return self._ws[key]
 
     def _img(self, vec):
         B = vec.shape[0]

@@ -49,6 +49,26 @@ class GradEvaluator:
         self.n_net_fwd = 0
         self.n_net_vjp = 0
 
+    def split(self, bounds):
+        """Evaluators for the chain groups [bounds[i], bounds[i+1]): same model / operator / schedule, every buffer a
+        VIEW of this evaluator's (chains are contiguous along dim 0), so `loss`, `xc`, `g_hat` stay whole-batch tensors
+        for the accept / commit kernels.  Chains are independent, so groups can run on separate streams."""
+        subs = []
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            e = object.__new__(GradEvaluator)
+            e.model, e.steps, e.op, e.net_grad, e.decode = self.model, self.steps, self.op, self.net_grad, self.decode
+            e.y = self.y[lo:hi]
+            e.B, e.N = hi - lo, self.N
+            e.t = [t[lo:hi] for t in self.t]
+            e.xt = [t[lo:hi] for t in self.xt]
+            e.mask = [t[lo:hi] for t in self.mask]
+            e.gxt = [t[lo:hi] for t in self.gxt]
+            e.g_hat, e.xc, e.loss = self.g_hat[lo:hi], self.xc[lo:hi], self.loss[lo:hi]
+            e.g_eps = None
+            e.n_net_fwd = e.n_net_vjp = 0
+            subs.append(e)
+        return subs
+
     def _net(self, x_in, k):
         if self.net_grad:
             xk = x_in.detach().requires_grad_(True)
@@ -116,8 +136,13 @@ class HMCSampler:
     """State + one-iteration stepper shared by hmc() and hmc_latent()."""
 
     def __init__(self, x, evaluator, tau, epsilon, sigma_0, mass=1.0, sched=_lib.SCHED_PIXEL, sigma_y=None,
-                 n_slots=20, reuse_gradient=False):
-        """reuse_gradient (opt-in): keep (loss, gradient) of the current state per chain instead
+                 n_slots=20, reuse_gradient=False, lanes=1):
+        """lanes > 1: the chains are cut into that many contiguous groups, each evaluated (score network, epilogues,
+        operator, VJP, leapfrog kernel) on its own stream; in a captured step the groups are parallel branches of the
+        graph, so one group's bandwidth-bound / latency-bound kernels overlap the other's convolutions.  Per-chain
+        results do not depend on the grouping (no quantity couples two chains).
+
+        reuse_gradient (opt-in): keep (loss, gradient) of the current state per chain instead
         of re-evaluating them at the top of every iteration (main_sampling.py:693-695): 20 instead of 21 gradient
         evaluations per iteration, same values (the reference recomputes exactly what it already had)."""
         self.ev = evaluator
@@ -139,14 +164,42 @@ class HMCSampler:
         self.g_state = torch.zeros_like(self.x) if self.reuse_gradient else None
         self.loss_state = torch.zeros(self.B, dtype=torch.float64, device=dev) if self.reuse_gradient else None
         self._state_valid = False    # (loss_state, g_state) hold the values at self.x
-        self._last = {}              # mode -> (g_a, g_b) of that step variant's evaluation (static buffers under graphs)
+        self._last = {}              # mode -> [(lo, hi, g_a, g_b)] of that step variant's evaluation (static buffers under graphs)
+        self.n_lanes = max(1, min(int(lanes), self.B, 8))
+        self.lanes = None
+        if self.n_lanes > 1:
+            bounds = [(i * self.B) // self.n_lanes for i in range(self.n_lanes + 1)]
+            self.lanes = [dict(idx=i, lo=lo, hi=hi, ev=e, chains=self.chains.view(lo, hi - lo),
+                               ws=kernels.leapfrog_workspace(hi - lo, dev), stream=torch.cuda.Stream(device=dev))
+                          for i, (lo, hi, e) in enumerate(zip(bounds[:-1], bounds[1:], evaluator.split(bounds)))]
 
     # ---- one gradient evaluation + leapfrog kernel, eager or as a replayed CUDA graph -------------------
     def _step_eager(self, mode):
         src = self.x if mode == _lib.LF_FIRST else self.x_prop
-        loss, g_a, g_b, _ = self.ev(src)
-        self._last[mode] = (g_a, g_b)
-        kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
+        if self.lanes is None:
+            loss, g_a, g_b, _ = self.ev(src)
+            self._last[mode] = [(0, self.B, g_a, g_b)]
+            kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
+            return
+        cur = torch.cuda.current_stream()
+        last = []
+        try:
+            for ln in self.lanes:                       # fork: every group on its own stream
+                lo, hi = ln["lo"], ln["hi"]
+                ln["stream"].wait_stream(cur)
+                kernels.set_lane(ln["idx"], self.n_lanes)
+                with torch.cuda.stream(ln["stream"]):
+                    loss, g_a, g_b, _ = ln["ev"](src[lo:hi])
+                    kernels.leapfrog(mode, src[lo:hi], self.x_prop[lo:hi], self.p[lo:hi], g_a, g_b, loss, ln["chains"],
+                                     self.mass, ln["ws"])
+                last.append((lo, hi, g_a, g_b))
+            for ln in self.lanes:                       # join
+                cur.wait_stream(ln["stream"])
+        finally:
+            kernels.set_lane(0, 1)
+        self._last[mode] = last
+        self.ev.n_net_fwd = sum(ln["ev"].n_net_fwd for ln in self.lanes) // self.n_lanes
+        self.ev.n_net_vjp = sum(ln["ev"].n_net_vjp for ln in self.lanes) // self.n_lanes
 
     def _first_from_state(self):
         """FIRST step without a gradient evaluation: energies, half kick and first drift from the kept (loss, g)."""
@@ -218,8 +271,8 @@ class HMCSampler:
         else:
             self.step(_lib.LF_FIRST)                                             # main_sampling.py:693-702,706
             if self.reuse_gradient:   # first iteration: every chain's state values come from this evaluation
-                g_a, g_b = self._last[_lib.LF_FIRST]
-                torch.add(g_a, g_b, out=self.g_state) if g_b is not None else self.g_state.copy_(g_a)
+                for lo, hi, g_a, g_b in self._last[_lib.LF_FIRST]:
+                    torch.add(g_a, g_b, out=self.g_state[lo:hi]) if g_b is not None else self.g_state[lo:hi].copy_(g_a)
                 self.loss_state.copy_(ev.loss)
                 self._state_valid = True
         for l in range(self.L):                                                  # main_sampling.py:704-715
@@ -230,8 +283,8 @@ class HMCSampler:
         kernels.accept(ch, self.u_dev, m, self.sched, self.n_slots)              # main_sampling.py:717-749
         kernels.commit(ch, self.x, self.x_prop, xc, self.x_keep, self.samples, self.sched, self.n_slots)
         if self.reuse_gradient:
-            g_a, g_b = self._last[_lib.LF_LAST]                                  # evaluation at the proposal
-            kernels.commit_grad(ch, self.g_state, g_a, g_b, self.loss_state, ev.loss)
+            for lo, hi, g_a, g_b in self._last[_lib.LF_LAST]:                    # evaluation at the proposal
+                kernels.commit_grad(ch.view(lo, hi - lo), self.g_state[lo:hi], g_a, g_b, self.loss_state[lo:hi], ev.loss[lo:hi])
         return xc
 
     def leapfrog_step_host(self, x_host, p_host):
@@ -292,7 +345,7 @@ def _model_of(algo):
 
 
 def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False, reuse_gradient=False):
+        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False, reuse_gradient=False, lanes=1):
     """Drop-in for main_sampling.hmc (main_sampling.py:660-774).
 
     x: [B,3,H,W] initial noise; b: fp32 betas [1000]; seq/seq_next: timestep lists; algo: object with
@@ -313,7 +366,8 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
     m = float(getattr(opt, "m", 1.0))
     ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
     smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20,
-                     reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False))
+                     reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False),
+                     lanes=max(int(lanes), int(getattr(opt, "lanes", 1) or 1)))
     if cuda_graphs or getattr(opt, "cuda_graphs", False):
         smp.capture_graphs()
     dm, du = _default_draws(m)

@@ -149,6 +149,47 @@ def test_hmc_batched_chains_equal_single_chains(golden):
         np.testing.assert_allclose(st1["H"][0], stb["H"][b], rtol=1e-5)
 
 
+@pytest.mark.parametrize("lanes,graphs,reuse", [(2, False, False), (3, True, False), (2, True, True)])
+def test_lanes_groups_on_streams_equal_groups_run_alone(golden, lanes, graphs, reuse):
+    """lanes > 1 evaluates contiguous groups of chains on their own streams (parallel branches of the captured step).
+    Per-chain results do not depend on the grouping (no cross-chain coupling): every group must equal
+    the same chains run alone as one single-lane batch (identical batch composition, hence identical library kernels;
+    what is left is last-bit nondeterminism amplified by the chaotic leapfrog map)."""
+    from nhmc_b200 import _lib, kernels, sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
+    B, n_it = 5, 2
+    gen = torch.Generator().manual_seed(33)
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
+    ps = [torch.randn(B, 3, 32, 32, generator=gen) for _ in range(n_it)]
+    us = [torch.tensor([0.0 if (i + b) % 2 == 0 else 0.9999 for b in range(B)]) for i in range(n_it)]
+
+    def run(sl, n_lanes, use_graphs):
+        ev = sampler.GradEvaluator(net, steps, op, y[sl].cuda(), x[sl].cuda())
+        smp = sampler.HMCSampler(x[sl].cuda(), ev, 1.0, 0.05, 0.1, sched=_lib.SCHED_PIXEL, lanes=n_lanes, reuse_gradient=reuse)
+        assert smp.n_lanes == n_lanes
+        if use_graphs:
+            smp.capture_graphs()
+        hist = []
+        for p, u in zip(ps, us):
+            smp.iteration(p[sl].cuda(), u[sl])
+            hist.append(smp.chains.read()["accept"].copy())
+        kernels.gn_check()
+        return smp.x.cpu(), smp.chains.read(), np.stack(hist), ev.loss.cpu()
+
+    xb, stb, hb, lb = run(slice(0, B), lanes, graphs)
+    assert 0 < hb.sum() < hb.size, "the draws should produce both accepts and rejects"
+    bounds = [(i * B) // lanes for i in range(lanes + 1)]
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        xa, sta, ha, la = run(slice(lo, hi), 1, False)
+        assert np.array_equal(ha, hb[:, lo:hi])
+        assert np.array_equal(sta["epoch"], stb["epoch"][lo:hi]) and np.array_equal(sta["epsilon"], stb["epsilon"][lo:hi])
+        np.testing.assert_allclose(xb[lo:hi].numpy(), xa.numpy(), atol=3e-3)
+        np.testing.assert_allclose(stb["H"][lo:hi], sta["H"], rtol=3e-4)
+        np.testing.assert_allclose(lb[lo:hi].numpy(), la.numpy(), rtol=1e-3)
+
+
 def test_reuse_gradient_skips_evaluation_zero_with_identical_results(golden):
     """keeping (loss, gradient) of the current state gives the same chain with 20 instead of 21
     network evaluations per iteration (mixed accepts / rejects across a batch of chains, eager and graph replay)."""
