@@ -275,6 +275,9 @@ int nhmc_gn_check(void);
  * channel-slice kernel for tensors beyond one wave (units of whole groups, >= 2 units on the chip at
  * once, x and dy read once).  Returns the previous setting.  For A/B measurements and tests. */
 int nhmc_gn_set_resident(int on);
+/* 1 (default): maps whose (sample, slice of whole groups) units fit one CTA's shared memory (8x8 .. 64x64 at
+ * FFHQ-256) take the one-CTA-per-unit kernel (no inter-CTA barrier); 0: never.  Returns the previous setting. */
+int nhmc_gn_set_solo(int on);
 /* Lanes: a host that evaluates groups of chains on n_lanes streams at once (the reference evaluates one chain at a
  * time, main_sampling.py:704-713; chains are independent) announces which lane the GroupNorm calls that follow
  * belong to.  Every lane owns its accumulators / tickets, and the single-wave resident kernel sizes itself for

@@ -796,7 +796,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 
 constexpr int kSliceThreads = 256;   // 3 CTAs per SM (24 warps): the backward is within 2x of the issue limit, occupancy matters
 
-template <typename T, int MODE, int PHASE>
+// SOLO: every unit fits ONE CTA (nb == 1, the 8x8 .. 64x64 maps): no ticket, no global accumulators, no barrier --
+// the unit index is the block index and the group totals never leave shared memory, so launches of any number of
+// waves are safe and a call is one short dependency chain (load -> reduce -> normalise -> store).
+template <typename T, int MODE, int PHASE, bool SOLO = false>
 __global__ void __launch_bounds__(kSliceThreads, 3)
 gn_nhwc_slice_kernel(const GnSliceArgs r) {
   constexpr int V = VecOf<T>::N;
@@ -808,9 +811,12 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
   __shared__ double g_acc[32][2];
   __shared__ float g_c0[32], g_c1[32];
   __shared__ unsigned int s_lid;
-  if (threadIdx.x == 0) s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
-  __syncthreads();
-  const int unit = (int)(s_lid / (unsigned int)r.nb), blk = (int)(s_lid % (unsigned int)r.nb);
+  if (!SOLO) {
+    if (threadIdx.x == 0) s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
+    __syncthreads();
+  }
+  const int unit = SOLO ? (int)blockIdx.x : (int)(s_lid / (unsigned int)r.nb);
+  const int blk = SOLO ? 0 : (int)(s_lid % (unsigned int)r.nb);
   const int b = unit / r.cs, sl = unit % r.cs;
   const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int cvec = r.Cs / V;                                   // vectors per row of the slice
@@ -936,11 +942,16 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
           t0 += (double)(j ? t.z : t.x); t1 += (double)(j ? t.w : t.y);
         }
       }
-      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
-      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
-      __threadfence();
+      if (SOLO) {
+        g_acc[threadIdx.x][0] = t0; g_acc[threadIdx.x][1] = t1;
+      } else {
+        atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
+        atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
+        __threadfence();
+      }
     }
     __syncthreads();
+    if (!SOLO) {
     if (threadIdx.x == 0) {
       atomicAdd(r.arrive + unit, 1u);
       const long long t_start = clock64();
@@ -962,6 +973,7 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
         for (int g = g_first; g < g_first + g_count; ++g) { a.partials[((int64_t)b * 64 + g) * 2] = 0.0; a.partials[((int64_t)b * 64 + g) * 2 + 1] = 0.0; }
         r.arrive[unit] = 0u;
       }
+    }
     }
   }
   const double inv_n = 1.0 / ((double)Cg * (double)a.HW);
@@ -1350,6 +1362,70 @@ static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaS
   return NHMC_ERR_UNSUPPORTED;
 }
 
+static int g_solo_mode = -1;       // NHMC_GN_SOLO=0 / nhmc_gn_set_solo(0): never take the one-CTA-per-unit kernel (A/B measurements, tests)
+static int solo_mode() {
+  if (g_solo_mode < 0) { const char* e = getenv("NHMC_GN_SOLO"); g_solo_mode = (e && e[0] == '0') ? 0 : 1; }
+  return g_solo_mode;
+}
+
+// One CTA per (sample, slice of whole groups) with the unit resident in shared memory: the small maps (8x8 .. 64x64),
+// where a call is bound by its dependency chain, not by bandwidth.  Picks the WIDEST slice (longest contiguous run per
+// pixel) that still yields >= ~one CTA per SM and whose unit fits 1/3 of an SM's shared memory (3 CTAs per SM overlap
+// each other's load / reduce / store phases); NHMC_ERR_UNSUPPORTED otherwise.
+template <typename T, int MODE, int PHASE>
+static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
+  constexpr int V = VecOf<T>::N;
+  constexpr int NSRC = PHASE == 1 ? 2 : 1;
+  if (!solo_mode() || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  const DevInfo d = dev_info();
+  if (!d.ok) return NHMC_ERR_UNSUPPORTED;
+  auto kern = gn_nhwc_slice_kernel<T, MODE, PHASE, true>;
+  static int static_smem = -1;
+  if (static_smem < 0) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes) != cudaSuccess) {
+      cudaGetLastError(); return NHMC_ERR_UNSUPPORTED;
+    }
+    static_smem = (int)fa.sharedSizeBytes;
+  }
+  const int Cg = a0.C / a0.G;
+  const int64_t budget = (d.smem_sm / 3 - d.smem_reserved - static_smem) & ~(int64_t)127;    // 3 CTAs per SM (~70 KiB)
+  int best_cs = 0, best_threads = 0; int64_t best_slab = 0;
+  for (int cs = 1; cs <= a0.G; cs <<= 1) {
+    if (a0.G % cs) continue;
+    const int Cs = a0.C / cs;
+    if (Cs % Cg || Cs % V) continue;
+    const int cvec = Cs / V;
+    if (cvec > kSliceThreads) continue;
+    bool ok = true;
+    for (int cv = 0; cv < cvec && ok; ++cv) ok = ((cv * V + V - 1) / Cg - (cv * V) / Cg) <= 1;   // <= 2 groups per thread
+    if (!ok) continue;
+    int rows = kSliceThreads / cvec;
+    if (rows > a0.HW) rows = (int)a0.HW;
+    const int threads = rows * cvec;
+    const int64_t n_pass = (a0.HW + rows - 1) / rows;
+    const int64_t slab = ((n_pass * threads * 16 + 127) / 128) * 128;
+    if (slab * NSRC > budget) continue;
+    // measured (tools/kernel_microbench.py --small --warm --graph-calls 20, SOLO on/off): the one-CTA kernel wins while a
+    // unit is <= 64 KiB AND a pixel's run is at least one 32-byte sector; with narrower runs only for tiny units
+    const int64_t unit_bytes = slab * NSRC, run_bytes = (int64_t)Cs * sizeof(T);
+    if (!(unit_bytes <= 8192 || (unit_bytes <= 65536 && run_bytes >= 32))) continue;
+    best_cs = cs; best_threads = threads; best_slab = slab;
+    if ((int64_t)batch * cs >= (int64_t)d.sms - 20) break;           // enough CTAs: keep the widest such slice
+  }
+  if (!best_cs) return NHMC_ERR_UNSUPPORTED;
+  GnSliceArgs r{};
+  r.a = a0;
+  r.cs = best_cs; r.Cs = a0.C / best_cs; r.nb = 1; r.rows_per_cta = a0.HW;
+  const int rows = best_threads / (r.Cs / V);
+  const int64_t n_pass = (a0.HW + rows - 1) / rows;
+  r.chunk_passes = (int)((n_pass + 3) / 4);
+  r.total_ctas = (unsigned int)(batch * best_cs);
+  kern<<<r.total_ctas, best_threads, (size_t)best_slab * NSRC, st>>>(r);
+  return NHMC_LAUNCH_CHECK();
+}
+
 template <typename T, int MODE, int PHASE>
 static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
@@ -1358,7 +1434,9 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
   if (!a.x1) {
-    int e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
+    int e = run_nhwc_solo<T, MODE, PHASE>(a, batch, st);
+    if (e != NHMC_ERR_UNSUPPORTED) return e;
+    e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
     e = run_nhwc_slice<T, MODE, PHASE>(a, s, batch, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
@@ -1526,6 +1604,12 @@ extern "C" int nhmc_gn_check(void) {
     if (flag) { set_error("resident GroupNorm: a per-sample barrier timed out (results of that call are invalid)"); return NHMC_ERR_CUDA; }
   }
   return NHMC_OK;
+}
+
+extern "C" int nhmc_gn_set_solo(int on) {
+  const int prev = solo_mode();
+  g_solo_mode = on ? 1 : 0;
+  return prev;
 }
 
 extern "C" int nhmc_gn_set_lane(int lane, int n_lanes) {

@@ -180,15 +180,16 @@ def test_resample_and_split_kernels(dtype):
     assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
 
 
-@pytest.mark.parametrize("resident", [3, 2, 1, 0])
+@pytest.mark.parametrize("resident", [4, 3, 2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("shape", [(8, 128, 128, 128), (3, 384, 64, 64), (2, 256, 256, 256), (5, 1024, 16, 16), (2, 128, 33, 7),
-                                   (8, 512, 8, 8), (2, 224, 32, 32)])
+                                   (8, 512, 8, 8), (2, 224, 32, 32), (8, 768, 16, 16), (8, 256, 64, 64)])
 def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
-    """Channels-last GroupNorm on both execution paths (shared-memory resident single kernel / statistics + apply
-    kernels): samples spanning many CTAs, a sample filling the whole chip, ragged pixel counts, the folded conv
-    bias and the fused skip-gradient add; repeated calls check that the self-resetting counters reset."""
+    """Channels-last GroupNorm on every execution path (4 = default: one-CTA-per-unit kernel for the small maps first;
+    3..1 = shared-memory resident kernels; 0 = statistics + apply kernels): samples spanning many CTAs, a sample filling
+    the whole chip, ragged pixel counts, 24-channel groups, the folded conv bias and the fused skip-gradient add;
+    repeated calls check that the self-resetting counters reset."""
     from nhmc_b200 import kernels, _lib
     B, C, H, W = shape
     if dtype == torch.float32 and B * C * H * W > 2 ** 25:
@@ -206,7 +207,8 @@ def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
     yr = _gn_ref(xr + bias[None, :, None, None], gamma, beta, scale, shift, mode)
     (dxr,) = torch.autograd.grad(yr, xr, dy.float())
     dxr = dxr + add.float()
-    prev = _lib.lib().nhmc_gn_set_resident(resident)
+    prev = _lib.lib().nhmc_gn_set_resident(min(resident, 3))
+    prev_solo = _lib.lib().nhmc_gn_set_solo(1 if resident == 4 else 0)
     try:
         for rep in range(3):
             y = torch.empty_like(x); dx = torch.empty_like(x); stats = torch.empty(B, 32, 2, device="cuda")
@@ -223,6 +225,7 @@ def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
             assert float((dd - tol["atol"] * float(dxr.abs().max()) - tol["rtol"] * dxr.abs()).max()) <= 0, (rep, float(dd.max()))
     finally:
         _lib.lib().nhmc_gn_set_resident(prev)
+        _lib.lib().nhmc_gn_set_solo(prev_solo)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

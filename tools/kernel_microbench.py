@@ -25,12 +25,25 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.isfile(p) else 6650.0
 
 
+GRAPH_CALLS = 1
+
+
 def timeit(fn, reps, flush=None):
     """Median CUDA-event time of fn() with a cold, CLEAN L2: the flush buffer (> L2) is written, then read back,
     so that the timed kernel neither hits in L2 nor pays for the write-back of the flush's dirty lines."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    if GRAPH_CALLS > 1:
+        # back-to-back launches replayed from a CUDA graph (as inside the captured sampler step): per-call device time
+        # without host launch gaps
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(GRAPH_CALLS):
+                fn()
+        one = fn
+        fn = g.replay
+        fn(); torch.cuda.synchronize()
     ms = []
     for _ in range(reps):
         if flush is not None:
@@ -41,7 +54,7 @@ def timeit(fn, reps, flush=None):
         torch.cuda.synchronize()
         ms.append(s.elapsed_time(e))
     ms.sort()
-    return ms[len(ms) // 2]
+    return ms[len(ms) // 2] / max(GRAPH_CALLS, 1)
 
 
 def report(name, shape, nbytes, ms, pk):
@@ -57,15 +70,25 @@ def main():
     ap.add_argument("--chains", type=int, default=64)
     ap.add_argument("--shape", default="", help="GroupNorm: only this B,C,H (e.g. 8,128,256)")
     ap.add_argument("--resident", type=int, default=1, help="GroupNorm: 1 = shared-memory resident single kernel, 0 = statistics + apply kernels")
+    ap.add_argument("--solo", type=int, default=1, help="GroupNorm: 1 = one-CTA-per-unit kernel for the small maps (default), 0 = off")
+    ap.add_argument("--warm", action="store_true", help="no L2 flush between repetitions (inputs L2-resident, as inside the U-Net for the small maps)")
+    ap.add_argument("--small", action="store_true", help="GroupNorm: the small-map shapes of the ffhq_10m U-Net at 8 chains")
+    ap.add_argument("--graph-calls", type=int, default=1, help="time this many back-to-back calls replayed from one CUDA graph (per-call time reported)")
     a = ap.parse_args()
+    global GRAPH_CALLS
+    GRAPH_CALLS = a.graph_calls
     pk = peak()
     dev = torch.device("cuda")
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    flush = None if a.warm else torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     want = lambda k: (not a.only) or a.only in k
     _lib.lib().nhmc_gn_set_resident(a.resident)
+    _lib.lib().nhmc_gn_set_solo(a.solo)
 
     if want("gn"):
         shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]
+        if a.small:
+            shapes = [(8, 512, 8), (8, 1024, 8), (8, 256, 16), (8, 512, 16), (8, 768, 16), (8, 1024, 16), (8, 256, 32), (8, 512, 32),
+                      (8, 768, 32), (8, 128, 64), (8, 256, 64), (1, 512, 8), (1, 256, 32)]
         if a.shape:
             shapes = [tuple(int(v) for v in a.shape.split(","))]
         for (B, C, H) in shapes:
@@ -76,7 +99,7 @@ def main():
                 sc = torch.zeros(B, C, device=dev); sh = torch.zeros(B, C, device=dev)
                 stats = torch.empty(B, 32, 2, device=dev)
                 nb = x.numel() * x.element_size()
-                for mode, nm in ((_lib.GN_SILU, "silu"), (_lib.GN_FILM_SILU, "film")):
+                for mode, nm in ((_lib.GN_SILU, "silu"),) if a.small else ((_lib.GN_SILU, "silu"), (_lib.GN_FILM_SILU, "film")):
                     s_, h_ = (sc, sh) if mode == _lib.GN_FILM_SILU else (None, None)
                     ms = timeit(lambda: kernels.gn_fwd(mode, x, y, gamma, beta, s_, h_, stats, 32, 1e-5, True), a.reps, flush)
                     report("gn_fwd_" + nm, [B, C, H, H], 2 * nb, ms, pk)
