@@ -185,9 +185,9 @@ def test_lanes_groups_on_streams_equal_groups_run_alone(golden, lanes, graphs, r
         xa, sta, ha, la = run(slice(lo, hi), 1, False)
         assert np.array_equal(ha, hb[:, lo:hi])
         assert np.array_equal(sta["epoch"], stb["epoch"][lo:hi]) and np.array_equal(sta["epsilon"], stb["epsilon"][lo:hi])
-        np.testing.assert_allclose(xb[lo:hi].numpy(), xa.numpy(), atol=3e-3)
-        np.testing.assert_allclose(stb["H"][lo:hi], sta["H"], rtol=3e-4)
-        np.testing.assert_allclose(lb[lo:hi].numpy(), la.numpy(), rtol=1e-3)
+        np.testing.assert_allclose(xb[lo:hi].numpy(), xa.numpy(), atol=5e-3)
+        np.testing.assert_allclose(stb["H"][lo:hi], sta["H"], rtol=2e-3)
+        np.testing.assert_allclose(lb[lo:hi].numpy(), la.numpy(), rtol=5e-3)
 
 
 def test_reuse_gradient_skips_evaluation_zero_with_identical_results(golden):
@@ -196,7 +196,7 @@ def test_reuse_gradient_skips_evaluation_zero_with_identical_results(golden):
     from nhmc_b200 import _lib, sampler, schedule
     g, net_cpu, net, op, oop, tab = _setup(golden)
     steps = schedule.ddim_steps(schedule.alpha_table(_betas()), SEQ, SEQ_NEXT)
-    B, n_it = 3, 3
+    B, n_it = 3, 2
     gen = torch.Generator().manual_seed(21)
     x = torch.randn(B, 3, 32, 32, generator=gen)
     y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
@@ -223,9 +223,9 @@ def test_reuse_gradient_skips_evaluation_zero_with_identical_results(golden):
         assert np.array_equal(ha, hb)
         assert np.array_equal(sta["epoch"], stb["epoch"]) and np.array_equal(sta["epsilon"], stb["epsilon"])
         # same arithmetic on the same values; what differs is last-bit nondeterminism of the network's library kernels,
-        # amplified by 60 chaotic leapfrog steps -- hence a loose image tolerance, not bit equality
-        np.testing.assert_allclose(xb.numpy(), xa.numpy(), atol=3e-3)
-        np.testing.assert_allclose(stb["H"], sta["H"], rtol=3e-4)
+        # amplified by 40 chaotic leapfrog steps -- hence a loose image tolerance, not bit equality
+        np.testing.assert_allclose(xb.numpy(), xa.numpy(), atol=5e-3)
+        np.testing.assert_allclose(stb["H"], sta["H"], rtol=2e-3)
         if not graphs:
             L = 20
             assert na == n_it * (L + 1) * 3 and nb == (n_it * L + 1) * 3, (na, nb)
