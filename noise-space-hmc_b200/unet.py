@@ -108,6 +108,54 @@ class _ScaledSoftmax(torch.autograd.Function):
         return dlogits, None
 
 
+class _AttentionCore(torch.autograd.Function):
+    """h = proj_out(attention(qkv(tok))) for channels-last tokens tok [B, T, C] (unet_ffhq.py:360-365, 408-425), with
+    the input gradient written out by hand: every product is a (strided-)batched GEMM whose OUTPUT already has the
+    layout its consumer wants, so the backward needs no transpose / contiguous copy (autograd's generic formulas leave
+    three of them per block: d_probs, d_a and d_tok come out transposed).  Weights are frozen: no weight gradients."""
+
+    @staticmethod
+    def forward(ctx, tok, wq, bq, wp, bp, nh):
+        B, T, C = tok.shape
+        ch = C // nh
+        scale = 1.0 / math.sqrt(ch)
+        # qkv in the reference's own layout [B, 3C, T] (channel = head*(3*ch) + {q,k,v}*ch + c): q, k, v of all B*nh
+        # heads are plain slices with ONE batch stride
+        qkv = torch.baddbmm(bq.view(1, 3 * C, 1), wq.unsqueeze(0).expand(B, 3 * C, C), tok.transpose(1, 2))
+        q, k, v = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)                       # each [B*nh, ch, T]
+        logits = torch.bmm(q.transpose(1, 2), k)                                     # [B*nh, T(q), T(k)]
+        probs = torch.empty_like(logits)
+        kernels.softmax_fwd(logits, probs, scale)
+        a = torch.bmm(v, probs.transpose(1, 2)).view(B, C, T)                        # a[b, c, t] = sum_s probs[t, s] v[c, s]
+        if bp is None:     # the caller adds proj_out's bias together with the residual (one pass of our bias_add kernel)
+            h = torch.bmm(a.transpose(1, 2), wp.t().unsqueeze(0).expand(B, C, C))                     # [B, T, C]
+        else:
+            h = torch.baddbmm(bp.view(1, 1, C), a.transpose(1, 2), wp.t().unsqueeze(0).expand(B, C, C))
+        ctx.save_for_backward(qkv, probs, wq, wp)
+        ctx.nh, ctx.scale = nh, scale
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        qkv, probs, wq, wp = ctx.saved_tensors
+        nh, scale = ctx.nh, ctx.scale
+        B, C3, T = qkv.shape
+        C = C3 // 3
+        ch = C // nh
+        dh = dh.contiguous()
+        q, k, v = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)
+        da = torch.bmm(wp.t().unsqueeze(0).expand(B, C, C), dh.transpose(1, 2)).view(B * nh, ch, T)   # da[c,t] = sum_o wp[o,c] dh[t,o]
+        dprobs = torch.bmm(da.transpose(1, 2), v)                                    # [B*nh, T, T], contiguous
+        dv = torch.bmm(da, probs)                                                    # dv[c,s] = sum_t da[c,t] probs[t,s]
+        dlogits = torch.empty_like(probs)
+        kernels.softmax_bwd(probs, dprobs, dlogits, scale)
+        dq = torch.bmm(k, dlogits.transpose(1, 2))                                   # dq[c,t] = sum_s k[c,s] dlogits[t,s]
+        dk = torch.bmm(q, dlogits)                                                   # dk[c,s] = sum_t q[c,t] dlogits[t,s]
+        dqkv = torch.cat([dq, dk, dv], dim=1).view(B, C3, T)
+        dtok = torch.bmm(dqkv.transpose(1, 2), wq.unsqueeze(0).expand(B, C3, C))     # [B, T, C], contiguous
+        return dtok, None, None, None, None, None
+
+
 def _cl(x):
     return x if _is_channels_last(x) else x.contiguous(memory_format=torch.channels_last)
 
@@ -380,20 +428,14 @@ class AttentionBlock(nn.Module):
         T, nh = H * W, self.num_heads
         ch = C // nh
         xn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
-        # Every operand below is a VIEW handed to a (strided-)batched GEMM: no permute/contiguous copy anywhere.
+        # Every operand is a VIEW handed to a (strided-)batched GEMM, forward and backward (_AttentionCore)
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
-        wq = self.qkv.weight[:, :, 0]
-        # qkv in the reference's own layout [B, 3C, T] (unet_ffhq.py:408-417: channel = head*(3*ch) + {q,k,v}*ch + c),
-        # so that q, k, v of all B*nh heads are plain slices with ONE batch stride
-        qkv = torch.baddbmm(self.qkv.bias.view(1, 3 * C, 1), wq.unsqueeze(0).expand(B, 3 * C, C), tok.transpose(1, 2))
-        q, k, v = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)                       # each [B*nh, ch, T]
-        logits = torch.bmm(q.transpose(1, 2), k)                                     # [B*nh, T(q), T(k)]
-        probs = _ScaledSoftmax.apply(logits, 1.0 / math.sqrt(ch))
-        a = torch.bmm(v, probs.transpose(1, 2)).view(B, C, T)                        # a[b, c, t] = sum_s probs[t, s] v[c, s]
-        wp = self.proj_out.weight[:, :, 0]
-        h = torch.baddbmm(self.proj_out.bias.view(1, 1, C), a.transpose(1, 2), wp.t().unsqueeze(0).expand(B, C, C))   # [B, T, C]
-        out = x.permute(0, 2, 3, 1).reshape(B, T, C) + h
-        return out.view(B, H, W, C).permute(0, 3, 1, 2)
+        h = _AttentionCore.apply(tok, self.qkv.weight[:, :, 0], self.qkv.bias, self.proj_out.weight[:, :, 0], None, nh)
+        b32 = getattr(self, "_proj_bias_f32", None)
+        if b32 is None or b32.device != x.device:
+            b32 = self._proj_bias_f32 = self.proj_out.bias.detach().float().contiguous()
+        # x + proj_out(a) (unet_ffhq.py:365): residual and proj_out's bias in ONE pass; h [B, T, C] IS channels-last [B, C, H, W]
+        return _BiasAdd.apply(x, h.view(B, H, W, C).permute(0, 3, 1, 2), b32)
 
 
 class _Seq(nn.Sequential):
@@ -508,6 +550,8 @@ class UNetModel(nn.Module):
                 m._skip_split = None
             if isinstance(m, nn.Conv2d) and hasattr(m, "_bias_f32"):
                 m._bias_f32 = None
+            if isinstance(m, AttentionBlock):
+                m._proj_bias_f32 = None
         return r
 
     def prepare(self, device="cuda"):
