@@ -250,8 +250,11 @@ int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, 
                 const float* gamma, const float* beta, const float* scale, const float* shift,
                 int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats,
                 float* dscale, float* dshift,
-                const void* dx_add, int batch, int channels, int64_t hw, int groups,
+                const void* dx_add, const void* dx_add2, int batch, int channels, int64_t hw, int groups,
                 nhmc_stream_t stream);
+/* dx_add2 (channels-last, needs dx_add): a second tensor added to dx in the same pass -- the gradient that reaches a
+ * block input through the U-Net's long skip connection (unet_ffhq.py:729-731), otherwise a read-read-write
+ * accumulation pass of autograd's.  Takes the statistics + apply kernels. */
 /* 0 unless a per-sample barrier of the shared-memory-resident GroupNorm path ever timed out on the
  * current device (synchronises; for tests and debugging, not for the hot loop). */
 /* GroupNorm over the VIRTUAL concatenation cat([x0, x1], channel) (the skip connections of the output

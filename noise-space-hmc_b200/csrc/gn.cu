@@ -94,6 +94,8 @@ __device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f
 struct GnArgs {
   const void* x; const void* dy; void* out;
   const void* add;   // backward: optional tensor added to dx in the same pass (skip-branch gradient), or null
+  const void* add2;  // backward, single-source statistics + apply path only: a second addend (the gradient that reaches the
+                     // block input through the U-Net's long skip connection), or null
   // virtual concatenation (unet_ffhq.py:730): when x1 != null the normalised tensor is cat([x, x1], channel) with
   // c_split channels in x and C - c_split in x1, each a dense channels-last block of its own; the backward then
   // writes dx / reads add per block (out, out1 / add, add1; add and add1 are independently nullable)
@@ -345,7 +347,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
 }
 
 // PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
-template <typename T, int MODE, int PHASE>
+template <typename T, int MODE, int PHASE, bool ADD2 = false>
 __global__ void __launch_bounds__(256, 3)
 gn_nhwc_apply_kernel(GnArgs a) {
   constexpr int V = VecOf<T>::N;
@@ -404,9 +406,11 @@ gn_nhwc_apply_kernel(GnArgs a) {
                                  : row_ptr<T>(sel.second ? a.out1 : a.out, sel.width, sel.cc, first);
   const void* addp = sel.second ? a.add1 : a.add;
   const bool has_add = PHASE == 1 && addp != nullptr;
-  const RowPtr extra[2] = {orow, row_ptr<T>(addp, sel.width, sel.cc, first)};
-  stream_rows<PHASE == 1 ? 2 : 1, 2, false>(xr, dr, extra, r_begin, r_end, prow, rows,
-      [&](const uint4& rx, const uint4& rd, char* const (&ep)[2]) {
+  constexpr int NX = ADD2 ? 3 : 2;
+  const RowPtr extra[3] = {orow, row_ptr<T>(addp, sel.width, sel.cc, first), row_ptr<T>(ADD2 ? a.add2 : nullptr, a.C, c0, first)};
+  const RowPtr (&extra_nx)[NX] = reinterpret_cast<const RowPtr (&)[NX]>(extra);
+  stream_rows<PHASE == 1 ? 2 : 1, NX, false>(xr, dr, extra_nx, r_begin, r_end, prow, rows,
+      [&](const uint4& rx, const uint4& rd, char* const (&ep)[NX]) {
         float xv[V], ov[V];
         unpack<T>(rx, xv);
         if (PHASE == 0) {
@@ -420,7 +424,14 @@ gn_nhwc_apply_kernel(GnArgs a) {
             const float d = dv[i] * gn_dact_a<MODE, T>(fmaf(ca[i], xv[i], cb[i]));
             ov[i] = fmaf(k1[i], d, fmaf(k2[i], xv[i], k3[i]));
           }
-          if (has_add) {
+          if (ADD2) {            // both addends present (host contract): issue the two loads together
+            float ad[V], ae[V];
+            const uint4 r1 = ld_raw(ep[1]);
+            const uint4 r2 = ld_raw(ep[ADD2 ? 2 : 1]);
+            unpack<T>(r1, ad); unpack<T>(r2, ae);
+#pragma unroll
+            for (int i = 0; i < V; ++i) ov[i] += ad[i] + ae[i];
+          } else if (has_add) {
             float ad[V];
             unpack<T>(ld_raw(ep[1]), ad);
 #pragma unroll
@@ -1433,7 +1444,7 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   int rows = 256 / cvec; if (rows < 1) rows = 1;
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
-  if (!a.x1) {
+  if (!a.x1 && !a.add2) {
     int e = run_nhwc_solo<T, MODE, PHASE>(a, batch, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
     e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
@@ -1465,14 +1476,19 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   a.b0 = 0;
   const dim3 grid((unsigned)nblk, (unsigned)batch);
   gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, red, st>>>(a);
-  gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, 0, st>>>(a);
+  if (PHASE == 1 && a.add2) {
+    NHMC_CHECK_ARG(a.add && !a.x1, "dx_add2 needs dx_add and a single-source tensor");
+    gn_nhwc_apply_kernel<T, MODE, PHASE, PHASE == 1><<<grid, threads, 0, st>>>(a);
+  } else {
+    gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, 0, st>>>(a);
+  }
   return NHMC_LAUNCH_CHECK();
 }
 
 template <typename T, int MODE, int PHASE>
 static int run_any(int layout, GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   if (layout == NHMC_LAYOUT_NHWC) return run_nhwc<T, MODE, PHASE>(a, s, batch, st);
-  NHMC_CHECK_ARG(!a.add, "dx_add needs the channels-last layout");
+  NHMC_CHECK_ARG(!a.add && !a.add2, "dx_add needs the channels-last layout");
   gn_nchw_kernel<T, MODE, PHASE><<<dim3(a.G, batch), 256, 0, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
@@ -1531,13 +1547,14 @@ extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void*
 extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                            const float* gamma, const float* beta, const float* scale, const float* shift,
                            int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats, float* dscale,
-                           float* dshift, const void* dx_add, int batch,
+                           float* dshift, const void* dx_add, const void* dx_add2, int batch,
                            int channels, int64_t hw, int groups, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(dy && stats, "dy and stats required");
   NHMC_CHECK_ARG(!dscale && !dshift, "dscale/dshift are not produced on the sampling path (timestep embedding carries no gradient)");
   NHMC_CHECK_ARG(layout != NHMC_LAYOUT_NHWC || aligned16(dy), "dy must be 16-byte aligned");
   NHMC_CHECK_ARG(!dx_add || aligned16(dx_add), "dx_add must be 16-byte aligned");
+  NHMC_CHECK_ARG(!dx_add2 || (dx_add && aligned16(dx_add2)), "dx_add2 needs dx_add and 16-byte alignment");
   GnScratch s;
   if (int e = get_scratch(batch, groups, s)) return e;
   GnArgs a{};
@@ -1547,7 +1564,7 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = 0.f;
   a.film_stride = film_stride > 0 ? film_stride : channels;
   NHMC_CHECK_ARG(a.film_stride >= channels, "film_stride must be >= channels");
-  a.add = dx_add;
+  a.add = dx_add; a.add2 = dx_add2;
   return dispatch<1>(mode, layout, dtype, a, s, batch, (cudaStream_t)stream);
 }
 

@@ -221,15 +221,17 @@ def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_l
                                 _in_bias_stride(in_bias, Cc), _p(stats), B, Cc, hw, groups, float(eps), _stream()), "nhmc_gn_fwd")
 
 
-def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None, dx_add=None):
-    """dx = d/dx act(GN(x)) . dy (+ dx_add, e.g. the gradient of the ResBlock's skip branch, in the same pass)."""
+def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None, dx_add=None, dx_add2=None):
+    """dx = d/dx act(GN(x)) . dy (+ dx_add, e.g. the gradient of the ResBlock's skip branch, + dx_add2, the gradient
+    arriving through the U-Net's long skip connection, in the same pass)."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
-    with _timed("gn_bwd", 1, (3 + (1 if dx_add is not None else 0)) * x.numel() * x.element_size()):
+    n_add = (1 if dx_add is not None else 0) + (1 if dx_add2 is not None else 0)
+    with _timed("gn_bwd", 1, (3 + n_add) * x.numel() * x.element_size()):
         check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
                                 _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc),
-                                _p(in_bias), _in_bias_stride(in_bias, Cc), _p(stats), 0, 0, _p(dx_add), B, Cc, hw, groups,
-                                _stream()), "nhmc_gn_bwd")
+                                _p(in_bias), _in_bias_stride(in_bias, Cc), _p(stats), 0, 0, _p(dx_add), _p(dx_add2), B, Cc, hw,
+                                groups, _stream()), "nhmc_gn_bwd")
 
 
 def gn_check():

@@ -166,26 +166,32 @@ class _GroupNormActSkip(torch.autograd.Function):
     kernel (dx_add) instead of leaving autograd a separate read-read-write accumulation pass."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias, eps=GN_EPS):
+    def forward(ctx, x, gamma, beta, scale, shift, mode, in_bias, eps=GN_EPS, fork=False):
+        """fork: a third output, one more pass-through of x, for the U-Net's list of skip tensors (unet_ffhq.py:722,730):
+        the gradient that comes back through the long skip connection is then added inside this backward kernel too
+        (dx_add2) instead of by a separate read-read-write accumulation pass of autograd's."""
         x = _cl(x)
         y = torch.empty_like(x)
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
         kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, eps, True, in_bias)
         ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
-        ctx.mode = mode
+        ctx.mode, ctx.fork = mode, fork
+        if fork:
+            return y, x.view_as(x), x.view_as(x)
         return y, x.view_as(x)
 
     @staticmethod
-    def backward(ctx, dy, dskip):
+    def backward(ctx, dy, dskip, dlong=None):
         x, gamma, beta, scale, shift, stats, in_bias = ctx.saved_tensors
+        none = (None,) * 8
+        adds = [_cl(g) for g in (dskip, dlong) if g is not None]
         if dy is None:
-            return dskip, None, None, None, None, None, None, None
+            return ((adds[0] + adds[1]) if len(adds) == 2 else (adds[0] if adds else None),) + none
         dy = _cl(dy)
-        if dskip is not None:
-            dskip = _cl(dskip)
         dx = torch.empty_like(x)
-        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias, dx_add=dskip)
-        return dx, None, None, None, None, None, None, None
+        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias,
+                       dx_add=adds[0] if adds else None, dx_add2=adds[1] if len(adds) == 2 else None)
+        return (dx,) + none
 
 
 class _AvgPool2(torch.autograd.Function):
@@ -274,13 +280,14 @@ def group_norm_act(x, norm, mode, scale=None, shift=None, in_bias=None):
     return _GroupNormAct.apply(x, norm.weight, norm.bias, scale, shift, mode, in_bias, getattr(norm, "eps", GN_EPS))
 
 
-def group_norm_act_skip(x, norm, mode):
-    """(act(GN32(x)), x): use the second output on the skip branch so that its gradient is added in-kernel."""
+def group_norm_act_skip(x, norm, mode, fork=False):
+    """(act(GN32(x)), x [, x]): use the second output on the skip branch (and the third, with fork, in the U-Net's list
+    of skip tensors) so that their gradients are added in-kernel."""
     if not x.is_cuda:
         raise _lib.NhmcError("the fused GroupNorm epilogue runs on CUDA only (sm_100a); no CPU fallback")
     if x.dim() != 4 or x.shape[1] % (4 if x.dtype == torch.float32 else 8):
-        return group_norm_act(x, norm, mode), x
-    return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None, getattr(norm, "eps", GN_EPS))
+        return (group_norm_act(x, norm, mode), x, x) if fork else (group_norm_act(x, norm, mode), x)
+    return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None, getattr(norm, "eps", GN_EPS), fork)
 
 
 def _conv_nobias(conv, x):
@@ -338,13 +345,17 @@ class ResBlock(nn.Module):
         self.out_layers = nn.Sequential(_Norm(oc), nn.Identity(), nn.Identity(), nn.Conv2d(oc, oc, 3, padding=1))
         self.skip_connection = nn.Identity() if oc == channels else nn.Conv2d(channels, oc, 1)
 
-    def forward(self, x, e):
+    def forward(self, x, e, fork=False):
         """e = this block's embedding projection emb_layers(emb) in fp32, [B, 2*oc] (FiLM) or [B, oc]: a view into
-        the one batched projection UNetModel.forward computes for all blocks (unet_ffhq.py:263-270,317-321)."""
-        xs = None
+        the one batched projection UNetModel.forward computes for all blocks (unet_ffhq.py:263-270,317-321).
+        fork: also return a pass-through of the block INPUT for the U-Net's skip list (see _GroupNormActSkip)."""
+        xs, x_long = None, None
         if isinstance(x, tuple):                 # virtual concatenation (h, skip) of an output block
+            assert not fork
             h, xa, xb = _CatGroupNormAct.apply(x[0], x[1], self.in_layers[0].weight, self.in_layers[0].bias, _lib.GN_SILU)
             xs = (xa, xb)
+        elif fork:
+            h, x, x_long = group_norm_act_skip(x, self.in_layers[0], _lib.GN_SILU, fork=True)
         else:
             h, x = group_norm_act_skip(x, self.in_layers[0], _lib.GN_SILU)
         if self.up:
@@ -367,7 +378,8 @@ class ResBlock(nn.Module):
             w0, w1 = self._split_skip_weights(xs[0].shape[1])
             return _BiasAdd.apply(F.conv2d(xs[0], w0), h, b_out, F.conv2d(xs[1], w1))
         skip = x if isinstance(self.skip_connection, nn.Identity) else _conv_nobias(self.skip_connection, x)
-        return _BiasAdd.apply(skip, h, b_out)
+        out = _BiasAdd.apply(skip, h, b_out)
+        return (out, x_long) if fork else out
 
     def _split_skip_weights(self, c0):
         """The skip 1x1 convolution's (frozen) weight split at input channel c0, as two dense channels-last filters."""
@@ -441,10 +453,15 @@ class AttentionBlock(nn.Module):
 class _Seq(nn.Sequential):
     """TimestepEmbedSequential (unet_ffhq.py:137-150)."""
 
-    def forward(self, x, embs):
-        for layer in self:
-            x = layer(x, embs[layer]) if isinstance(layer, ResBlock) else layer(x)
-        return x
+    def forward(self, x, embs, fork=False):
+        """fork (first layer must be a ResBlock): returns (output, pass-through of the input for the skip list)."""
+        x_long = None
+        for j, layer in enumerate(self):
+            if fork and j == 0:
+                x, x_long = layer(x, embs[layer], fork=True)
+            else:
+                x = layer(x, embs[layer]) if isinstance(layer, ResBlock) else layer(x)
+        return (x, x_long) if fork else x
 
 
 class UNetModel(nn.Module):
@@ -455,6 +472,7 @@ class UNetModel(nn.Module):
         self.image_size, self.in_channels, self.model_channels = image_size, in_channels, model_channels
         self.out_channels, self.compute_dtype = out_channels, dtype
         self.virtual_cat_min_pixels = 64 * 64      # skip concatenations at >= this many pixels stay virtual
+        self.fork_min_bytes = 32 << 20             # tensors from this size on (statistics + apply GroupNorm path): see forward
         E = model_channels * 4
         self.time_embed = nn.Sequential(nn.Linear(model_channels, E), nn.SiLU(), nn.Linear(E, E))
         rb = dict(film=use_scale_shift_norm)
@@ -572,6 +590,11 @@ class UNetModel(nn.Module):
             if i == 0:
                 conv = module[0]
                 h = _BiasAdd.apply(_conv_nobias(conv, h), None, self._first_bias())
+            elif (self.fork_min_bytes is not None and isinstance(module[0], ResBlock)
+                  and h.numel() * h.element_size() >= self.fork_min_bytes):
+                # large maps: the skip list keeps a pass-through output of the NEXT block's first GroupNorm, so the
+                # gradient coming back through the long skip is added inside that GroupNorm's backward kernel
+                h, hs[-1] = module(h, embs, fork=True)
             else:
                 h = module(h, embs)
             hs.append(h)

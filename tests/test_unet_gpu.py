@@ -325,3 +325,47 @@ def test_unet_virtual_concat_matches_materialised_concat(golden):
         outs.append((out.detach(), gx))
         np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=1e-4)
         np.testing.assert_allclose(gx.cpu().numpy(), g["grad_x"], atol=5e-5 * max(1.0, float(np.abs(g["grad_x"]).max())), rtol=1e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("shape", [(8, 128, 128, 128), (2, 128, 33, 7), (3, 256, 16, 16)])
+def test_group_norm_backward_two_addends(dtype, mode, shape):
+    """dx = gn_bwd(dy) + dx_add + dx_add2 in one pass (ResBlock skip-branch gradient + long-skip gradient)."""
+    from nhmc_b200 import kernels
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(5)
+    cl = torch.channels_last
+    x = (torch.randn(shape, generator=g) * 1.3 - 0.2).cuda().to(dtype).contiguous(memory_format=cl)
+    dy, a1, a2 = (torch.randn(shape, generator=g).cuda().to(dtype).contiguous(memory_format=cl) for _ in range(3))
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).cuda(); beta = (0.1 * torch.randn(C, generator=g)).cuda()
+    scale = (0.3 * torch.randn(B, C, generator=g)).cuda(); shift = (0.3 * torch.randn(B, C, generator=g)).cuda()
+    sc, sh = (scale, shift) if mode == 2 else (None, None)
+    xr = x.float().detach().clone().requires_grad_(True)
+    yr = _gn_ref(xr, gamma, beta, scale, shift, mode)
+    (dxr,) = torch.autograd.grad(yr, xr, dy.float())
+    dxr = dxr + a1.float() + a2.float()
+    for rep in range(2):
+        y = torch.empty_like(x); dx = torch.empty_like(x); stats = torch.empty(B, 32, 2, device="cuda")
+        kernels.gn_fwd(mode, x, y, gamma, beta, sc, sh, stats, 32, 1e-5, True)
+        kernels.gn_bwd(mode, x, dy, dx, gamma, beta, sc, sh, stats, 32, True, dx_add=a1, dx_add2=a2)
+        kernels.gn_check()
+        tol = dict(atol=5e-5, rtol=1e-4) if dtype == torch.float32 else dict(atol=3e-2, rtol=2e-2)
+        dd = (dx.float() - dxr).abs()
+        assert float((dd - tol["atol"] * float(dxr.abs().max()) - tol["rtol"] * dxr.abs()).max()) <= 0, (rep, float(dd.max()))
+
+
+def test_unet_long_skip_gradient_fused_into_group_norm_backward(golden):
+    """fork_min_bytes = 0: every input block hands the skip list a pass-through output of the next block's first
+    GroupNorm, whose backward kernel then adds the long-skip gradient (dx_add2); None: autograd's own accumulation."""
+    g = golden("unet_small.npz")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    m, sd, cfg = _small_model(torch.float32)
+    for fork in (0, None):
+        m.fork_min_bytes = fork
+        x = T(g["x"]).cuda().requires_grad_(True)
+        out = m(x, T(g["t"]).cuda())
+        (gx,) = torch.autograd.grad(out, x, T(g["w"]).cuda())
+        np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=1e-4)
+        np.testing.assert_allclose(gx.cpu().numpy(), g["grad_x"], atol=5e-5 * max(1.0, float(np.abs(g["grad_x"]).max())), rtol=1e-3)
