@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
     ap.add_argument("--workload", default="pixel", choices=["pixel", "latent"], help="pixel: --algo hmc (BASELINE config[1], the metric's configuration); latent: --algo hmc_latent on the ffhq_latent architecture (BASELINE config[4])")
     ap.add_argument("--lanes", type=int, default=1, help="groups of chains evaluated on their own streams (parallel branches of the captured step)")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the U-Net epilogue kernels (1 = library default)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -145,6 +146,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
+    _lib.lib().nhmc_set_pdl(args.pdl)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B, K, W = args.chains, args.steps, max(args.warmup, 3)
 

@@ -278,6 +278,11 @@ int nhmc_gn_check(void);
  * channel-slice kernel for tensors beyond one wave (units of whole groups, >= 2 units on the chip at
  * once, x and dy read once).  Returns the previous setting.  For A/B measurements and tests. */
 int nhmc_gn_set_resident(int on);
+/* Programmatic dependent launch for the U-Net epilogue kernels (GroupNorm statistics / apply / one-CTA kernel, pooling,
+ * residual add): 1 (default, NHMC_PDL=0 in the environment disables) launches them with the programmatic-stream-
+ * serialization attribute so that a kernel's CTAs are scheduled while its predecessor drains; 0 = plain launches.
+ * Returns the previous setting. */
+int nhmc_set_pdl(int on);
 /* 1 (default): maps whose (sample, slice of whole groups) units fit one CTA's shared memory (8x8 .. 64x64 at
  * FFHQ-256) take the one-CTA-per-unit kernel (no inter-CTA barrier); 0: never.  Returns the previous setting. */
 int nhmc_gn_set_solo(int on);

@@ -82,6 +82,7 @@ _SIGS = {
     "nhmc_gn_set_resident": (C.c_int, [C.c_int]),
     "nhmc_gn_set_lane": (C.c_int, [C.c_int, C.c_int]),
     "nhmc_gn_set_solo": (C.c_int, [C.c_int]),
+    "nhmc_set_pdl": (C.c_int, [C.c_int]),
     "nhmc_bias_add": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "nhmc_pool2_gather": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "nhmc_pool2_scatter": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

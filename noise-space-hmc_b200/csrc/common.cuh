@@ -28,6 +28,31 @@ int cuda_status(cudaError_t e, const char* what);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- programmatic dependent launch (PDL, sm_90+) -------------------------------------------------------------
+// The U-Net epilogue kernels (GroupNorm statistics / apply / one-CTA kernel, pooling, residual add) often follow one
+// another directly.  Launched with the programmatic-stream-serialization attribute, a kernel's CTAs are scheduled as
+// soon as the previous kernel's CTAs have all STARTED and executed pdl_trigger(); they then block in pdl_wait() until
+// that kernel has completed and flushed its writes.  Launch latency and CTA scheduling of the dependent overlap the
+// tail of its predecessor; captured into a CUDA graph the edge becomes a programmatic dependency.  Kernels whose CTAs
+// wait on each other (the resident GroupNorm with its global barrier) never trigger early.  NHMC_PDL=0 disables.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+bool pdl_enabled();
+void pdl_set(int on);
+
+template <typename... KA, typename... A>
+static inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
+}
+
 // ---- streaming loads/stores: data is touched once per kernel, keep it out of L1 ----------
 // ld_stream: plain global load (safe when the same thread rewrites the location later);
 // ld_ro: read-only path, only for buffers the kernel never writes.

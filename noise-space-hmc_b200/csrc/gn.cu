@@ -256,6 +256,7 @@ __device__ __forceinline__ void stream_rows(const RowPtr x, const RowPtr d, cons
 template <typename T, int MODE, int PHASE>
 __global__ void __launch_bounds__(256, 3)
 gn_nhwc_stats_kernel(GnArgs a) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = VecOf<T>::N;
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -350,6 +351,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
 template <typename T, int MODE, int PHASE, bool ADD2 = false>
 __global__ void __launch_bounds__(256, 3)
 gn_nhwc_apply_kernel(GnArgs a) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = VecOf<T>::N;
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   const int b = blockIdx.y + a.b0, blk = blockIdx.x;
@@ -813,6 +815,7 @@ constexpr int kSliceThreads = 256;   // 3 CTAs per SM (24 warps): the backward i
 template <typename T, int MODE, int PHASE, bool SOLO = false>
 __global__ void __launch_bounds__(kSliceThreads, 3)
 gn_nhwc_slice_kernel(const GnSliceArgs r) {
+  if (SOLO) { pdl_wait(); pdl_trigger(); }     // units never wait on each other: safe to let the next kernel's CTAs in early
   constexpr int V = VecOf<T>::N;
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
@@ -1433,6 +1436,11 @@ static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
   const int64_t n_pass = (a0.HW + rows - 1) / rows;
   r.chunk_passes = (int)((n_pass + 3) / 4);
   r.total_ctas = (unsigned int)(batch * best_cs);
+  // Programmatic launch only for launches of small units or at most one CTA per SM: with several large-unit CTAs per SM
+  // the dependents that slip in early crowd some SMs and the launch ends unbalanced (measured: 15.5 -> 18.4 us at
+  // [8,512,32,32] backward); a plain launch spreads evenly over the idle chip.
+  if ((int64_t)r.total_ctas <= d.sms || (int64_t)best_slab * NSRC <= 16384)
+    return cuda_status(launch_pdl(kern, dim3(r.total_ctas), dim3(best_threads), (size_t)best_slab * NSRC, st, r), "gn one-CTA launch");
   kern<<<r.total_ctas, best_threads, (size_t)best_slab * NSRC, st>>>(r);
   return NHMC_LAUNCH_CHECK();
 }
@@ -1475,14 +1483,12 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   a.rows_per_cta_iter = rows;
   a.b0 = 0;
   const dim3 grid((unsigned)nblk, (unsigned)batch);
-  gn_nhwc_stats_kernel<T, MODE, PHASE><<<grid, threads, red, st>>>(a);
+  if (int e = cuda_status(launch_pdl(gn_nhwc_stats_kernel<T, MODE, PHASE>, grid, dim3(threads), red, st, a), "gn statistics launch")) return e;
   if (PHASE == 1 && a.add2) {
     NHMC_CHECK_ARG(a.add && !a.x1, "dx_add2 needs dx_add and a single-source tensor");
-    gn_nhwc_apply_kernel<T, MODE, PHASE, PHASE == 1><<<grid, threads, 0, st>>>(a);
-  } else {
-    gn_nhwc_apply_kernel<T, MODE, PHASE><<<grid, threads, 0, st>>>(a);
+    return cuda_status(launch_pdl(gn_nhwc_apply_kernel<T, MODE, PHASE, PHASE == 1>, grid, dim3(threads), 0, st, a), "gn apply launch");
   }
-  return NHMC_LAUNCH_CHECK();
+  return cuda_status(launch_pdl(gn_nhwc_apply_kernel<T, MODE, PHASE>, grid, dim3(threads), 0, st, a), "gn apply launch");
 }
 
 template <typename T, int MODE, int PHASE>

@@ -56,6 +56,7 @@ template <> __device__ __forceinline__ uint4 down<__half>(const float (&v)[8]) {
 template <typename T, bool GATHER>
 __global__ void __launch_bounds__(256)
 pool2_kernel(const T* __restrict__ in, T* __restrict__ out, int h, int w, int cvec, int64_t total, float scale) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = V16<T>::N;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int cv = (int)(idx % cvec);
@@ -105,6 +106,7 @@ split2_kernel(const T* __restrict__ in, T* __restrict__ o1, T* __restrict__ o2, 
 template <typename T, bool HAS_B, bool HAS_BIAS>
 __global__ void __launch_bounds__(256)
 bias_add_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const float* __restrict__ bias, T* out, int64_t total, int cvec) {
+  pdl_wait(); pdl_trigger();
   constexpr int V = V16<T>::N;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     float va[V], vb[V];
@@ -141,9 +143,9 @@ static int run_pool(bool gather, const void* in, void* out, int batch, int h, in
   constexpr int V = V16<T>::N;
   NHMC_CHECK_ARG(C % V == 0, "channels must be a multiple of the 16-byte vector width");
   const int64_t total = (int64_t)batch * h * w * (C / V);
-  if (gather) pool2_kernel<T, true><<<grid_for(total), 256, 0, st>>>((const T*)in, (T*)out, h, w, C / V, total, scale);
-  else pool2_kernel<T, false><<<grid_for(total), 256, 0, st>>>((const T*)in, (T*)out, h, w, C / V, total, scale);
-  return NHMC_LAUNCH_CHECK();
+  const dim3 g(grid_for(total)), b(256);
+  if (gather) return cuda_status(launch_pdl(pool2_kernel<T, true>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
+  return cuda_status(launch_pdl(pool2_kernel<T, false>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
 }
 
 }  // namespace nhmc
@@ -196,11 +198,10 @@ static int run_bias_add(const void* a, const void* b, const void* c, const float
   NHMC_CHECK_ARG(C % V == 0, "channels must be a multiple of the 16-byte vector width");
   const int64_t total = rows * (C / V);
   const unsigned g = grid_for(total);
-#define BA(HB, HBI) bias_add_kernel<T, HB, HBI><<<g, 256, 0, st>>>((const T*)a, (const T*)b, (const T*)c, bias, (T*)out, total, C / V)
+#define BA(HB, HBI) return cuda_status(launch_pdl(bias_add_kernel<T, HB, HBI>, dim3(g), dim3(256), 0, st, (const T*)a, (const T*)b, (const T*)c, bias, (T*)out, total, C / V), "bias_add launch")
   if (b) { if (bias) BA(true, true); else BA(true, false); }
   else   { if (bias) BA(false, true); else BA(false, false); }
 #undef BA
-  return NHMC_LAUNCH_CHECK();
 }
 
 extern "C" int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c, const float* bias, void* out,

@@ -71,6 +71,7 @@ def main():
     ap.add_argument("--shape", default="", help="GroupNorm: only this B,C,H (e.g. 8,128,256)")
     ap.add_argument("--resident", type=int, default=1, help="GroupNorm: 1 = shared-memory resident single kernel, 0 = statistics + apply kernels")
     ap.add_argument("--solo", type=int, default=1, help="GroupNorm: 1 = one-CTA-per-unit kernel for the small maps (default), 0 = off")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the U-Net epilogue kernels (1 = default)")
     ap.add_argument("--warm", action="store_true", help="no L2 flush between repetitions (inputs L2-resident, as inside the U-Net for the small maps)")
     ap.add_argument("--small", action="store_true", help="GroupNorm: the small-map shapes of the ffhq_10m U-Net at 8 chains")
     ap.add_argument("--graph-calls", type=int, default=1, help="time this many back-to-back calls replayed from one CUDA graph (per-call time reported)")
@@ -83,6 +84,7 @@ def main():
     want = lambda k: (not a.only) or a.only in k
     _lib.lib().nhmc_gn_set_resident(a.resident)
     _lib.lib().nhmc_gn_set_solo(a.solo)
+    _lib.lib().nhmc_set_pdl(a.pdl)
 
     if want("gn"):
         shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]
