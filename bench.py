@@ -261,8 +261,17 @@ def run_ours(args, rank, world, local_rank):
         # one graph replay under CUPTI (torch.profiler): device-side duration of every kernel IN SITU (warm L2,
         # back-to-back launches) -- explains the step; the timed region above ran without any profiler
         from torch.profiler import profile, ProfilerActivity
+        step_p = step
+        if use_graphs and args.pdl:
+            # with programmatic dependent launch a kernel's CTAs are scheduled while its predecessor drains, so CUPTI's
+            # per-kernel durations would include that wait: the breakdown is taken on a capture with plain launches
+            _lib.lib().nhmc_set_pdl(0)
+            g_plain, _ = smp.capture_profiled_step(_lib.LF_MIDDLE, events=False)
+            _lib.lib().nhmc_set_pdl(1)
+            g_plain.replay(); torch.cuda.synchronize()
+            step_p = g_plain.replay
         with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
-            step()
+            step_p()
             torch.cuda.synchronize()
         fam = {}
         for ev in prof_t.events():
@@ -283,7 +292,8 @@ def run_ours(args, rank, world, local_rank):
             in_situ = {"sum_ms": tot / 1e3, "ours_launches_per_step": ours_n, "all_launches_per_step": sum(n for n, _ in fam.values()), "families": {k: {"launches": n, "ms": us / 1e3} for k, (n, us) in sorted(fam.items(), key=lambda kv: -kv[1][1])[:24]},
                        "ours_ms": sum(us for k, (_, us) in fam.items() if k.startswith("nhmc::")) / 1e3,
                        "library_ms": fam.get("library conv/gemm (cuDNN, cuBLAS)", (0, 0.0))[1] / 1e3,
-                       "note": "CUPTI kernel durations of ONE graph-replayed step after the timed region"}
+                       "note": "CUPTI kernel durations of ONE graph-replayed step after the timed region (captured with plain launches: "
+                               "under programmatic dependent launch a kernel's duration would include its wait on the predecessor)"}
         if args.torch_profile:
             with open(args.torch_profile, "w") as f:
                 f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=90))
@@ -375,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
                                 "random-init ffhq_10m U-Net (BASELINE config[1])") % (args.deg, B),
                    "chains_per_gpu": B, "deg": args.deg, "l2": "activations per step >> 126 MB L2 (8 chains x 3 U-Net passes); no flush needed",
                    "parallelism": "chains sharded, dp%d, no collective in the loop" % world, "cuda_graphs": use_graphs,
-                   "lanes": smp.n_lanes},
+                   "lanes": smp.n_lanes, "pdl": bool(args.pdl)},
         "e2e": e2e,
         # kernels of libnhmc.so launched inside the timed region: exact CUPTI count of one replayed step x K x ranks when the
         # in-situ pass ran, else the python-side count of the C calls (which counts a two-kernel GroupNorm call once)

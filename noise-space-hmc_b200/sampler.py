@@ -243,19 +243,21 @@ class HMCSampler:
         self._graphs = graphs
         return self
 
-    def capture_profiled_step(self, mode=_lib.LF_MIDDLE):
+    def capture_profiled_step(self, mode=_lib.LF_MIDDLE, events=True):
         """One step variant captured as a CUDA graph WITH a pair of timing events around every kernel of ours
         (event-record nodes).  Returns (graph, records): replay, then kernels.profile_read(records, acc) gives the
         per-kernel CUDA-event times of that replay -- measured in situ (warm L2, back-to-back launches) on the
-        launching stream.  Sampler state is restored after the capture."""
+        launching stream.  Sampler state is restored after the capture.  events=False: the same capture without the
+        event nodes (e.g. with other library settings than the sampler's own graphs, for A/B or profiler passes)."""
         keep = [t.clone() for t in (self.x, self.x_prop, self.p, self.chains.dev)]
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         pool = next(iter(self._graphs.values()))[0].pool() if self._graphs else None
-        kernels.profile_start()
+        if events:
+            kernels.profile_start()
         with torch.cuda.graph(g, pool=pool):
             self._step_eager(mode)
-        records = kernels.profile_take()
+        records = kernels.profile_take() if events else {}
         torch.cuda.synchronize()
         for dst, src in zip((self.x, self.x_prop, self.p, self.chains.dev), keep):
             dst.copy_(src)
