@@ -438,7 +438,6 @@ class AttentionBlock(nn.Module):
     def forward(self, x):
         B, C, H, W = x.shape
         T, nh = H * W, self.num_heads
-        ch = C // nh
         xn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
         # Every operand is a VIEW handed to a (strided-)batched GEMM, forward and backward (_AttentionCore)
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
@@ -554,7 +553,7 @@ class UNetModel(nn.Module):
             embs = self._emb_projection(emb_act)
         if not torch.cuda.is_current_stream_capturing():       # never keep graph-pool memory alive from here
             memo.append((timesteps, timesteps._version, w0.device, w0.dtype, embs))
-            del memo[:-8]
+            del memo[:-32]
         return embs
 
     def load_state_dict(self, *args, **kwargs):

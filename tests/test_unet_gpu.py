@@ -369,3 +369,47 @@ def test_unet_long_skip_gradient_fused_into_group_norm_backward(golden):
         (gx,) = torch.autograd.grad(out, x, T(g["w"]).cuda())
         np.testing.assert_allclose(out.detach().cpu().numpy(), g["out"], atol=5e-5, rtol=1e-4)
         np.testing.assert_allclose(gx.cpu().numpy(), g["grad_x"], atol=5e-5 * max(1.0, float(np.abs(g["grad_x"]).max())), rtol=1e-3)
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """The epilogue kernels launched with and without the programmatic-stream-serialization attribute (nhmc_set_pdl):
+    bit-identical GroupNorm / residual-add / pooling results, eagerly and replayed from a CUDA graph."""
+    from nhmc_b200 import kernels, _lib, unet
+    g = torch.Generator().manual_seed(17)
+    cl = torch.channels_last
+    shape = (4, 256, 32, 32)
+    x = torch.randn(shape, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    dy = torch.randn(shape, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    big = torch.randn(8, 128, 128, 128, generator=g).cuda().to(torch.bfloat16).contiguous(memory_format=cl)
+    gamma = (1 + 0.2 * torch.randn(256, generator=g)).cuda(); beta = (0.1 * torch.randn(256, generator=g)).cuda()
+    bias = torch.randn(256, generator=g).cuda()
+
+    def chain():
+        s = torch.empty_like(x); y = torch.empty_like(x); dx = torch.empty_like(x); st = torch.empty(4, 32, 2, device="cuda")
+        kernels.bias_add(x, dy, bias, s)                                       # residual add -> GroupNorm -> pooling
+        kernels.gn_fwd(1, s, y, gamma, beta, None, None, st, 32, 1e-5, True)
+        p = torch.empty((4, 256, 16, 16), dtype=x.dtype, device="cuda", memory_format=cl)
+        kernels.pool2_gather(y, p, 0.25)
+        kernels.gn_bwd(1, s, dy, dx, gamma, beta, None, None, st, 32, True, dx_add=y)
+        yb = torch.empty_like(big); stb = torch.empty(8, 32, 2, device="cuda")   # statistics + apply pair
+        kernels.gn_fwd(1, big, yb, gamma[:128].contiguous(), beta[:128].contiguous(), None, None, stb, 32, 1e-5, True)
+        return s, y, p, dx, yb
+
+    outs = {}
+    for pdl in (0, 1):
+        prev = _lib.lib().nhmc_set_pdl(pdl)
+        try:
+            outs[(pdl, "eager")] = [t.clone() for t in chain()]
+            chain(); torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                res = chain()
+            gr.replay(); gr.replay(); torch.cuda.synchronize()
+            outs[(pdl, "graph")] = [t.clone() for t in res]
+        finally:
+            _lib.lib().nhmc_set_pdl(prev)
+    kernels.gn_check()
+    ref = outs[(0, "eager")]
+    for key, val in outs.items():
+        for a, b in zip(ref, val):
+            assert torch.equal(a, b), key
