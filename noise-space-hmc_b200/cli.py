@@ -6,7 +6,7 @@
 
 Unknown flags are ignored like in the reference (`parse_known_args`, main_sampling.py:1031).  Additions:
 `--chains` (independent chains per GPU), `--synthetic` (seeded synthetic ground truth instead of the FFHQ folder),
-`--dtype`, `--cuda_graphs`, `--reuse_gradient`, `--save_progress`.  Under torchrun, chains are sharded across the GPUs (dist.py).
+`--dtype`, `--cuda_graphs`, `--reuse_gradient`, `--lanes`, `--save_progress`.  Under torchrun, chains are sharded across the GPUs (dist.py).
 """
 import argparse
 import math
@@ -50,6 +50,7 @@ def get_parser():
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"], help="score-network compute dtype")
     p.add_argument("--cuda_graphs", action="store_true", help="replay the leapfrog step as CUDA graphs")
     p.add_argument("--reuse_gradient", action="store_true", help="keep (loss, gradient) of the current state instead of re-evaluating it at the top of each iteration (20 instead of 21 evaluations; main_sampling.py:693-695)")
+    p.add_argument("--lanes", type=int, default=1, help="pixel path: evaluate the chains in this many groups on parallel streams (default 1: measured fastest at 8 chains)")
     p.add_argument("--save_progress", action="store_true", help="PNG of every accepted epoch like the reference (main_sampling.py:735)")
     p.add_argument("--ldm_ckpt", type=str, default="", help="hmc_latent: LatentDiffusion checkpoint (model.ckpt); random init if absent")
     p.add_argument("--max_iters", type=int, default=None, help="stop after this many HMC iterations (smoke runs)")
@@ -135,7 +136,7 @@ def _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_fun
     if n:
         lat = sampler.hmc_latent(z, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
                                  max_iters=opt.max_iters, on_iteration=on_it, image_size=config.data.image_size,
-                                 reuse_gradient=opt.reuse_gradient)
+                                 reuse_gradient=opt.reuse_gradient, lanes=opt.lanes)
         lat = [lat] if n == 1 else lat
         out = [ldm.decode_first_stage(l_).float() if l_.numel() else torch.zeros(0, 3, config.data.image_size, config.data.image_size, device=device)
                for l_ in lat]
