@@ -136,7 +136,7 @@ def _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_fun
     if n:
         lat = sampler.hmc_latent(z, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
                                  max_iters=opt.max_iters, on_iteration=on_it, image_size=config.data.image_size,
-                                 reuse_gradient=opt.reuse_gradient, lanes=opt.lanes)
+                                 reuse_gradient=opt.reuse_gradient)
         lat = [lat] if n == 1 else lat
         out = [ldm.decode_first_stage(l_).float() if l_.numel() else torch.zeros(0, 3, config.data.image_size, config.data.image_size, device=device)
                for l_ in lat]
@@ -194,7 +194,7 @@ def sample_image(opt, config, model_config, device):
     if n:
         out = sampler.hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, momentum=mom, uniform=uni,
                           max_iters=opt.max_iters, on_iteration=on_it, cuda_graphs=opt.cuda_graphs,
-                          reuse_gradient=opt.reuse_gradient)
+                          reuse_gradient=opt.reuse_gradient, lanes=opt.lanes)
         out = out[None] if n == 1 else out                                  # [n, S, C, H, W]
     allc = ndist.gather_chains(out, opt.chains) if world > 1 else out
     if rank == 0 and allc is not None and allc.numel():
