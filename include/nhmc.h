@@ -283,8 +283,10 @@ int nhmc_gn_set_resident(int on);
  * serialization attribute so that a kernel's CTAs are scheduled while its predecessor drains; 0 = plain launches.
  * Returns the previous setting. */
 int nhmc_set_pdl(int on);
-/* 1 (default): maps whose (sample, slice of whole groups) units fit one CTA's shared memory (8x8 .. 64x64 at
- * FFHQ-256) take the one-CTA-per-unit kernel (no inter-CTA barrier); 0: never.  Returns the previous setting. */
+/* 1: maps whose (sample, slice of whole groups) units fit one CTA's shared memory (8x8 .. 32x32 at FFHQ-256) take
+ * the one-CTA-per-unit kernel (no inter-CTA barrier); 2 (default): in addition the 64x64 maps take the same kernel
+ * with one thread-block cluster (2-8 CTAs, partial sums exchanged over distributed shared memory) per unit; 0: never.
+ * Returns the previous setting. */
 int nhmc_gn_set_solo(int on);
 /* Lanes: a host that evaluates groups of chains on n_lanes streams at once (the reference evaluates one chain at a
  * time, main_sampling.py:704-713; chains are independent) announces which lane the GroupNorm calls that follow

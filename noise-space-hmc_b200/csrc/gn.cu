@@ -812,10 +812,16 @@ constexpr int kSliceThreads = 256;   // 3 CTAs per SM (24 warps): the backward i
 // SOLO: every unit fits ONE CTA (nb == 1, the 8x8 .. 64x64 maps): no ticket, no global accumulators, no barrier --
 // the unit index is the block index and the group totals never leave shared memory, so launches of any number of
 // waves are safe and a call is one short dependency chain (load -> reduce -> normalise -> store).
-template <typename T, int MODE, int PHASE, bool SOLO = false>
+// SYNC 2: a unit is ONE thread-block cluster of nb <= 8 CTAs (the 64x64 maps, whose units exceed one CTA's share of shared
+// memory): the CTAs exchange their per-group partial sums through distributed shared memory behind the hardware cluster
+// barrier -- still no ticket, no global accumulators, no spinning, and clusters never wait on each other.
+template <typename T, int MODE, int PHASE, int SYNC = 0>
 __global__ void __launch_bounds__(kSliceThreads, 3)
 gn_nhwc_slice_kernel(const GnSliceArgs r) {
+  constexpr bool SOLO = SYNC == 1;
+  constexpr bool CLUSTER = SYNC == 2;
   if (SOLO) { pdl_wait(); pdl_trigger(); }     // units never wait on each other: safe to let the next kernel's CTAs in early
+  if (CLUSTER) pdl_wait();
   constexpr int V = VecOf<T>::N;
   constexpr float kAff = AffineHalf<MODE, T>::value ? 0.5f : 1.0f;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
@@ -825,12 +831,13 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
   __shared__ double g_acc[32][2];
   __shared__ float g_c0[32], g_c1[32];
   __shared__ unsigned int s_lid;
-  if (!SOLO) {
+  __shared__ double g_part[CLUSTER ? 32 : 1][2];
+  if (!SOLO && !CLUSTER) {
     if (threadIdx.x == 0) s_lid = atomicInc(r.ticket, r.total_ctas - 1u);
     __syncthreads();
   }
-  const int unit = SOLO ? (int)blockIdx.x : (int)(s_lid / (unsigned int)r.nb);
-  const int blk = SOLO ? 0 : (int)(s_lid % (unsigned int)r.nb);
+  const int unit = SOLO ? (int)blockIdx.x : CLUSTER ? (int)(blockIdx.x / (unsigned int)r.nb) : (int)(s_lid / (unsigned int)r.nb);
+  const int blk = SOLO ? 0 : CLUSTER ? (int)(blockIdx.x % (unsigned int)r.nb) : (int)(s_lid % (unsigned int)r.nb);
   const int b = unit / r.cs, sl = unit % r.cs;
   const float* in_bias = a.in_bias ? a.in_bias + (int64_t)b * a.in_bias_stride : nullptr;
   const int cvec = r.Cs / V;                                   // vectors per row of the slice
@@ -958,6 +965,8 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
       }
       if (SOLO) {
         g_acc[threadIdx.x][0] = t0; g_acc[threadIdx.x][1] = t1;
+      } else if (CLUSTER) {
+        g_part[threadIdx.x][0] = t0; g_part[threadIdx.x][1] = t1;       // read by every CTA of the cluster through DSMEM
       } else {
         atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
         atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
@@ -965,7 +974,20 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
       }
     }
     __syncthreads();
-    if (!SOLO) {
+    if (CLUSTER) {
+      cluster_arrive();
+      cluster_wait();
+      if ((int)threadIdx.x < g_count) {
+        double t0 = 0.0, t1 = 0.0;
+        for (int k = 0; k < r.nb; ++k) {           // rank order: deterministic
+          t0 += ld_dsmem_f64(&g_part[threadIdx.x][0], (unsigned)k); t1 += ld_dsmem_f64(&g_part[threadIdx.x][1], (unsigned)k);
+        }
+        g_acc[threadIdx.x][0] = t0; g_acc[threadIdx.x][1] = t1;
+      }
+      cluster_arrive();        // peers may exit (and release their shared memory) only after everybody has read: waited at kernel end
+      __syncthreads();
+    }
+    if (!SOLO && !CLUSTER) {
     if (threadIdx.x == 0) {
       atomicAdd(r.arrive + unit, 1u);
       const long long t_start = clock64();
@@ -1059,6 +1081,7 @@ gn_nhwc_slice_kernel(const GnSliceArgs r) {
       }
     }
   }
+  if (CLUSTER) cluster_wait();    // every peer has finished reading this CTA's partial sums
 }
 
 // ============================== NCHW =========================================================
@@ -1376,9 +1399,9 @@ static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaS
   return NHMC_ERR_UNSUPPORTED;
 }
 
-static int g_solo_mode = -1;       // NHMC_GN_SOLO=0 / nhmc_gn_set_solo(0): never take the one-CTA-per-unit kernel (A/B measurements, tests)
+static int g_solo_mode = -1;       // NHMC_GN_SOLO / nhmc_gn_set_solo: 0 never, 1 one-CTA-per-unit kernel, 2 (default) + cluster-per-unit kernel
 static int solo_mode() {
-  if (g_solo_mode < 0) { const char* e = getenv("NHMC_GN_SOLO"); g_solo_mode = (e && e[0] == '0') ? 0 : 1; }
+  if (g_solo_mode < 0) { const char* e = getenv("NHMC_GN_SOLO"); g_solo_mode = e ? atoi(e) : 2; }
   return g_solo_mode;
 }
 
@@ -1393,7 +1416,7 @@ static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
   if (!solo_mode() || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
   const DevInfo d = dev_info();
   if (!d.ok) return NHMC_ERR_UNSUPPORTED;
-  auto kern = gn_nhwc_slice_kernel<T, MODE, PHASE, true>;
+  auto kern = gn_nhwc_slice_kernel<T, MODE, PHASE, 1>;
   static int static_smem = -1;
   if (static_smem < 0) {
     cudaFuncAttributes fa;
@@ -1428,7 +1451,56 @@ static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
     best_cs = cs; best_threads = threads; best_slab = slab;
     if ((int64_t)batch * cs >= (int64_t)d.sms - 20) break;           // enough CTAs: keep the widest such slice
   }
-  if (!best_cs) return NHMC_ERR_UNSUPPORTED;
+  if (!best_cs) {
+    // ---- one thread-block cluster per unit (2, 4 or 8 CTAs of <= 64 KiB each): the 64x64 maps ----
+    // measured (tools/kernel_microbench.py --small --warm --graph-calls 20 --solo 1/2): wins on the 64x64 maps with >= 64-byte
+    // runs per pixel while x (+ dy) stay <= 36 MB in total (10.2 vs 15.2 us forward, 24.4 vs 26.9 us backward at
+    // [8,256,64,64]); loses on 32x32 maps (resident kernel: 16.5 vs 22.6 us), with 32-byte runs and beyond that size
+    if (solo_mode() < 2 || a0.HW < 4096 || (int64_t)batch * a0.HW * a0.C * (int64_t)sizeof(T) * NSRC > ((int64_t)36 << 20)) return NHMC_ERR_UNSUPPORTED;
+    auto ckern = gn_nhwc_slice_kernel<T, MODE, PHASE, 2>;
+    static int c_static = -1;
+    if (c_static < 0) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, ckern) == cudaSuccess &&
+          cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes) == cudaSuccess)
+        c_static = (int)fa.sharedSizeBytes;
+      else { cudaGetLastError(); c_static = 1 << 30; }
+    }
+    if (c_static >= (1 << 30)) return NHMC_ERR_UNSUPPORTED;
+    for (int cs = 1; cs <= a0.G; cs <<= 1) {                       // widest slice first
+      if (a0.G % cs) continue;
+      const int Cs = a0.C / cs;
+      if (Cs % Cg || Cs % V || (int64_t)Cs * sizeof(T) < 64) continue;
+      const int cvec = Cs / V;
+      if (cvec > kSliceThreads) continue;
+      bool ok = true;
+      for (int cv = 0; cv < cvec && ok; ++cv) ok = ((cv * V + V - 1) / Cg - (cv * V) / Cg) <= 1;
+      if (!ok) continue;
+      const int rows = kSliceThreads / cvec, threads = rows * cvec;
+      for (int nb = 2; nb <= 8; nb <<= 1) {
+        const int64_t rows_per_cta = (a0.HW + nb - 1) / nb;
+        const int64_t n_pass = (rows_per_cta + rows - 1) / rows;
+        const int64_t slab = ((n_pass * threads * 16 + 127) / 128) * 128;
+        if (slab * NSRC > 65536) continue;
+        if ((a0.HW + rows_per_cta - 1) / rows_per_cta != nb) continue;      // every rank owns rows
+        GnSliceArgs r{};
+        r.a = a0;
+        r.cs = cs; r.Cs = Cs; r.nb = nb; r.rows_per_cta = rows_per_cta;
+        r.chunk_passes = (int)((n_pass + 3) / 4);
+        r.total_ctas = (unsigned int)(batch * cs * nb);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(r.total_ctas); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)slab * NSRC; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)nb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, ckern, &cfg) != cudaSuccess || n_clusters < 1) { cudaGetLastError(); continue; }
+        return cuda_status(cudaLaunchKernelEx(&cfg, ckern, r), "gn cluster-unit launch");
+      }
+    }
+    return NHMC_ERR_UNSUPPORTED;
+  }
   GnSliceArgs r{};
   r.a = a0;
   r.cs = best_cs; r.Cs = a0.C / best_cs; r.nb = 1; r.rows_per_cta = a0.HW;
@@ -1631,7 +1703,7 @@ extern "C" int nhmc_gn_check(void) {
 
 extern "C" int nhmc_gn_set_solo(int on) {
   const int prev = solo_mode();
-  g_solo_mode = on ? 1 : 0;
+  g_solo_mode = on < 0 ? 0 : (on > 2 ? 2 : on);
   return prev;
 }
 

@@ -180,13 +180,13 @@ def test_resample_and_split_kernels(dtype):
     assert ga.is_contiguous(memory_format=torch.channels_last) and gb.is_contiguous(memory_format=torch.channels_last)
 
 
-@pytest.mark.parametrize("resident", [4, 3, 2, 1, 0])
+@pytest.mark.parametrize("resident", [5, 4, 3, 2, 1, 0])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode", [0, 2])
 @pytest.mark.parametrize("shape", [(8, 128, 128, 128), (3, 384, 64, 64), (2, 256, 256, 256), (5, 1024, 16, 16), (2, 128, 33, 7),
                                    (8, 512, 8, 8), (2, 224, 32, 32), (8, 768, 16, 16), (8, 256, 64, 64)])
 def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
-    """Channels-last GroupNorm on every execution path (4 = default: one-CTA-per-unit kernel for the small maps first;
+    """Channels-last GroupNorm on every execution path (5 = + cluster-per-unit kernel for the 64x64 maps; 4 = one-CTA-per-unit kernel for the small maps first;
     3..1 = shared-memory resident kernels; 0 = statistics + apply kernels): samples spanning many CTAs, a sample filling
     the whole chip, ragged pixel counts, 24-channel groups, the folded conv bias and the fused skip-gradient add;
     repeated calls check that the self-resetting counters reset."""
@@ -208,7 +208,7 @@ def test_group_norm_channels_last_paths(resident, dtype, mode, shape):
     (dxr,) = torch.autograd.grad(yr, xr, dy.float())
     dxr = dxr + add.float()
     prev = _lib.lib().nhmc_gn_set_resident(min(resident, 3))
-    prev_solo = _lib.lib().nhmc_gn_set_solo(1 if resident == 4 else 0)
+    prev_solo = _lib.lib().nhmc_gn_set_solo(2 if resident == 5 else (1 if resident == 4 else 0))
     try:
         for rep in range(3):
             y = torch.empty_like(x); dx = torch.empty_like(x); stats = torch.empty(B, 32, 2, device="cuda")

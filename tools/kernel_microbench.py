@@ -70,7 +70,7 @@ def main():
     ap.add_argument("--chains", type=int, default=64)
     ap.add_argument("--shape", default="", help="GroupNorm: only this B,C,H (e.g. 8,128,256)")
     ap.add_argument("--resident", type=int, default=1, help="GroupNorm: 1 = shared-memory resident single kernel, 0 = statistics + apply kernels")
-    ap.add_argument("--solo", type=int, default=1, help="GroupNorm: 1 = one-CTA-per-unit kernel for the small maps (default), 0 = off")
+    ap.add_argument("--solo", type=int, default=2, help="GroupNorm: 1 = one-CTA-per-unit kernel for the small maps, 2 = + cluster-per-unit kernel for the 64x64 maps, 0 = off")
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the U-Net epilogue kernels (1 = default)")
     ap.add_argument("--warm", action="store_true", help="no L2 flush between repetitions (inputs L2-resident, as inside the U-Net for the small maps)")
     ap.add_argument("--small", action="store_true", help="GroupNorm: the small-map shapes of the ffhq_10m U-Net at 8 chains")
@@ -90,7 +90,7 @@ def main():
         shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]
         if a.small:
             shapes = [(8, 512, 8), (8, 1024, 8), (8, 256, 16), (8, 512, 16), (8, 768, 16), (8, 1024, 16), (8, 256, 32), (8, 512, 32),
-                      (8, 768, 32), (8, 128, 64), (8, 256, 64), (1, 512, 8), (1, 256, 32)]
+                      (8, 768, 32), (8, 128, 64), (8, 256, 64), (8, 512, 64), (8, 128, 128), (1, 512, 8), (1, 256, 32)]
         if a.shape:
             shapes = [tuple(int(v) for v in a.shape.split(","))]
         for (B, C, H) in shapes:
