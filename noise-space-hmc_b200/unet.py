@@ -372,7 +372,7 @@ class ResBlock(nn.Module):
             scale, shift = e[:, : self.out_channels], e[:, self.out_channels:]       # strided views, no split copies
             h = group_norm_act(h, self.out_layers[0], _lib.GN_FILM_SILU, scale, shift, in_bias=b1)
         else:   # h + emb_out (openaimodel.py:274-276): folded into the norm as a per-sample bias, no broadcast-add pass
-            h = group_norm_act(h, self.out_layers[0], _lib.GN_SILU, in_bias=(e + b1).contiguous())
+            h = group_norm_act(h, self.out_layers[0], _lib.GN_SILU, in_bias=e)       # e already holds emb_out + b1 (_emb_projection)
         h = _conv_nobias(self.out_layers[3], h)
         if xs is not None:                       # skip 1x1 conv of cat([xa, xb]) = conv(xa, W[:, :c0]) + conv(xb, W[:, c0:])
             w0, w1 = self._split_skip_weights(xs[0].shape[1])
@@ -524,15 +524,23 @@ class UNetModel(nn.Module):
             blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
             W = torch.cat([m.emb_layers[1].weight.detach() for m in blocks], 0).contiguous()
             b = torch.cat([m.emb_layers[1].bias.detach() for m in blocks], 0).contiguous()
+            # additive-embedding blocks (openaimodel.py:274-276) normalise conv1(h) + b1 + emb_out: b1 (fp32) is added to the
+            # whole projection ONCE, so the per-sample norm bias is a view of it (no add per block and call)
+            b1_all = None
+            if any(not m.film for m in blocks):
+                b1_all = torch.cat([torch.zeros_like(m.emb_layers[1].bias, dtype=torch.float32) if m.film else
+                                    m.in_layers[2].bias.detach().float() for m in blocks], 0).contiguous()
             offs, o = [], 0
             for m in blocks:
                 n = m.emb_layers[1].weight.shape[0]
                 offs.append((m, o, n))
                 o += n
-            cache = (W, b, offs)
+            cache = (W, b, offs, b1_all)
             self._emb_cache = cache
-        W, b, offs = cache
+        W, b, offs, b1_all = cache
         e_all = F.linear(emb_act, W, b).float()
+        if b1_all is not None:
+            e_all = e_all + b1_all
         return {m: e_all[:, o: o + n] for m, o, n in offs}
 
     def _embeddings(self, timesteps):
