@@ -111,6 +111,9 @@ struct GnArgs {
   int C, G; int64_t HW; float eps;
   int64_t film_stride;  // elements between two samples' rows of scale / shift (>= C)
   int b0;            // first sample of this launch (two-kernel path launched per L2-sized group of samples)
+  int reps;          // statistics + apply kernels: replicas of the fp64 accumulators (CTA blk adds to replica blk % reps of
+                     // its sample, slot = replica * gridDim.y + sample; 0 or 1 = none): spreads the atomics of the many CTAs
+                     // of one sample (B = 1: 444) over more addresses
   int rows_per_cta_iter;  // pixel rows covered by one CTA pass (channels-last)
   int64_t rows_per_cta;   // pixel rows owned by a CTA (channels-last)
 };
@@ -342,8 +345,9 @@ gn_nhwc_stats_kernel(GnArgs a) {
     double t0 = 0.0, t1 = 0.0;
     for (int c = g * Cg; c < (g + 1) * Cg; ++c)
       for (int r = 0; r < rows; ++r) { t0 += (double)sm0[(size_t)r * a.C + c]; t1 += (double)sm1[(size_t)r * a.C + c]; }
-    atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
-    atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
+    const int64_t slot = a.reps > 1 ? (int64_t)(blk % a.reps) * gridDim.y + b : b;
+    atomicAdd(a.partials + (slot * 64 + g) * 2, t0);
+    atomicAdd(a.partials + (slot * 64 + g) * 2 + 1, t1);
   }
 }
 
@@ -367,8 +371,12 @@ gn_nhwc_apply_kernel(GnArgs a) {
   if (threadIdx.x < a.G) {
     const int g = threadIdx.x;
     const double inv_n = 1.0 / n;
-    const double a0 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2) * inv_n;
-    const double a1 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1) * inv_n;
+    double a0 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2), a1 = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
+    for (int rep = 1; rep < a.reps; ++rep) {
+      const int64_t slot = (int64_t)rep * gridDim.y + b;
+      a0 += __ldcg(a.partials + (slot * 64 + g) * 2); a1 += __ldcg(a.partials + (slot * 64 + g) * 2 + 1);
+    }
+    a0 *= inv_n; a1 *= inv_n;
     if (PHASE == 0) {
       double var = a1 - a0 * a0; if (var < 0.0) var = 0.0;
       g_mean[g] = (float)a0; g_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
@@ -458,6 +466,10 @@ gn_nhwc_apply_kernel(GnArgs a) {
         a.stats[((int64_t)b * a.G + g) * 2 + 1] = g_rstd[g];
       }
       acc[0] = 0.0; acc[1] = 0.0;
+      for (int rep = 1; rep < a.reps; ++rep) {
+        double* racc = a.partials + (((int64_t)rep * gridDim.y + b) * 64 + g) * 2;
+        racc[0] = 0.0; racc[1] = 0.0;
+      }
     }
   }
 }
@@ -484,6 +496,9 @@ struct GnResArgs {
   unsigned int* arrive;     // [B]   CTAs of the sample whose partial sums are published
   unsigned int* done;       // [B]   CTAs of the sample that have read the totals (wraps to 0 by itself)
   unsigned int* err;        // [1]   set to 1 if a wait timed out
+  int reps;                 // replicas of the fp64 accumulators per (sample, group): CTA blk adds to replica blk % reps, so that
+                            // hundreds of CTAs of one sample (B = 1: 592) do not serialise on 64 addresses; readers sum them
+  int batch;                // samples of this launch (replica r of sample b lives in accumulator slot r * batch + b)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -534,8 +549,9 @@ __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (
     if (CLUSTER) {
       g_part[g][0] = t0; g_part[g][1] = t1;        // read by every CTA of the cluster through DSMEM
     } else if (r.nb > 1) {
-      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2, t0);
-      atomicAdd(a.partials + ((int64_t)b * 64 + g) * 2 + 1, t1);
+      const int64_t slot = (int64_t)(blockIdx.x % (unsigned)r.reps) * r.batch + b;
+      atomicAdd(a.partials + (slot * 64 + g) * 2, t0);
+      atomicAdd(a.partials + (slot * 64 + g) * 2 + 1, t1);
       __threadfence();
     } else {
       g_acc[g][0] = t0; g_acc[g][1] = t1;
@@ -569,15 +585,22 @@ __device__ __forceinline__ void group_totals(const float (&s0)[V], const float (
     __syncthreads();
     if (threadIdx.x < a.G) {
       const int g = threadIdx.x;
-      g_acc[g][0] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2);
-      g_acc[g][1] = __ldcg(a.partials + ((int64_t)b * 64 + g) * 2 + 1);
+      double t0 = 0.0, t1 = 0.0;
+      for (int rep = 0; rep < r.reps; ++rep) {       // fixed order: deterministic given the replica contents
+        const int64_t slot = (int64_t)rep * r.batch + b;
+        t0 += __ldcg(a.partials + (slot * 64 + g) * 2); t1 += __ldcg(a.partials + (slot * 64 + g) * 2 + 1);
+      }
+      g_acc[g][0] = t0; g_acc[g][1] = t1;
     }
     __syncthreads();
     // the last CTA of the sample to have read the totals re-zeroes them for the next call on this stream
     if (threadIdx.x == 0) {
       const bool last = atomicInc(r.done + b, (unsigned int)(r.nb - 1)) == (unsigned int)(r.nb - 1);
       if (last) {
-        for (int g = 0; g < a.G; ++g) { a.partials[((int64_t)b * 64 + g) * 2] = 0.0; a.partials[((int64_t)b * 64 + g) * 2 + 1] = 0.0; }
+        for (int rep = 0; rep < r.reps; ++rep) {
+          const int64_t slot = (int64_t)rep * r.batch + b;
+          for (int g = 0; g < a.G; ++g) { a.partials[(slot * 64 + g) * 2] = 0.0; a.partials[(slot * 64 + g) * 2 + 1] = 0.0; }
+        }
         r.arrive[b] = 0u;
       }
     }
@@ -1270,6 +1293,7 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
       const int64_t n_pass = (rows_per_cta * row_bytes + pass_bytes - 1) / pass_bytes;
       r.chunk_passes = (int)((n_pass + kResChunks - 1) / kResChunks);
       r.total_ctas = (unsigned int)(nb * batch);
+      r.reps = 1; r.batch = batch;
       cudaLaunchConfig_t cfg{};
       cfg.gridDim = dim3(r.total_ctas); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = (size_t)slab * NSRC; cfg.stream = st;
       cudaLaunchAttribute attr[1];
@@ -1314,6 +1338,9 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     const int64_t n_pass = (rows_per_cta * row_bytes + pass_bytes - 1) / pass_bytes;
     r.chunk_passes = (int)((n_pass + kResChunks - 1) / kResChunks);
     r.total_ctas = (unsigned int)(nb * batch);
+    r.batch = batch;
+    r.reps = (int)(nb >= 64 ? 8 : (nb >= 16 ? 4 : 1));             // replicas only where a sample has many CTAs
+    while (r.reps > 1 && (int64_t)r.reps * batch > s.batch) r.reps >>= 1;
     r.ticket = s.res; r.err = s.res + 1; r.arrive = s.res + 4; r.done = s.res + 4 + s.batch;
     kern<<<r.total_ctas, threads, dyn, st>>>(r);
     return NHMC_LAUNCH_CHECK();
@@ -1554,6 +1581,8 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   a.rows_per_cta = rows_per_cta;
   a.rows_per_cta_iter = rows;
   a.b0 = 0;
+  a.reps = nblk >= 64 ? 8 : (nblk >= 16 ? 4 : 1);
+  while (a.reps > 1 && (int64_t)a.reps * batch > s.batch) a.reps >>= 1;
   const dim3 grid((unsigned)nblk, (unsigned)batch);
   if (int e = cuda_status(launch_pdl(gn_nhwc_stats_kernel<T, MODE, PHASE>, grid, dim3(threads), red, st, a), "gn statistics launch")) return e;
   if (PHASE == 1 && a.add2) {
