@@ -9,6 +9,7 @@
 // the images is made.  The SVD factor tables are inputs: torch.svd signs / tie order are
 // implementation-defined, so they are built once by the caller and shared with the checker.
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace nhmc {
 
@@ -134,13 +135,99 @@ static GemmArgs right(const float* X, const float* M, bool trans, float* out, in
   return a;
 }
 
+// =====================================================================================
+// Tensor-core path (gemm_tc.cu): every product of the chains below is C = A * B^T with BOTH operands K-major, so
+// the chains are ordered right-factor first and alternate transposed / row-major results:
+//   S^T = (X R)^T ; W^T = (gain .* (L S))^T ; T = L' W ; out = T R'^T
+// (matrix products are associative; the result differs from the reference's left-to-right evaluation only by fp32
+// rounding).  Operands travel as (hi, lo) tf32 plane pairs; the factor tables are split (and transposed where the
+// chain wants them) by one small kernel per table at the head of every call -- the caller owns all memory, so the
+// split tables live in the call's workspace.
+// =====================================================================================
+namespace {
+
+struct TcWs {                    // floats
+  float* tab[8];                 // plane pairs of V2^T, V1^T, U1, U2, U2^T, U1^T, V1, V2     (each 2 * D * D)
+  float *xs, *t0, *t1, *rr;      // plane pairs of [mats][D][D]
+  int64_t P, DD;
+};
+
+static inline size_t tc_ws_floats(int64_t mats, int64_t D) { return (size_t)(16 * D * D + 8 * mats * D * D); }
+
+static TcWs tc_ws(float* base, int64_t mats, int64_t D) {
+  TcWs w; w.DD = D * D; w.P = mats * w.DD;
+  for (int i = 0; i < 8; ++i) w.tab[i] = base + (int64_t)i * 2 * w.DD;
+  float* d = base + 16 * w.DD;
+  w.xs = d; w.t0 = d + 2 * w.P; w.t1 = d + 4 * w.P; w.rr = d + 6 * w.P;
+  return w;
+}
+
+static TcOperand tab_op(const float* p, int rows, int cols) { TcOperand o{p, rows, cols, 0, (int64_t)rows * cols}; return o; }
+static TcOperand dat_op(const float* p, int rows, int cols, int64_t mats) {
+  TcOperand o{p, rows, cols, (int64_t)rows * cols, mats * rows * cols}; return o;
+}
+
+static TcGemm tc_base(TcOperand A, TcOperand B, int mats, int C, float* out, bool planes, bool transposed) {
+  TcGemm g{};
+  g.A = A; g.B = B; g.mats = mats; g.channels = C; g.epi = TC_EPI_NONE; g.out_transposed = transposed ? 1 : 0;
+  g.out_hi = out; g.out_lo = planes ? out + (int64_t)mats * A.rows * B.rows : nullptr;
+  g.out_mat_stride = (int64_t)A.rows * B.rows;
+  return g;
+}
+
+// tables of the forward chain (first = true) or of the adjoint chain
+static int tc_tables(const nhmc_op* op, const TcWs& w, bool fwd, cudaStream_t st) {
+  const int D = op->img_dim;
+  struct { const float* src; int idx; int tr; } f[4] = {{op->V2, 0, 1}, {op->V1, 1, 1}, {op->U1, 2, 0}, {op->U2, 3, 0}},
+                                                 b[4] = {{op->U2, 4, 1}, {op->U1, 5, 1}, {op->V1, 6, 0}, {op->V2, 7, 0}};
+  for (int i = 0; i < 4; ++i) {
+    const auto& t = fwd ? f[i] : b[i];
+    if (int e = tc_split_table_launch(t.src, w.tab[t.idx], w.tab[t.idx] + w.DD, D, D, t.tr, st)) return e;
+  }
+  return NHMC_OK;
+}
+
+// chain on split input `in` (plane pair [mats][D][D]):  fwd: U1 (gain .* (V1^T in V2)) U2^T ;  adjoint: V1 (gain .* (U1^T in U2)) V2^T.
+// The last product is configured by `last` (epilogue, outputs) and launched here.
+static int tc_chain(const nhmc_op* op, const TcWs& w, const float* in, const float* gain, bool fwd, TcGemm last, int mats,
+                    cudaStream_t st) {
+  const int D = op->img_dim, C = op->channels;
+  const int o = fwd ? 0 : 4;
+  TcGemm g1 = tc_base(dat_op(in, D, D, mats), tab_op(w.tab[o + 0], D, D), mats, C, w.t0, true, true);       // S^T = (in R)^T
+  if (int e = tc_gemm_launch(g1, st)) return e;
+  TcGemm g2 = tc_base(tab_op(w.tab[o + 1], D, D), dat_op(w.t0, D, D, mats), mats, C, w.t1, true, true);     // (gain .* (L S))^T
+  g2.epi = TC_EPI_GAIN; g2.gain = gain;
+  if (int e = tc_gemm_launch(g2, st)) return e;
+  TcGemm g3 = tc_base(tab_op(w.tab[o + 2], D, D), dat_op(w.t1, D, D, mats), mats, C, w.t0, true, false);    // T = L' W
+  if (int e = tc_gemm_launch(g3, st)) return e;
+  last.A = dat_op(w.t0, D, D, mats); last.B = tab_op(w.tab[o + 3], D, D);                                   // out = T R'^T
+  last.mats = mats; last.channels = C; last.out_mat_stride = (int64_t)D * D;
+  return tc_gemm_launch(last, st);
+}
+
+}  // namespace
+
+static bool use_tc(const nhmc_op* op) {
+  const int D = op->img_dim, d = op->kind == NHMC_OP_SEPMAT ? D / op->ratio : D;
+  return tc_gemm_supported(D, D, D) && d > 0 && d % 4 == 0;
+}
+
 size_t deblur_workspace_bytes(const nhmc_op* op, int n_chains) {
-  return (size_t)3 * n_chains * op->channels * op->img_dim * op->img_dim * sizeof(float) + 256;
+  const size_t mats = (size_t)n_chains * op->channels, D = op->img_dim;
+  const size_t simt = (size_t)3 * mats * D * D, tc = tc_ws_floats(mats, D);
+  return (simt > tc ? simt : tc) * sizeof(float) + 256;
 }
 
 // y = U1 (gain .* (V1^T x V2)) U2^T       (Hfuncs.py:65-71 with Vt :493-499, U :501-509)
 int deblur_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  if (use_tc(op)) {
+    const TcWs w = tc_ws(reinterpret_cast<float*>(ws), mats, D);
+    if (int e = tc_tables(op, w, true, st)) return e;
+    if (int e = tc_split_launch(x, w.xs, w.xs + w.P, w.P, 0, st)) return e;
+    TcGemm last{}; last.out_hi = y;
+    return tc_chain(op, w, w.xs, op->gain, true, last, mats, st);
+  }
   float* t0 = reinterpret_cast<float*>(ws);
   float* t1 = t0 + (size_t)mats * D * D;
   launch<EPI_NONE, false>(left(op->V1, true, x, t0, D, C), mats, st);
@@ -154,6 +241,13 @@ int deblur_forward(const nhmc_op* op, const float* x, float* y, int n_chains, vo
 // out = V1 (gain' .* (U1^T r U2)) V2^T   with gain' = gain (H^T, Hfuncs.py:73-79) or 1/gain (H^+, :81-91)
 int deblur_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  if (use_tc(op)) {
+    const TcWs w = tc_ws(reinterpret_cast<float*>(ws), mats, D);
+    if (int e = tc_tables(op, w, false, st)) return e;
+    if (int e = tc_split_launch(r, w.xs, w.xs + w.P, w.P, 0, st)) return e;
+    TcGemm last{}; last.out_hi = out;
+    return tc_chain(op, w, w.xs, pinv ? op->gain_pinv : op->gain, false, last, mats, st);
+  }
   float* t0 = reinterpret_cast<float*>(ws);
   float* t1 = t0 + (size_t)mats * D * D;
   launch<EPI_NONE, false>(left(op->U1, true, r, t0, D, C), mats, st);
@@ -172,26 +266,38 @@ __global__ void clamp_copy_kernel(const float* __restrict__ x, float* __restrict
 int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
                      int n_chains, void* workspace, cudaStream_t st) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
-  NHMC_CHECK_ARG(((D + TM - 1) / TM) * ((D + TN - 1) / TN) * C <= kMaxBlocksPerChain, "image too large for the deblur loss reduction");
   const RedWs rw = red_ws(workspace, n_chains);
-  float* t0 = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
-  float* t1 = t0 + (size_t)mats * D * D;
-  float* rr = t1 + (size_t)mats * D * D;
-  // forward through clamp(x_hat)
-  GemmArgs g1 = left(op->V1, true, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
-  launch<EPI_NONE, true>(g1, mats, st);
-  GemmArgs g2 = right(t0, op->V2, false, t1, D, C); g2.gain = op->gain;
-  launch<EPI_GAIN, false>(g2, mats, st);
-  launch<EPI_NONE, false>(left(op->U1, false, t1, t0, D, C), mats, st);
-  GemmArgs g4 = right(t0, op->U2, true, rr, D, C); g4.y = y; g4.loss = loss; g4.ws = rw;
-  launch<EPI_RESID, false>(g4, mats, st);
-  // adjoint of the residual
-  launch<EPI_NONE, false>(left(op->U1, true, rr, t0, D, C), mats, st);
-  GemmArgs g6 = right(t0, op->U2, false, t1, D, C); g6.gain = op->gain;
-  launch<EPI_GAIN, false>(g6, mats, st);
-  launch<EPI_NONE, false>(left(op->V1, false, t1, t0, D, C), mats, st);
-  GemmArgs g8 = right(t0, op->V2, true, g, D, C); g8.xhat = x_hat; g8.no_clamp = op->no_clamp;
-  launch<EPI_GRAD, false>(g8, mats, st);
+  float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
+  if (use_tc(op)) {
+    const TcWs w = tc_ws(scratch, mats, D);
+    if (int e = tc_tables(op, w, true, st)) return e;
+    if (int e = tc_tables(op, w, false, st)) return e;
+    if (int e = tc_split_launch(x_hat, w.xs, w.xs + w.P, w.P, op->no_clamp ? 0 : 1, st)) return e;   // clamp(x_hat), split
+    TcGemm f{}; f.epi = TC_EPI_RESID; f.y = y; f.loss = loss; f.ws = rw; f.out_hi = w.rr; f.out_lo = w.rr + w.P;
+    if (int e = tc_chain(op, w, w.xs, op->gain, true, f, mats, st)) return e;                          // R = y - H(xc), loss
+    TcGemm b{}; b.epi = TC_EPI_GRAD; b.xhat = x_hat; b.no_clamp = op->no_clamp; b.out_hi = g;
+    if (int e = tc_chain(op, w, w.rr, op->gain, false, b, mats, st)) return e;                         // g = -2 H^T R .* mask
+  } else {
+    NHMC_CHECK_ARG(((D + TM - 1) / TM) * ((D + TN - 1) / TN) * C <= kMaxBlocksPerChain, "image too large for the deblur loss reduction");
+    float* t0 = scratch;
+    float* t1 = t0 + (size_t)mats * D * D;
+    float* rr = t1 + (size_t)mats * D * D;
+    // forward through clamp(x_hat)
+    GemmArgs g1 = left(op->V1, true, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
+    launch<EPI_NONE, true>(g1, mats, st);
+    GemmArgs g2 = right(t0, op->V2, false, t1, D, C); g2.gain = op->gain;
+    launch<EPI_GAIN, false>(g2, mats, st);
+    launch<EPI_NONE, false>(left(op->U1, false, t1, t0, D, C), mats, st);
+    GemmArgs g4 = right(t0, op->U2, true, rr, D, C); g4.y = y; g4.loss = loss; g4.ws = rw;
+    launch<EPI_RESID, false>(g4, mats, st);
+    // adjoint of the residual
+    launch<EPI_NONE, false>(left(op->U1, true, rr, t0, D, C), mats, st);
+    GemmArgs g6 = right(t0, op->U2, false, t1, D, C); g6.gain = op->gain;
+    launch<EPI_GAIN, false>(g6, mats, st);
+    launch<EPI_NONE, false>(left(op->V1, false, t1, t0, D, C), mats, st);
+    GemmArgs g8 = right(t0, op->V2, true, g, D, C); g8.xhat = x_hat; g8.no_clamp = op->no_clamp;
+    launch<EPI_GRAD, false>(g8, mats, st);
+  }
   if (xc_out) {
     const int64_t total = (int64_t)mats * D * D;
     clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
@@ -203,8 +309,33 @@ int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, floa
 // Separable matrix operator Y_c = L X_c L^T (bicubic "SRConv", Hfuncs.py:527-607): in the reference's SVD form
 // H = U S V^T with the permutation of :558-559 this is L = U_small diag(s) V_small[:, :d]^T, a d x D matrix
 // (d = D / stride) applied on both sides; H^T R = L^T R L, H^+ Y = P Y P^T with P = V_small[:, :d] diag(1/s) U_small^T.
-// L and P are built by the caller from the reference's own SVD factors.  Same fp32 SIMT GEMM as above, rectangular.
+// L and P are built by the caller from the reference's own SVD factors.  Tensor-core path: two products per
+// application, S^T = (X Rt^T)^T then out = Lt S (Rt, Lt row-major tables whose K dimension is contiguous).
 // =====================================================================================
+namespace {
+
+// out[mats][m2 x n1] = Lt (m2 x k2) * in[mats] (k2 x k1) * Rt^T (k1 x n1);  Lt given K-major [m2][k2], Rt K-major [n1][k1].
+// `in` is a plane pair; st_t = plane-pair scratch for S^T [mats][n1][k2]; `last` carries the epilogue / outputs.
+static int tc_sandwich(const float* in, int k2, int k1, const float* Rt, int n1, const float* Lt, int m2, float* st_t,
+                       TcGemm last, int mats, int C, cudaStream_t st) {
+  TcGemm g1 = tc_base(dat_op(in, k2, k1, mats), tab_op(Rt, n1, k1), mats, C, st_t, true, true);            // S^T [n1][k2]
+  if (int e = tc_gemm_launch(g1, st)) return e;
+  last.A = tab_op(Lt, m2, k2); last.B = dat_op(st_t, n1, k2, mats);
+  last.mats = mats; last.channels = C; last.out_mat_stride = (int64_t)m2 * n1;
+  return tc_gemm_launch(last, st);
+}
+
+struct SepWs { float *L, *Lt, *P, *in, *s, *rr; int64_t dD; };
+static inline size_t sep_ws_floats(int64_t mats, int64_t D, int64_t d) { return (size_t)(6 * d * D + 2 * mats * D * D + 2 * mats * d * D + 2 * mats * d * d); }
+static SepWs sep_ws(float* base, int64_t mats, int64_t D, int64_t d) {
+  SepWs w; w.dD = d * D;
+  w.L = base; w.Lt = base + 2 * w.dD; w.P = base + 4 * w.dD;
+  w.in = base + 6 * w.dD; w.s = w.in + 2 * mats * D * D; w.rr = w.s + 2 * mats * d * D;
+  return w;
+}
+
+}  // namespace
+
 // out[mats][M x N] = Lm(M x K) * X[mats][K x N]          (Lm given row-major [rows x cols], optionally transposed)
 static GemmArgs left_rect(const float* Lm, int rows, int cols, bool trans, const float* X, float* out, int N, int C) {
   GemmArgs a{};
@@ -226,11 +357,19 @@ static GemmArgs right_rect(const float* X, int M, const float* Rm, int rows, int
 
 size_t sepmat_workspace_bytes(const nhmc_op* op, int n_chains) {
   const size_t D = op->img_dim, d = op->img_dim / op->ratio, mats = (size_t)n_chains * op->channels;
-  return (2 * mats * d * D + mats * d * d) * sizeof(float) + 256;
+  const size_t simt = 2 * mats * d * D + mats * d * d, tc = sep_ws_floats(mats, D, d);
+  return (simt > tc ? simt : tc) * sizeof(float) + 256;
 }
 
 int sepmat_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
   const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
+  if (use_tc(op)) {
+    const SepWs w = sep_ws(reinterpret_cast<float*>(ws), mats, D, d);
+    if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
+    if (int e = tc_split_launch(x, w.in, w.in + (int64_t)mats * D * D, (int64_t)mats * D * D, 0, st)) return e;
+    TcGemm last{}; last.out_hi = y;
+    return tc_sandwich(w.in, D, D, w.L, d, w.L, d, w.s, last, mats, C, st);                                   // L (X L^T)
+  }
   float* t0 = reinterpret_cast<float*>(ws);                                       // [mats][d x D]
   launch<EPI_NONE, false>(left_rect(op->U1, d, D, false, x, t0, D, C), mats, st);             // L X
   launch<EPI_NONE, false>(right_rect(t0, d, op->U1, d, D, true, y, C), mats, st);             // (L X) L^T
@@ -239,6 +378,16 @@ int sepmat_forward(const nhmc_op* op, const float* x, float* y, int n_chains, vo
 
 int sepmat_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
   const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
+  if (use_tc(op)) {
+    const SepWs w = sep_ws(reinterpret_cast<float*>(ws), mats, D, d);
+    // H^T R = L^T R L: tables K-major = L^T [D][d];  H^+ Y = P Y P^T: tables K-major = P [D][d]
+    if (pinv) { if (int e = tc_split_table_launch(op->V1, w.P, w.P + w.dD, D, d, 0, st)) return e; }
+    else      { if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e; }
+    if (int e = tc_split_launch(r, w.rr, w.rr + (int64_t)mats * d * d, (int64_t)mats * d * d, 0, st)) return e;
+    const float* T = pinv ? w.P : w.Lt;
+    TcGemm last{}; last.out_hi = out;
+    return tc_sandwich(w.rr, d, d, T, D, T, D, w.s, last, mats, C, st);
+  }
   float* t0 = reinterpret_cast<float*>(ws);                                       // [mats][D x d]
   if (!pinv) {
     launch<EPI_NONE, false>(left_rect(op->U1, d, D, true, r, t0, d, C), mats, st);             // L^T R
@@ -253,18 +402,30 @@ int sepmat_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, 
 int sepmat_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
                      int n_chains, void* workspace, cudaStream_t st) {
   const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
-  NHMC_CHECK_ARG(((d + TM - 1) / TM) * ((d + TN - 1) / TN) * C <= kMaxBlocksPerChain, "measurement too large for the loss reduction");
   const RedWs rw = red_ws(workspace, n_chains);
-  float* t0 = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));   // [mats][d x D]
-  float* t1 = t0 + (size_t)mats * d * D;                                               // [mats][D x d]
-  float* rr = t1 + (size_t)mats * d * D;                                               // [mats][d x d]
-  GemmArgs g1 = left_rect(op->U1, d, D, false, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
-  launch<EPI_NONE, true>(g1, mats, st);                                                // L clamp(X)
-  GemmArgs g2 = right_rect(t0, d, op->U1, d, D, true, rr, C); g2.y = y; g2.loss = loss; g2.ws = rw;
-  launch<EPI_RESID, false>(g2, mats, st);                                              // R = y - (L X) L^T, loss
-  launch<EPI_NONE, false>(left_rect(op->U1, d, D, true, rr, t1, d, C), mats, st);      // L^T R
-  GemmArgs g4 = right_rect(t1, D, op->U1, d, D, false, g, C); g4.xhat = x_hat; g4.no_clamp = op->no_clamp;
-  launch<EPI_GRAD, false>(g4, mats, st);                                               // -2 (L^T R L) .* mask
+  float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
+  if (use_tc(op)) {
+    const SepWs w = sep_ws(scratch, mats, D, d);
+    if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
+    if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e;
+    if (int e = tc_split_launch(x_hat, w.in, w.in + (int64_t)mats * D * D, (int64_t)mats * D * D, op->no_clamp ? 0 : 1, st)) return e;
+    TcGemm f{}; f.epi = TC_EPI_RESID; f.y = y; f.loss = loss; f.ws = rw; f.out_hi = w.rr; f.out_lo = w.rr + (int64_t)mats * d * d;
+    if (int e = tc_sandwich(w.in, D, D, w.L, d, w.L, d, w.s, f, mats, C, st)) return e;                     // R = y - L xc L^T, loss
+    TcGemm b{}; b.epi = TC_EPI_GRAD; b.xhat = x_hat; b.no_clamp = op->no_clamp; b.out_hi = g;
+    if (int e = tc_sandwich(w.rr, d, d, w.Lt, D, w.Lt, D, w.s, b, mats, C, st)) return e;                   // -2 (L^T R L) .* mask
+  } else {
+    NHMC_CHECK_ARG(((d + TM - 1) / TM) * ((d + TN - 1) / TN) * C <= kMaxBlocksPerChain, "measurement too large for the loss reduction");
+    float* t0 = scratch;                                                                 // [mats][d x D]
+    float* t1 = t0 + (size_t)mats * d * D;                                               // [mats][D x d]
+    float* rr = t1 + (size_t)mats * d * D;                                               // [mats][d x d]
+    GemmArgs g1 = left_rect(op->U1, d, D, false, x_hat, t0, D, C); g1.no_clamp = op->no_clamp;
+    launch<EPI_NONE, true>(g1, mats, st);                                                // L clamp(X)
+    GemmArgs g2 = right_rect(t0, d, op->U1, d, D, true, rr, C); g2.y = y; g2.loss = loss; g2.ws = rw;
+    launch<EPI_RESID, false>(g2, mats, st);                                              // R = y - (L X) L^T, loss
+    launch<EPI_NONE, false>(left_rect(op->U1, d, D, true, rr, t1, d, C), mats, st);      // L^T R
+    GemmArgs g4 = right_rect(t1, D, op->U1, d, D, false, g, C); g4.xhat = x_hat; g4.no_clamp = op->no_clamp;
+    launch<EPI_GRAD, false>(g4, mats, st);                                               // -2 (L^T R L) .* mask
+  }
   if (xc_out) {
     const int64_t total = (int64_t)mats * D * D;
     clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
