@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the U-Net epilogue kernels (1 = library default)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-line", action="store_true", help="skip the fp32 (TF32 off) timing + bf16-vs-fp32 comparison that accompanies the bf16 line at N=1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-in-situ", action="store_true", help="skip the CUPTI breakdown of one step after the timed region")
     ap.add_argument("--profile-kernels", action="store_true", default=True)
@@ -146,7 +147,7 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.benchmark = True
-    _lib.lib().nhmc_set_pdl(args.pdl)
+    kernels.set_flags(0 if args.pdl else _lib.F_NO_PDL)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B, K, W = args.chains, args.steps, max(args.warmup, 3)
 
@@ -265,9 +266,9 @@ def run_ours(args, rank, world, local_rank):
         if use_graphs and args.pdl:
             # with programmatic dependent launch a kernel's CTAs are scheduled while its predecessor drains, so CUPTI's
             # per-kernel durations would include that wait: the breakdown is taken on a capture with plain launches
-            _lib.lib().nhmc_set_pdl(0)
+            kernels.set_flags(_lib.F_NO_PDL)
             g_plain, _ = smp.capture_profiled_step(_lib.LF_MIDDLE, events=False)
-            _lib.lib().nhmc_set_pdl(1)
+            kernels.set_flags(0)
             g_plain.replay(); torch.cuda.synchronize()
             step_p = g_plain.replay
         with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
@@ -321,6 +322,11 @@ def run_ours(args, rank, world, local_rank):
             ms_e = float(t.item())
         e2e = {"value": world * B * Ke / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(2 * xh.numel() * 4),
                "d2h_bytes_per_step": int(res["bytes"]), "steps": Ke, "ms_per_step": ms_e / Ke}
+
+    # ---- the same workload with an fp32 score network (TF32 off, the reference's precision: use_fp16 False) ----
+    fp32_line = None
+    if (not latent_wl and args.dtype == "bf16" and world == 1 and not args.no_fp32_line):
+        fp32_line = fp32_companion(args, dev, op, y, x_orig, x0, steps, smp, sigma_0, B, max(3, min(K, 5)))
 
     if rank != 0:
         if dist is not None:
@@ -394,12 +400,63 @@ def run_ours(args, rank, world, local_rank):
         "shares": shares,
         "unet": unet_rep,
         "finite": finite,
+        "fp32": fp32_line,
     }
     if not args.no_cpu_baseline and world >= 1:
         out["cpu_baseline"] = cpu_baseline(args.deg, steps_timed=1, warm=1)
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def fp32_companion(args, dev, op, y, x_orig, x0, steps, smp_bf16, sigma_0, B, K):
+    """The bf16 line's companion: the same step with an fp32 score network, TF32 off -- the reference's own
+    precision (config_ffhq.yml: use_fp16 False) -- timed the same way, plus how far one gradient evaluation of the bf16
+    network is from the fp32 one on the same state (the full-size parity tests assert these bounds: tests/test_fullsize_gpu.py)."""
+    from nhmc_b200 import _lib, kernels, sampler, unet
+    tf = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(1234)                                           # same initialisation as the bf16 model, kept in fp32
+        m32 = unet.create_model(**FFHQ, dtype=torch.float32)
+        unet.randomize_zero_tensors(m32, seed=1234)
+        m32.prepare(dev)
+        ev32 = sampler.GradEvaluator(m32, steps, op, y, x0.to(dev))
+        s32 = sampler.HMCSampler(x0.to(dev), ev32, 1.0, 0.05, sigma_0, sched=_lib.SCHED_PIXEL)
+        kernels.begin_iteration(s32.chains, _lib.SCHED_PIXEL)
+        s32.p.copy_(smp_bf16.p)
+        # one gradient evaluation of both networks at the same state
+        xs = smp_bf16.x_prop.clone()
+        l16, ga, gb, xc16 = smp_bf16.ev(xs)
+        l16, xc16, g16 = l16.clone(), xc16.clone(), (ga + gb).clone()
+        l32, ga, gb, xc32 = ev32(xs)
+        g32 = ga + gb
+        xo = x_orig.to(dev)
+        psnr = lambda a: 10 * torch.log10(1.0 / (((a + 1) / 2).clamp(0, 1) - ((xo + 1) / 2).clamp(0, 1)).pow(2).mean(dim=(1, 2, 3)))
+        cmp = {"psnr_diff_db_max": float((psnr(xc16) - psnr(xc32)).abs().max()), "x_hat_rms_diff": float((xc16 - xc32).pow(2).mean().sqrt()),
+               "loss_rel_diff_max": float(((l16 - l32).abs() / l32.abs()).max()),
+               "grad_cosine": float((g16 * g32).sum() / (g16.norm() * g32.norm())),
+               "note": "one gradient evaluation (3 U-Net forwards + VJPs) of the bf16 and the fp32 network at the same state; north star: PSNR "
+                       "difference < 0.05 dB.  With random weights the map is chaotic (17x gain before a hard clip), so whole "
+                       "trajectories agree statistically only (tests/test_fullsize_gpu.py)"}
+        s32.x_prop.copy_(xs)
+        s32.step(_lib.LF_FIRST)
+        s32.capture_graphs()
+        for _ in range(3):
+            s32.step(_lib.LF_MIDDLE)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            s32.step(_lib.LF_MIDDLE)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": K, "dtype": "f32 sampler state / fp32 score network (TF32 off)",
+                "bf16_vs_fp32": cmp}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf
 
 
 # ----------------------------------------------------------------------------------------------------

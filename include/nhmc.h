@@ -9,7 +9,10 @@
  * Conventions
  *  - every tensor argument is a raw DEVICE pointer plus explicit sizes; `stream` is a
  *    cudaStream_t (pass torch's current stream); nothing synchronises the device;
- *  - the caller owns every buffer, the library allocates nothing;
+ *  - the caller owns every buffer; the library allocates no device memory, keeps no mutable state between calls
+ *    (no setters, no environment switches: execution-path choices travel in a per-call `flags` word) and is
+ *    re-entrant: any number of host threads may call it concurrently as long as calls that run at the same time
+ *    on one device use different workspaces;
  *  - return value: 0 = OK, otherwise an NHMC_ERR_* code; nhmc_last_error() gives the text
  *    (thread-local); no C++ exception crosses the boundary;
  *  - per-chain scalars live in a device array of `nhmc_chain` (one entry per chain) so that
@@ -161,6 +164,9 @@ typedef struct nhmc_op {
   const float* gain_pinv;     /* deblur2d: [C,D,D] 1/D_c where non-zero else 0               */
   float coef[12];             /* color: [0..2] forward weights w_c (y = sum_c w_c x_c),      */
                               /*        [3..5] adjoint weights, [6..8] pseudo-inverse weights */
+  const float* tc_tables;     /* deblur2d / sepmat, optional: the tables nhmc_op_prepare_tables wrote (tf32 hi/lo     */
+                              /* splits of U1,V1,U2,V2 and their transposes for the tensor-core GEMMs); NULL: every   */
+                              /* call rebuilds them in its workspace                                                  */
 } nhmc_op;
 
 size_t nhmc_sizeof_op(void);
@@ -168,6 +174,10 @@ size_t nhmc_sizeof_op(void);
 /* measurement elements per chain (M) for this operator */
 int64_t nhmc_op_meas_size(const nhmc_op* op);
 size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains);
+/* Derived operator tables (caller-owned, written once): bytes needed (0: the operator has none) and the kernel launches
+ * that fill them; afterwards set op->tc_tables = tables. */
+size_t nhmc_op_tables_bytes(const nhmc_op* op);
+int nhmc_op_prepare_tables(const nhmc_op* op, void* tables, nhmc_stream_t stream);
 
 /* y = H(x) in the reference's layout (no clamp). Replaces H_functions.H (Hfuncs.py:65-71). */
 int nhmc_op_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* workspace,
@@ -232,31 +242,42 @@ int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const float* g_a,
 #define NHMC_GN_FILM_SILU 2
 #define NHMC_LAYOUT_NCHW 0
 #define NHMC_LAYOUT_NHWC 1
+/* GroupNorm scratch (fp64 accumulators, reduction tickets, barrier counters, the timeout flag): CALLER-OWNED device
+ * memory of nhmc_gn_workspace_bytes(max_batch) bytes, 16-byte aligned, zero-filled ONCE after allocation (everything in
+ * it resets itself).  Calls that may run concurrently (other streams / lanes / host threads) need separate workspaces;
+ * calls ordered on one stream share one.  `flags`: 0 = defaults, or a combination of */
+#define NHMC_F_NO_PDL (1u << 6)              /* plain launches instead of programmatic dependent launch (also pool2 / bias_add) */
+#define NHMC_GN_F_NO_RESIDENT (1u << 0)      /* channels-last: statistics + apply kernels only                              */
+#define NHMC_GN_F_NO_CLUSTER (1u << 1)       /* no thread-block-cluster variant of the shared-memory-resident kernel          */
+#define NHMC_GN_F_SLICE_BWD (1u << 2)        /* resident-by-channel-slice kernel for large backward tensors (off by default)   */
+#define NHMC_GN_F_SLICE_ALL (1u << 3)        /* ... and for large forward tensors                                              */
+#define NHMC_GN_F_NO_SOLO (1u << 4)          /* no one-CTA-per-unit kernel on the small maps                                   */
+#define NHMC_GN_F_NO_SOLO_CLUSTER (1u << 5)  /* no cluster-per-unit kernel on the 64x64 maps                                   */
+#define NHMC_GN_F_LANES_SHIFT 8              /* bits 8-10: (number of lanes - 1) this call shares the chip with (sizing only)  */
+size_t nhmc_gn_workspace_bytes(int max_batch);
 int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
                 const float* beta, const float* scale, const float* shift, int64_t film_stride,
                 const float* in_bias, int64_t in_bias_stride, float* stats_out,
-                int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream);
+                int batch, int channels, int64_t hw, int groups, float eps,
+                void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream);
 /* dx (and optionally dscale/dshift [B,C] fp32) given dy; weights are frozen on this path, so
  * no dgamma/dbeta.  dx_add (nullable, same dtype/layout as dx, channels-last only): a tensor added to
  * dx in the same pass -- the gradient arriving through the ResBlock's skip branch
  * (unet_ffhq.py:327), which autograd would otherwise add with a separate read-read-write pass.
+ * dx_add2 (channels-last, needs dx_add): a second tensor added in the same pass -- the gradient that reaches a block
+ * input through the U-Net's long skip connection (unet_ffhq.py:729-731).
  *
  * Channels-last execution: when one sample's slab fits in the shared memory of the chip (every
  * FFHQ-256 site except the backward of the two 256-channel 256x256 sites), ONE kernel reads the
  * tensor once into shared memory (TMA bulk copies), reduces, synchronises the CTAs of a sample
- * through a per-sample arrival counter and normalises out of shared memory: HBM traffic equals
- * the algorithmic bytes.  Otherwise a statistics kernel + an apply kernel (two reads). */
+ * (cluster barrier, or a per-sample arrival counter under a cooperative launch) and normalises out of shared
+ * memory: HBM traffic equals the algorithmic bytes.  Otherwise a statistics kernel + an apply kernel (two reads). */
 int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, void* dx,
                 const float* gamma, const float* beta, const float* scale, const float* shift,
                 int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats,
                 float* dscale, float* dshift,
                 const void* dx_add, const void* dx_add2, int batch, int channels, int64_t hw, int groups,
-                nhmc_stream_t stream);
-/* dx_add2 (channels-last, needs dx_add): a second tensor added to dx in the same pass -- the gradient that reaches a
- * block input through the U-Net's long skip connection (unet_ffhq.py:729-731), otherwise a read-read-write
- * accumulation pass of autograd's.  Takes the statistics + apply kernels. */
-/* 0 unless a per-sample barrier of the shared-memory-resident GroupNorm path ever timed out on the
- * current device (synchronises; for tests and debugging, not for the hot loop). */
+                void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream);
 /* GroupNorm over the VIRTUAL concatenation cat([x0, x1], channel) (the skip connections of the output
  * blocks, unet_ffhq.py:729-731): x0 [B, HW, c0] and x1 [B, HW, c1] are separate dense channels-last
  * tensors, y is the dense [B, HW, c0+c1] result the next convolution reads; gamma/beta/scale/shift index
@@ -266,33 +287,17 @@ int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const void* dy, 
 int nhmc_gn_cat_fwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, void* y,
                     const float* gamma, const float* beta, const float* scale, const float* shift,
                     int64_t film_stride, float* stats_out, int batch, int64_t hw, int groups, float eps,
-                    nhmc_stream_t stream);
+                    void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream);
 int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, const void* dy,
                     void* dx0, void* dx1, const float* gamma, const float* beta, const float* scale,
                     const float* shift, int64_t film_stride, const float* stats, const void* add0,
-                    const void* add1, int batch, int64_t hw, int groups, nhmc_stream_t stream);
-int nhmc_gn_check(void);
-/* Channels-last execution paths: 0 = statistics + apply kernels only; 1 = + the shared-memory-resident
- * single kernel with a global per-sample barrier; 2 = + its thread-block-cluster variant (one sample per
- * cluster of <= 8 CTAs, reduction over distributed shared memory); 3 (default) = + the resident-by-
- * channel-slice kernel for tensors beyond one wave (units of whole groups, >= 2 units on the chip at
- * once, x and dy read once).  Returns the previous setting.  For A/B measurements and tests. */
-int nhmc_gn_set_resident(int on);
-/* Programmatic dependent launch for the U-Net epilogue kernels (GroupNorm statistics / apply / one-CTA kernel, pooling,
- * residual add): 1 (default, NHMC_PDL=0 in the environment disables) launches them with the programmatic-stream-
- * serialization attribute so that a kernel's CTAs are scheduled while its predecessor drains; 0 = plain launches.
- * Returns the previous setting. */
-int nhmc_set_pdl(int on);
-/* 1: maps whose (sample, slice of whole groups) units fit one CTA's shared memory (8x8 .. 32x32 at FFHQ-256) take
- * the one-CTA-per-unit kernel (no inter-CTA barrier); 2 (default): in addition the 64x64 maps take the same kernel
- * with one thread-block cluster (2-8 CTAs, partial sums exchanged over distributed shared memory) per unit; 0: never.
- * Returns the previous setting. */
-int nhmc_gn_set_solo(int on);
-/* Lanes: a host that evaluates groups of chains on n_lanes streams at once (the reference evaluates one chain at a
- * time, main_sampling.py:704-713; chains are independent) announces which lane the GroupNorm calls that follow
- * belong to.  Every lane owns its accumulators / tickets, and the single-wave resident kernel sizes itself for
- * 1/n_lanes of the chip.  Default (0, 1).  At most 8 lanes. */
-int nhmc_gn_set_lane(int lane, int n_lanes);
+                    const void* add1, int batch, int64_t hw, int groups,
+                    void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream);
+/* Copies the workspace's timeout flag to *flag_out (device or pinned-host int32) on `stream`, without synchronising:
+ * non-zero = a barrier wait of a shared-memory-resident GroupNorm kernel timed out since the workspace was last
+ * zero-filled (the results of that call are invalid; zero-fill the workspace again before reuse).  The global-barrier
+ * kernel is launched cooperatively, so this is a backstop, not an expected event. */
+int nhmc_gn_check(const void* workspace, size_t workspace_bytes, int32_t* flag_out, nhmc_stream_t stream);
 
 /* K10 attention softmax epilogue (unet_ffhq.py:418-425): in place over the last dim of
  * logits [rows, T] (dtype f32/bf16/f16), computed in fp32; logits are multiplied by
@@ -313,16 +318,16 @@ int nhmc_softmax_bwd(int dtype, const void* probs, const void* dprobs, void* dlo
  *   split2 : backward of cat([a,b], channel): in [rows, c1+c2] -> out1 [rows, c1], out2 [rows, c2]
  * ---------------------------------------------------------------------------------------- */
 int nhmc_pool2_gather(int dtype, const void* in_big, void* out_small, int batch, int h_small,
-                      int w_small, int channels, float scale, nhmc_stream_t stream);
+                      int w_small, int channels, float scale, unsigned int flags, nhmc_stream_t stream);
 int nhmc_pool2_scatter(int dtype, const void* in_small, void* out_big, int batch, int h_small,
-                       int w_small, int channels, float scale, nhmc_stream_t stream);
+                       int w_small, int channels, float scale, unsigned int flags, nhmc_stream_t stream);
 int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows, int c1, int c2,
                 nhmc_stream_t stream);
 /* out[r, c] = a[r, c] (+ b[r, c] (+ c3[r, c])) (+ bias[c]): residual add of the ResBlock (unet_ffhq.py:327) with
  * the biases of the convolutions that produced the addends folded in; the third addend is the second half of a
  * skip 1x1 convolution applied block-wise to a virtual concatenation.  channels-last rows, out may alias a. */
 int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c3, const float* bias, void* out,
-                  int64_t rows, int channels, nhmc_stream_t stream);
+                  int64_t rows, int channels, unsigned int flags, nhmc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Latent path, first stage: nearest-codebook lookup of the VQ-f4 autoencoder

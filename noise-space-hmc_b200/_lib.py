@@ -15,6 +15,10 @@ SCHED_PIXEL, SCHED_LATENT = 0, 1
 OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE, OP_DENOISE, OP_COLOR, OP_SEPMAT, OP_CS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 GN_PLAIN, GN_SILU, GN_FILM_SILU = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+# per-call flag word of the U-Net epilogue entry points
+F_NO_PDL = 1 << 6
+GN_F_NO_RESIDENT, GN_F_NO_CLUSTER, GN_F_SLICE_BWD, GN_F_SLICE_ALL, GN_F_NO_SOLO, GN_F_NO_SOLO_CLUSTER = 1, 2, 4, 8, 16, 32
+GN_F_LANES_SHIFT = 8
 
 
 class NhmcError(RuntimeError):
@@ -27,7 +31,8 @@ class OpDesc(C.Structure):
                 ("n_kept", C.c_int32), ("pad", C.c_int32), ("no_clamp", C.c_int32), ("reserved", C.c_int32),
                 ("kept_pix", C.c_void_p), ("pix_to_kept", C.c_void_p),
                 ("U1", C.c_void_p), ("V1", C.c_void_p), ("U2", C.c_void_p), ("V2", C.c_void_p),
-                ("gain", C.c_void_p), ("gain_pinv", C.c_void_p), ("coef", C.c_float * 12)]
+                ("gain", C.c_void_p), ("gain_pinv", C.c_void_p), ("coef", C.c_float * 12),
+                ("tc_tables", C.c_void_p)]
 
 
 def build(verbose=False):
@@ -57,6 +62,8 @@ _SIGS = {
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64, C.c_void_p]),
     "nhmc_op_meas_size": (C.c_int64, [C.POINTER(OpDesc)]),
     "nhmc_op_workspace_bytes": (C.c_size_t, [C.POINTER(OpDesc), C.c_int]),
+    "nhmc_op_tables_bytes": (C.c_size_t, [C.POINTER(OpDesc)]),
+    "nhmc_op_prepare_tables": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p]),
     "nhmc_op_forward": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "nhmc_op_adjoint": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "nhmc_op_pinv": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -69,23 +76,22 @@ _SIGS = {
                                    C.c_void_p]),
     "nhmc_gn_fwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int,
-                              C.c_float, C.c_void_p]),
+                              C.c_float, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]),
     "nhmc_gn_bwd": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_uint,
+                              C.c_void_p]),
     "nhmc_gn_cat_fwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+                                  C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_float, C.c_void_p,
+                                  C.c_size_t, C.c_uint, C.c_void_p]),
     "nhmc_gn_cat_bwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_int, C.c_int64, C.c_int, C.c_void_p]),
-    "nhmc_gn_check": (C.c_int, []),
-    "nhmc_gn_set_resident": (C.c_int, [C.c_int]),
-    "nhmc_gn_set_lane": (C.c_int, [C.c_int, C.c_int]),
-    "nhmc_gn_set_solo": (C.c_int, [C.c_int]),
-    "nhmc_set_pdl": (C.c_int, [C.c_int]),
-    "nhmc_bias_add": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
-    "nhmc_pool2_gather": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
-    "nhmc_pool2_scatter": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+                                  C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]),
+    "nhmc_gn_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "nhmc_gn_check": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "nhmc_bias_add": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint, C.c_void_p]),
+    "nhmc_pool2_gather": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
+    "nhmc_pool2_scatter": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint, C.c_void_p]),
     "nhmc_split2": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "nhmc_vq_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "nhmc_softmax_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_void_p]),

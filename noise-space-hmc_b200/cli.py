@@ -142,7 +142,8 @@ def _sample_latent(opt, config, model_config, device, rank, world, a0, a1, H_fun
                for l_ in lat]
         S = min(o.shape[0] for o in out)
         out = torch.stack([o[:S] for o in out]) if S else None
-    allc = ndist.gather_chains(out, opt.chains) if (world > 1 and out is not None) else out
+    # every rank enters the gather, also one that owns no chain or collected nothing (ranks agree on S inside)
+    allc = ndist.gather_samples(out, opt.chains, (3, config.data.image_size, config.data.image_size), device) if world > 1 else out
     if rank == 0 and allc is not None and allc.numel():
         img = ((allc + 1) / 2).clamp(0, 1)
         orig = ((x_orig[0] + 1) / 2).clamp(0, 1)
@@ -196,7 +197,7 @@ def sample_image(opt, config, model_config, device):
                           max_iters=opt.max_iters, on_iteration=on_it, cuda_graphs=opt.cuda_graphs,
                           reuse_gradient=opt.reuse_gradient, lanes=opt.lanes)
         out = out[None] if n == 1 else out                                  # [n, S, C, H, W]
-    allc = ndist.gather_chains(out, opt.chains) if world > 1 else out
+    allc = ndist.gather_samples(out, opt.chains, (config.data.channels, config.data.image_size, config.data.image_size), device) if world > 1 else out
     if rank == 0 and allc is not None and allc.numel():
         img = ((allc + 1) / 2).clamp(0, 1)                                  # inverse_data_transform (datasets/__init__.py:214)
         orig = ((x_orig[0] + 1) / 2).clamp(0, 1)

@@ -20,17 +20,10 @@ int cuda_status(cudaError_t e, const char* what) {
   set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
   return NHMC_ERR_CUDA;
 }
-static int g_pdl = -1;
-bool pdl_enabled() {
-  if (g_pdl < 0) { const char* e = getenv("NHMC_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
-  return g_pdl != 0;
-}
-void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 }  // namespace nhmc
 
 extern "C" {
-int nhmc_set_pdl(int on) { const int prev = nhmc::pdl_enabled() ? 1 : 0; nhmc::pdl_set(on); return prev; }
-int nhmc_version(void) { return 100; }
+int nhmc_version(void) { return 200; }
 const char* nhmc_last_error(void) { return nhmc::g_err; }
 size_t nhmc_sizeof_chain(void) { return sizeof(nhmc_chain); }
 size_t nhmc_sizeof_op(void) { return sizeof(nhmc_op); }

@@ -34,22 +34,21 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // soon as the previous kernel's CTAs have all STARTED and executed pdl_trigger(); they then block in pdl_wait() until
 // that kernel has completed and flushed its writes.  Launch latency and CTA scheduling of the dependent overlap the
 // tail of its predecessor; captured into a CUDA graph the edge becomes a programmatic dependency.  Kernels whose CTAs
-// wait on each other (the resident GroupNorm with its global barrier) never trigger early.  NHMC_PDL=0 disables.
+// wait on each other (the resident GroupNorm with its global barrier) never trigger early.  Per call: NHMC_F_NO_PDL in
+// the entry point's flag word launches plainly.
 #if defined(__CUDACC__)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
-bool pdl_enabled();
-void pdl_set(int on);
 
 template <typename... KA, typename... A>
-static inline cudaError_t launch_pdl(void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+static inline cudaError_t launch_pdl(bool pdl, void (*kern)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
 }
 

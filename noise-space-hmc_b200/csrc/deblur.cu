@@ -154,9 +154,10 @@ struct TcWs {                    // floats
 
 static inline size_t tc_ws_floats(int64_t mats, int64_t D) { return (size_t)(16 * D * D + 8 * mats * D * D); }
 
-static TcWs tc_ws(float* base, int64_t mats, int64_t D) {
+static TcWs tc_ws(const nhmc_op* op, float* base, int64_t mats, int64_t D) {
   TcWs w; w.DD = D * D; w.P = mats * w.DD;
-  for (int i = 0; i < 8; ++i) w.tab[i] = base + (int64_t)i * 2 * w.DD;
+  float* tb = op->tc_tables ? const_cast<float*>(op->tc_tables) : base;     // prepared once by the caller, or rebuilt per call
+  for (int i = 0; i < 8; ++i) w.tab[i] = tb + (int64_t)i * 2 * w.DD;
   float* d = base + 16 * w.DD;
   w.xs = d; w.t0 = d + 2 * w.P; w.t1 = d + 4 * w.P; w.rr = d + 6 * w.P;
   return w;
@@ -176,8 +177,9 @@ static TcGemm tc_base(TcOperand A, TcOperand B, int mats, int C, float* out, boo
 }
 
 // tables of the forward chain (first = true) or of the adjoint chain
-static int tc_tables(const nhmc_op* op, const TcWs& w, bool fwd, cudaStream_t st) {
+static int tc_tables(const nhmc_op* op, const TcWs& w, bool fwd, cudaStream_t st, bool force = false) {
   const int D = op->img_dim;
+  if (op->tc_tables && !force) return NHMC_OK;
   struct { const float* src; int idx; int tr; } f[4] = {{op->V2, 0, 1}, {op->V1, 1, 1}, {op->U1, 2, 0}, {op->U2, 3, 0}},
                                                  b[4] = {{op->U2, 4, 1}, {op->U1, 5, 1}, {op->V1, 6, 0}, {op->V2, 7, 0}};
   for (int i = 0; i < 4; ++i) {
@@ -222,7 +224,7 @@ size_t deblur_workspace_bytes(const nhmc_op* op, int n_chains) {
 int deblur_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
   if (use_tc(op)) {
-    const TcWs w = tc_ws(reinterpret_cast<float*>(ws), mats, D);
+    const TcWs w = tc_ws(op, reinterpret_cast<float*>(ws), mats, D);
     if (int e = tc_tables(op, w, true, st)) return e;
     if (int e = tc_split_launch(x, w.xs, w.xs + w.P, w.P, 0, st)) return e;
     TcGemm last{}; last.out_hi = y;
@@ -242,7 +244,7 @@ int deblur_forward(const nhmc_op* op, const float* x, float* y, int n_chains, vo
 int deblur_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
   if (use_tc(op)) {
-    const TcWs w = tc_ws(reinterpret_cast<float*>(ws), mats, D);
+    const TcWs w = tc_ws(op, reinterpret_cast<float*>(ws), mats, D);
     if (int e = tc_tables(op, w, false, st)) return e;
     if (int e = tc_split_launch(r, w.xs, w.xs + w.P, w.P, 0, st)) return e;
     TcGemm last{}; last.out_hi = out;
@@ -269,7 +271,7 @@ int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, floa
   const RedWs rw = red_ws(workspace, n_chains);
   float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
   if (use_tc(op)) {
-    const TcWs w = tc_ws(scratch, mats, D);
+    const TcWs w = tc_ws(op, scratch, mats, D);
     if (int e = tc_tables(op, w, true, st)) return e;
     if (int e = tc_tables(op, w, false, st)) return e;
     if (int e = tc_split_launch(x_hat, w.xs, w.xs + w.P, w.P, op->no_clamp ? 0 : 1, st)) return e;   // clamp(x_hat), split
@@ -327,9 +329,10 @@ static int tc_sandwich(const float* in, int k2, int k1, const float* Rt, int n1,
 
 struct SepWs { float *L, *Lt, *P, *in, *s, *rr; int64_t dD; };
 static inline size_t sep_ws_floats(int64_t mats, int64_t D, int64_t d) { return (size_t)(6 * d * D + 2 * mats * D * D + 2 * mats * d * D + 2 * mats * d * d); }
-static SepWs sep_ws(float* base, int64_t mats, int64_t D, int64_t d) {
+static SepWs sep_ws(const nhmc_op* op, float* base, int64_t mats, int64_t D, int64_t d) {
   SepWs w; w.dD = d * D;
-  w.L = base; w.Lt = base + 2 * w.dD; w.P = base + 4 * w.dD;
+  float* tb = op->tc_tables ? const_cast<float*>(op->tc_tables) : base;
+  w.L = tb; w.Lt = tb + 2 * w.dD; w.P = tb + 4 * w.dD;
   w.in = base + 6 * w.dD; w.s = w.in + 2 * mats * D * D; w.rr = w.s + 2 * mats * d * D;
   return w;
 }
@@ -364,8 +367,8 @@ size_t sepmat_workspace_bytes(const nhmc_op* op, int n_chains) {
 int sepmat_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* ws, cudaStream_t st) {
   const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
   if (use_tc(op)) {
-    const SepWs w = sep_ws(reinterpret_cast<float*>(ws), mats, D, d);
-    if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
+    const SepWs w = sep_ws(op, reinterpret_cast<float*>(ws), mats, D, d);
+    if (!op->tc_tables) if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
     if (int e = tc_split_launch(x, w.in, w.in + (int64_t)mats * D * D, (int64_t)mats * D * D, 0, st)) return e;
     TcGemm last{}; last.out_hi = y;
     return tc_sandwich(w.in, D, D, w.L, d, w.L, d, w.s, last, mats, C, st);                                   // L (X L^T)
@@ -379,10 +382,12 @@ int sepmat_forward(const nhmc_op* op, const float* x, float* y, int n_chains, vo
 int sepmat_adjoint(const nhmc_op* op, const float* r, float* out, int n_chains, void* ws, cudaStream_t st, bool pinv) {
   const int D = op->img_dim, d = D / op->ratio, C = op->channels, mats = n_chains * C;
   if (use_tc(op)) {
-    const SepWs w = sep_ws(reinterpret_cast<float*>(ws), mats, D, d);
+    const SepWs w = sep_ws(op, reinterpret_cast<float*>(ws), mats, D, d);
     // H^T R = L^T R L: tables K-major = L^T [D][d];  H^+ Y = P Y P^T: tables K-major = P [D][d]
-    if (pinv) { if (int e = tc_split_table_launch(op->V1, w.P, w.P + w.dD, D, d, 0, st)) return e; }
-    else      { if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e; }
+    if (!op->tc_tables) {
+      if (pinv) { if (int e = tc_split_table_launch(op->V1, w.P, w.P + w.dD, D, d, 0, st)) return e; }
+      else      { if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e; }
+    }
     if (int e = tc_split_launch(r, w.rr, w.rr + (int64_t)mats * d * d, (int64_t)mats * d * d, 0, st)) return e;
     const float* T = pinv ? w.P : w.Lt;
     TcGemm last{}; last.out_hi = out;
@@ -405,9 +410,9 @@ int sepmat_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, floa
   const RedWs rw = red_ws(workspace, n_chains);
   float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
   if (use_tc(op)) {
-    const SepWs w = sep_ws(scratch, mats, D, d);
-    if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
-    if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e;
+    const SepWs w = sep_ws(op, scratch, mats, D, d);
+    if (!op->tc_tables) if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
+    if (!op->tc_tables) if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e;
     if (int e = tc_split_launch(x_hat, w.in, w.in + (int64_t)mats * D * D, (int64_t)mats * D * D, op->no_clamp ? 0 : 1, st)) return e;
     TcGemm f{}; f.epi = TC_EPI_RESID; f.y = y; f.loss = loss; f.ws = rw; f.out_hi = w.rr; f.out_lo = w.rr + (int64_t)mats * d * d;
     if (int e = tc_sandwich(w.in, D, D, w.L, d, w.L, d, w.s, f, mats, C, st)) return e;                     // R = y - L xc L^T, loss
@@ -431,6 +436,34 @@ int sepmat_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, floa
     clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
   }
   return NHMC_LAUNCH_CHECK();
+}
+
+// Derived tables, written once into caller-owned memory (include/nhmc.h: nhmc_op_tables_bytes / nhmc_op_prepare_tables)
+size_t spectral_tables_bytes(const nhmc_op* op) {
+  if (!use_tc(op)) return 0;
+  const size_t D = op->img_dim;
+  if (op->kind == NHMC_OP_DEBLUR2D) return 16 * D * D * sizeof(float);
+  if (op->kind == NHMC_OP_SEPMAT) return 6 * (D / op->ratio) * D * sizeof(float);
+  return 0;
+}
+
+int spectral_prepare_tables(const nhmc_op* op, float* tables, cudaStream_t st) {
+  const int D = op->img_dim;
+  nhmc_op tmp = *op;
+  tmp.tc_tables = nullptr;
+  if (op->kind == NHMC_OP_DEBLUR2D) {
+    const TcWs w = tc_ws(&tmp, tables, 1, D);
+    if (int e = tc_tables(&tmp, w, true, st, true)) return e;
+    return tc_tables(&tmp, w, false, st, true);
+  }
+  if (op->kind == NHMC_OP_SEPMAT) {
+    const int d = D / op->ratio;
+    const SepWs w = sep_ws(&tmp, tables, 1, D, d);
+    if (int e = tc_split_table_launch(op->U1, w.L, w.L + w.dD, d, D, 0, st)) return e;
+    if (int e = tc_split_table_launch(op->U1, w.Lt, w.Lt + w.dD, d, D, 1, st)) return e;
+    return tc_split_table_launch(op->V1, w.P, w.P + w.dD, D, d, 0, st);
+  }
+  return NHMC_OK;
 }
 
 }  // namespace nhmc

@@ -46,12 +46,17 @@ using namespace tc5;
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = one 128-byte swizzle row
-constexpr int STAGES = 3;
-constexpr int PLANE_A = BM * BK * 4, PLANE_B = BN * BK * 4;
-constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;                 // 64 KiB
+constexpr int BM = 128, BK = 32;                    // BK fp32 = one 128-byte swizzle row
+constexpr int PLANE_A = BM * BK * 4;
 constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers etc. */;
+// Tile width BN: 128 (3 stages of 64 KiB) while that keeps the launch within one wave of the chip, else 256 (2 stages of
+// 96 KiB): half the CTAs, each A tile reused over twice the columns, the widest MMA shape.
+template <int BN> struct TcTile {
+  static constexpr int PLANE_B = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * PLANE_A + 2 * PLANE_B;
+  static constexpr int STAGES = BN == 128 ? 3 : 2;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers etc. */;
+};
 
 struct TcKernelArgs {
   int M, N, K, channels;
@@ -65,9 +70,10 @@ struct TcKernelArgs {
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcKernelArgs a) {
+  constexpr int PLANE_B = TcTile<BN>::PLANE_B, STAGE_BYTES = TcTile<BN>::STAGE_BYTES, STAGES = TcTile<BN>::STAGES;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
@@ -277,13 +283,29 @@ int operand_map(CUtensorMap* map, const TcOperand& op, int mats, int box_rows) {
   return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, op.base, dims, strides, box);
 }
 
-template <int EPI>
-int launch_epi(const CUtensorMap& ma, const CUtensorMap& mb, const TcKernelArgs& k, dim3 grid, cudaStream_t st) {
-  auto kern = tc_gemm_kernel<EPI>;
-  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+template <int EPI, int BN>
+int launch_epi_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcKernelArgs& k, int mats, cudaStream_t st) {
+  auto kern = tc_gemm_kernel<EPI, BN>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTile<BN>::SMEM);
   if (attr != cudaSuccess) return cuda_status(attr, "tc_gemm smem attribute");
-  kern<<<grid, TC_THREADS, TC_SMEM, st>>>(ma, mb, k);
+  const dim3 grid((k.N + BN - 1) / BN, (k.M + BM - 1) / BM, mats);
+  kern<<<grid, TC_THREADS, TcTile<BN>::SMEM, st>>>(ma, mb, k);
   return NHMC_LAUNCH_CHECK();
+}
+
+static inline int pick_bn(int M, int N, int mats) {
+  const int64_t ctas128 = (int64_t)((N + 127) / 128) * ((M + BM - 1) / BM) * mats;
+  return (N > 128 && ctas128 > kSMs) ? 256 : 128;
+}
+
+template <int EPI>
+int launch_epi(const TcGemm& g, const TcKernelArgs& k, cudaStream_t st) {
+  const int bn = pick_bn(k.M, k.N, g.mats);
+  CUtensorMap ma, mb;
+  if (int e = operand_map(&ma, g.A, g.mats, BM)) return e;
+  if (int e = operand_map(&mb, g.B, g.mats, bn)) return e;
+  if (bn == 256) return launch_epi_bn<EPI, 256>(ma, mb, k, g.mats, st);
+  return launch_epi_bn<EPI, 128>(ma, mb, k, g.mats, st);
 }
 
 }  // namespace
@@ -299,23 +321,19 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
                  "tc_gemm: operands must be 16-byte aligned");
   NHMC_CHECK_ARG(g.A.plane_stride % 4 == 0 && g.B.plane_stride % 4 == 0 && g.A.mat_stride % 4 == 0 && g.B.mat_stride % 4 == 0 &&
                  g.out_mat_stride % 4 == 0, "tc_gemm: strides must be multiples of 16 bytes");
-  CUtensorMap ma, mb;
-  if (int e = operand_map(&ma, g.A, g.mats, BM)) return e;
-  if (int e = operand_map(&mb, g.B, g.mats, BN)) return e;
   TcKernelArgs k{};
   k.M = M; k.N = N; k.K = K; k.channels = g.channels > 0 ? g.channels : 1;
   k.a_shared = g.A.mat_stride == 0; k.b_shared = g.B.mat_stride == 0;
   k.epi = g.epi; k.out_transposed = g.out_transposed; k.no_clamp = g.no_clamp;
   k.out_hi = g.out_hi; k.out_lo = g.out_lo; k.out_mat_stride = g.out_mat_stride;
   k.gain = g.gain; k.y = g.y; k.xhat = g.xhat; k.loss = g.loss; k.ws = g.ws;
-  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, g.mats);
   switch (g.epi) {
-    case TC_EPI_NONE: return launch_epi<TC_EPI_NONE>(ma, mb, k, grid, st);
-    case TC_EPI_GAIN: NHMC_CHECK_ARG(g.gain, "gain required"); return launch_epi<TC_EPI_GAIN>(ma, mb, k, grid, st);
+    case TC_EPI_NONE: return launch_epi<TC_EPI_NONE>(g, k, st);
+    case TC_EPI_GAIN: NHMC_CHECK_ARG(g.gain, "gain required"); return launch_epi<TC_EPI_GAIN>(g, k, st);
     case TC_EPI_RESID:
-      NHMC_CHECK_ARG(g.y && g.loss && (int)(grid.x * grid.y) * k.channels <= kMaxBlocksPerChain, "residual epilogue arguments");
-      return launch_epi<TC_EPI_RESID>(ma, mb, k, grid, st);
-    case TC_EPI_GRAD: NHMC_CHECK_ARG(g.xhat, "xhat required"); return launch_epi<TC_EPI_GRAD>(ma, mb, k, grid, st);
+      NHMC_CHECK_ARG(g.y && g.loss && ((N + 127) / 128) * ((M + BM - 1) / BM) * k.channels <= kMaxBlocksPerChain, "residual epilogue arguments");
+      return launch_epi<TC_EPI_RESID>(g, k, st);
+    case TC_EPI_GRAD: NHMC_CHECK_ARG(g.xhat, "xhat required"); return launch_epi<TC_EPI_GRAD>(g, k, st);
   }
   set_error("tc_gemm: unknown epilogue %d", g.epi);
   return NHMC_ERR_ARG;

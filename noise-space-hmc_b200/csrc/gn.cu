@@ -1178,39 +1178,44 @@ gn_nchw_kernel(GnArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// GN scratch (partials + tickets) lives in a library-static device buffer per device: it is tiny,
-// self-resetting, and keeping it here spares every caller a workspace argument on the hottest
-// U-Net path.  (The header's "library allocates nothing" covers tensors; this is documented there.)
-struct GnScratch { double* partials; unsigned int* tickets; float* bstats; unsigned int* res; int batch; };  // res: [ticket, err, pad, pad, arrive[nb], done[nb]]
-// Lanes: a host that evaluates groups of chains on several streams at once (nhmc_gn_set_lane) gets one scratch set per
-// lane, so concurrent launches never share accumulators / tickets, and the single-wave resident kernel budgets
-// 1/n_lanes of the chip for itself.
-constexpr int kMaxLanes = 8;
-static GnScratch g_scratch[16][kMaxLanes] = {};
-static int g_lane = 0, g_lanes = 1;
+// GN scratch (fp64 accumulators, tickets, barrier counters) is CALLER-OWNED device memory (include/nhmc.h:
+// nhmc_gn_workspace_bytes, zero-filled once): the library keeps no device allocation and no mutable state of its own,
+// so two host threads / samplers / lanes never share accumulators unless they share a workspace.  The execution-path
+// switches that used to be process globals arrive as a per-call flag word.
+struct GnCfg { bool resident, cluster, pdl; int slice, solo, lanes; };
+struct GnScratch { double* partials; unsigned int* tickets; float* bstats; unsigned int* res; int batch; GnCfg cfg; };  // res: [ticket, err, ticket2, pad, arrive[nb], done[nb]]
 
-static int get_scratch(int batch, int G, GnScratch& out) {
-  int dev = 0;
-  if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
-  if (dev < 0 || dev >= 16) { set_error("device index %d out of range", dev); return NHMC_ERR_ARG; }
-  GnScratch& s = g_scratch[dev][g_lane];
-  if (s.batch < batch || !s.partials) {
-    // grow-only; allocation happens outside any stream capture (first call) -- warm up before capturing
-    if (s.partials) { cudaFree(s.partials); cudaFree(s.tickets); cudaFree(s.bstats); cudaFree(s.res); }
-    const int nb = batch < 64 ? 64 : batch;
-    if (int e = cuda_status(cudaMalloc(&s.partials, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMemset(s.partials, 0, (size_t)nb * 64 * 2 * sizeof(double)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMalloc(&s.tickets, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMalloc(&s.bstats, (size_t)nb * 64 * 2 * sizeof(float)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMemset(s.tickets, 0, (size_t)nb * sizeof(unsigned int)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMalloc(&s.res, (size_t)(4 + 2 * nb) * sizeof(unsigned int)), "gn scratch")) return e;
-    if (int e = cuda_status(cudaMemset(s.res, 0, (size_t)(4 + 2 * nb) * sizeof(unsigned int)), "gn scratch")) return e;
-    s.batch = nb;
-  }
-  (void)G;
-  out = s;
+constexpr size_t kGnWsPerSample = 64 * 2 * sizeof(double) + 64 * 2 * sizeof(float) + 3 * sizeof(unsigned int) + 4;   // 1552 B
+constexpr size_t kGnWsHeader = 64;
+
+static GnCfg parse_flags(unsigned int f) {
+  GnCfg c;
+  c.resident = !(f & NHMC_GN_F_NO_RESIDENT);
+  c.cluster = !(f & NHMC_GN_F_NO_CLUSTER);
+  c.slice = (f & NHMC_GN_F_SLICE_ALL) ? 2 : ((f & NHMC_GN_F_SLICE_BWD) ? 1 : 0);
+  c.solo = (f & NHMC_GN_F_NO_SOLO) ? 0 : ((f & NHMC_GN_F_NO_SOLO_CLUSTER) ? 1 : 2);
+  c.pdl = !(f & NHMC_F_NO_PDL);
+  c.lanes = (int)((f >> NHMC_GN_F_LANES_SHIFT) & 7u) + 1;
+  return c;
+}
+
+static int get_scratch(void* workspace, size_t workspace_bytes, unsigned int flags, int batch, GnScratch& out) {
+  NHMC_CHECK_ARG(workspace && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "GroupNorm workspace must be a 16-byte aligned device buffer");
+  NHMC_CHECK_ARG(workspace_bytes >= kGnWsHeader + kGnWsPerSample * (size_t)(batch < 64 ? 64 : batch),
+                 "GroupNorm workspace too small for this batch: size it with nhmc_gn_workspace_bytes(max_batch)");
+  const size_t nb = (workspace_bytes - kGnWsHeader) / kGnWsPerSample;
+  char* p = reinterpret_cast<char*>(workspace);
+  out.res = reinterpret_cast<unsigned int*>(p);                         // 4 header words, then arrive[nb], done[nb] behind the arrays
+  out.partials = reinterpret_cast<double*>(p + kGnWsHeader);
+  out.bstats = reinterpret_cast<float*>(out.partials + nb * 64 * 2);
+  out.tickets = reinterpret_cast<unsigned int*>(out.bstats + nb * 64 * 2);
+  out.batch = (int)nb;
+  out.cfg = parse_flags(flags);
   return NHMC_OK;
 }
+// arrive / done counters of the barrier kernels live behind the ticket array
+static inline unsigned int* ws_arrive(const GnScratch& s) { return s.tickets + s.batch; }
+static inline unsigned int* ws_done(const GnScratch& s) { return s.tickets + 2 * (size_t)s.batch; }
 
 struct DevInfo { int sms, smem_sm, smem_optin, smem_reserved; bool ok; };
 static DevInfo dev_info() {
@@ -1229,16 +1234,6 @@ static DevInfo dev_info() {
   return d;
 }
 
-static int g_cluster_mode = -1;    // NHMC_GN_CLUSTER=0 / nhmc_gn_set_resident(1) keep the global-barrier resident kernel only
-static int cluster_mode() {
-  if (g_cluster_mode < 0) { const char* e = getenv("NHMC_GN_CLUSTER"); g_cluster_mode = (e && e[0] == '0') ? 0 : 1; }
-  return g_cluster_mode;
-}
-static int g_resident_mode = -1;   // NHMC_GN_RESIDENT=0 / nhmc_gn_set_resident(0) force the two-kernel path (A/B measurements, tests)
-static int resident_mode() {
-  if (g_resident_mode < 0) { const char* e = getenv("NHMC_GN_RESIDENT"); g_resident_mode = (e && e[0] == '0') ? 0 : 1; }
-  return g_resident_mode;
-}
 
 // Returns NHMC_OK after launching, NHMC_ERR_UNSUPPORTED when the shape does not fit the resident scheme
 // (the caller then takes the two-kernel path).
@@ -1246,7 +1241,7 @@ template <typename T, int MODE, int PHASE>
 static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, int threads, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
-  if (!resident_mode() || threads > 256 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  if (!s.cfg.resident || threads > 256 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
   const int Cg = a0.C / a0.G, cvec = a0.C / V;
   for (int cv = 0; cv < cvec; ++cv)
     if ((cv * V + V - 1) / Cg - (cv * V) / Cg > 1) return NHMC_ERR_UNSUPPORTED;   // a thread may span at most 2 groups
@@ -1267,7 +1262,7 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
   // (a) One sample per thread-block cluster (<= 8 CTAs, the portable limit): the per-sample reduction runs over
   // distributed shared memory behind the hardware cluster barrier -- no global atomics, no ticket, no spinning.
   // Taken whenever a sample's slab fits in 8 CTAs' shared memory (the 8x8 .. 32x32 maps at FFHQ-256).
-  if (cluster_mode()) {
+  if (s.cfg.cluster) {
     auto ckern = gn_nhwc_resident_kernel<T, MODE, PHASE, true>;
     static int c_static = -1;
     if (c_static < 0) {
@@ -1312,13 +1307,14 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
   // through the statistics + apply kernels, whose second read is served by the L2 for what still fits there
   // (measured in situ: the resident scheme loses once a launch needs several waves, because the per-sample
   // barrier then serialises load -> reduce -> store phases that the two-kernel path overlaps).
+  if (s.cfg.lanes > 1) return NHMC_ERR_UNSUPPORTED;   // concurrent lanes never run the global-barrier kernel
   for (int k = 4; k >= 1; --k) {
     int64_t dyn_limit = d.smem_sm / k - d.smem_reserved;
     if (dyn_limit > d.smem_optin) dyn_limit = d.smem_optin;
     dyn_limit -= static_smem;
     const int64_t slab_limit = (dyn_limit / NSRC) & ~(int64_t)127;
     if (slab_limit < row_bytes) continue;
-    const int64_t slots = ((int64_t)k * d.sms) / g_lanes;         // this lane's share of the chip
+    const int64_t slots = ((int64_t)k * d.sms) / s.cfg.lanes;         // this lane's share of the chip
     int64_t nb = slots / batch;                                   // CTAs per sample that keep the launch in one wave
     if (nb < 1) continue;
     int64_t rows_per_cta = (a0.HW + nb - 1) / nb;
@@ -1330,7 +1326,7 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     const size_t dyn = (size_t)slab * NSRC;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, dyn) != cudaSuccess) { cudaGetLastError(); continue; }
-    if (((int64_t)occ * d.sms) / g_lanes < nb * batch) continue;
+    if (((int64_t)occ * d.sms) / s.cfg.lanes < nb * batch) continue;
     GnResArgs r{};
     r.a = a0;
     r.a.rows_per_cta = rows_per_cta;
@@ -1341,18 +1337,20 @@ static int run_nhwc_resident(const GnArgs& a0, const GnScratch& s, int batch, in
     r.batch = batch;
     r.reps = (int)(nb >= 64 ? 8 : (nb >= 16 ? 4 : 1));             // replicas only where a sample has many CTAs
     while (r.reps > 1 && (int64_t)r.reps * batch > s.batch) r.reps >>= 1;
-    r.ticket = s.res; r.err = s.res + 1; r.arrive = s.res + 4; r.done = s.res + 4 + s.batch;
-    kern<<<r.total_ctas, threads, dyn, st>>>(r);
-    return NHMC_LAUNCH_CHECK();
+    r.ticket = s.res; r.err = s.res + 1; r.arrive = ws_arrive(s); r.done = ws_done(s);
+    // cooperative launch: the driver guarantees that every CTA of the grid is resident at once (or fails the launch), so
+    // the per-sample spin barrier cannot starve behind CTAs of other kernels
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(r.total_ctas); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = dyn; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cuda_status(cudaLaunchKernelEx(&cfg, kern, r), "resident GroupNorm launch");
   }
   return NHMC_ERR_UNSUPPORTED;
 }
 
-static int g_slice_mode = -1;      // NHMC_GN_SLICE: 0 off (default: measured slower in situ than statistics + apply), 1 backward only, 2 backward + large forward tensors
-static int slice_mode() {
-  if (g_slice_mode < 0) { const char* e = getenv("NHMC_GN_SLICE"); g_slice_mode = e ? atoi(e) : 0; }
-  return g_slice_mode;
-}
 
 // Resident-by-channel-slice kernel for tensors that do not fit the single-wave resident kernel.  NHMC_ERR_UNSUPPORTED
 // when the shape cannot be cut into units of which at least two fit on the chip at once.
@@ -1360,8 +1358,8 @@ template <typename T, int MODE, int PHASE>
 static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
-  const int mode = slice_mode();
-  if (!resident_mode() || mode == 0 || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  const int mode = s.cfg.slice;
+  if (!s.cfg.resident || mode == 0 || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
   const int64_t row_bytes = (int64_t)a0.C * sizeof(T);
   const int64_t sample_bytes = a0.HW * row_bytes;
   if (PHASE == 0 && (mode < 2 || (int64_t)batch * sample_bytes < ((int64_t)200 << 20))) return NHMC_ERR_UNSUPPORTED;
@@ -1418,7 +1416,7 @@ static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaS
       const int64_t n_pass = (rows_per_cta + rows - 1) / rows;
       r.chunk_passes = (int)((n_pass + 3) / 4);
       r.total_ctas = (unsigned int)(nb * batch * cs);
-      r.ticket = s.res + 2; r.err = s.res + 1; r.arrive = s.res + 4; r.done = s.res + 4 + s.batch;
+      r.ticket = s.res + 2; r.err = s.res + 1; r.arrive = ws_arrive(s); r.done = ws_done(s);
       kern<<<r.total_ctas, threads, (size_t)slab * NSRC, st>>>(r);
       return NHMC_LAUNCH_CHECK();
     }
@@ -1426,21 +1424,16 @@ static int run_nhwc_slice(const GnArgs& a0, const GnScratch& s, int batch, cudaS
   return NHMC_ERR_UNSUPPORTED;
 }
 
-static int g_solo_mode = -1;       // NHMC_GN_SOLO / nhmc_gn_set_solo: 0 never, 1 one-CTA-per-unit kernel, 2 (default) + cluster-per-unit kernel
-static int solo_mode() {
-  if (g_solo_mode < 0) { const char* e = getenv("NHMC_GN_SOLO"); g_solo_mode = e ? atoi(e) : 2; }
-  return g_solo_mode;
-}
 
 // One CTA per (sample, slice of whole groups) with the unit resident in shared memory: the small maps (8x8 .. 64x64),
 // where a call is bound by its dependency chain, not by bandwidth.  Picks the WIDEST slice (longest contiguous run per
 // pixel) that still yields >= ~one CTA per SM and whose unit fits 1/3 of an SM's shared memory (3 CTAs per SM overlap
 // each other's load / reduce / store phases); NHMC_ERR_UNSUPPORTED otherwise.
 template <typename T, int MODE, int PHASE>
-static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
+static int run_nhwc_solo(const GnArgs& a0, const GnScratch& s, int batch, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
   constexpr int NSRC = PHASE == 1 ? 2 : 1;
-  if (!solo_mode() || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
+  if (!s.cfg.solo || a0.x1 || a0.G > 32) return NHMC_ERR_UNSUPPORTED;
   const DevInfo d = dev_info();
   if (!d.ok) return NHMC_ERR_UNSUPPORTED;
   auto kern = gn_nhwc_slice_kernel<T, MODE, PHASE, 1>;
@@ -1483,7 +1476,7 @@ static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
     // measured (tools/kernel_microbench.py --small --warm --graph-calls 20 --solo 1/2): wins on the 64x64 maps with >= 64-byte
     // runs per pixel while x (+ dy) stay <= 36 MB in total (10.2 vs 15.2 us forward, 24.4 vs 26.9 us backward at
     // [8,256,64,64]); loses on 32x32 maps (resident kernel: 16.5 vs 22.6 us), with 32-byte runs and beyond that size
-    if (solo_mode() < 2 || a0.HW < 4096 || (int64_t)batch * a0.HW * a0.C * (int64_t)sizeof(T) * NSRC > ((int64_t)36 << 20)) return NHMC_ERR_UNSUPPORTED;
+    if (s.cfg.solo < 2 || a0.HW < 4096 || (int64_t)batch * a0.HW * a0.C * (int64_t)sizeof(T) * NSRC > ((int64_t)36 << 20)) return NHMC_ERR_UNSUPPORTED;
     auto ckern = gn_nhwc_slice_kernel<T, MODE, PHASE, 2>;
     static int c_static = -1;
     if (c_static < 0) {
@@ -1539,7 +1532,7 @@ static int run_nhwc_solo(const GnArgs& a0, int batch, cudaStream_t st) {
   // the dependents that slip in early crowd some SMs and the launch ends unbalanced (measured: 15.5 -> 18.4 us at
   // [8,512,32,32] backward); a plain launch spreads evenly over the idle chip.
   if ((int64_t)r.total_ctas <= d.sms || (int64_t)best_slab * NSRC <= 16384)
-    return cuda_status(launch_pdl(kern, dim3(r.total_ctas), dim3(best_threads), (size_t)best_slab * NSRC, st, r), "gn one-CTA launch");
+    return cuda_status(launch_pdl(s.cfg.pdl, kern, dim3(r.total_ctas), dim3(best_threads), (size_t)best_slab * NSRC, st, r), "gn one-CTA launch");
   kern<<<r.total_ctas, best_threads, (size_t)best_slab * NSRC, st>>>(r);
   return NHMC_LAUNCH_CHECK();
 }
@@ -1552,7 +1545,7 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   const int threads = cvec * rows;
   NHMC_CHECK_ARG(threads <= 1024, "too many channels for the channels-last GroupNorm mapping");
   if (!a.x1 && !a.add2) {
-    int e = run_nhwc_solo<T, MODE, PHASE>(a, batch, st);
+    int e = run_nhwc_solo<T, MODE, PHASE>(a, s, batch, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
     e = run_nhwc_resident<T, MODE, PHASE>(a, s, batch, threads, st);
     if (e != NHMC_ERR_UNSUPPORTED) return e;
@@ -1584,12 +1577,12 @@ static int run_nhwc(GnArgs a, const GnScratch& s, int batch, cudaStream_t st) {
   a.reps = nblk >= 64 ? 8 : (nblk >= 16 ? 4 : 1);
   while (a.reps > 1 && (int64_t)a.reps * batch > s.batch) a.reps >>= 1;
   const dim3 grid((unsigned)nblk, (unsigned)batch);
-  if (int e = cuda_status(launch_pdl(gn_nhwc_stats_kernel<T, MODE, PHASE>, grid, dim3(threads), red, st, a), "gn statistics launch")) return e;
+  if (int e = cuda_status(launch_pdl(s.cfg.pdl, gn_nhwc_stats_kernel<T, MODE, PHASE>, grid, dim3(threads), red, st, a), "gn statistics launch")) return e;
   if (PHASE == 1 && a.add2) {
     NHMC_CHECK_ARG(a.add && !a.x1, "dx_add2 needs dx_add and a single-source tensor");
-    return cuda_status(launch_pdl(gn_nhwc_apply_kernel<T, MODE, PHASE, PHASE == 1>, grid, dim3(threads), 0, st, a), "gn apply launch");
+    return cuda_status(launch_pdl(s.cfg.pdl, gn_nhwc_apply_kernel<T, MODE, PHASE, PHASE == 1>, grid, dim3(threads), 0, st, a), "gn apply launch");
   }
-  return cuda_status(launch_pdl(gn_nhwc_apply_kernel<T, MODE, PHASE>, grid, dim3(threads), 0, st, a), "gn apply launch");
+  return cuda_status(launch_pdl(s.cfg.pdl, gn_nhwc_apply_kernel<T, MODE, PHASE>, grid, dim3(threads), 0, st, a), "gn apply launch");
 }
 
 template <typename T, int MODE, int PHASE>
@@ -1638,11 +1631,12 @@ using namespace nhmc;
 
 extern "C" int nhmc_gn_fwd(int mode, int layout, int dtype, const void* x, void* y, const float* gamma,
                            const float* beta, const float* scale, const float* shift, int64_t film_stride, const float* in_bias,
-                           int64_t in_bias_stride, float* stats_out, int batch, int channels, int64_t hw, int groups, float eps, nhmc_stream_t stream) {
+                           int64_t in_bias_stride, float* stats_out, int batch, int channels, int64_t hw, int groups, float eps,
+                           void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(stats_out, "stats_out required");
   GnScratch s;
-  if (int e = get_scratch(batch, groups, s)) return e;
+  if (int e = get_scratch(workspace, workspace_bytes, flags, batch, s)) return e;
   GnArgs a{};
   a.x = x; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.in_bias_stride = in_bias_stride; a.stats = stats_out;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
@@ -1655,7 +1649,8 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
                            const float* gamma, const float* beta, const float* scale, const float* shift,
                            int64_t film_stride, const float* in_bias, int64_t in_bias_stride, const float* stats, float* dscale,
                            float* dshift, const void* dx_add, const void* dx_add2, int batch,
-                           int channels, int64_t hw, int groups, nhmc_stream_t stream) {
+                           int channels, int64_t hw, int groups, void* workspace, size_t workspace_bytes, unsigned int flags,
+                           nhmc_stream_t stream) {
   if (int e = check_common(mode, layout, dtype, x, dx, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   NHMC_CHECK_ARG(dy && stats, "dy and stats required");
   NHMC_CHECK_ARG(!dscale && !dshift, "dscale/dshift are not produced on the sampling path (timestep embedding carries no gradient)");
@@ -1663,7 +1658,7 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
   NHMC_CHECK_ARG(!dx_add || aligned16(dx_add), "dx_add must be 16-byte aligned");
   NHMC_CHECK_ARG(!dx_add2 || (dx_add && aligned16(dx_add2)), "dx_add2 needs dx_add and 16-byte alignment");
   GnScratch s;
-  if (int e = get_scratch(batch, groups, s)) return e;
+  if (int e = get_scratch(workspace, workspace_bytes, flags, batch, s)) return e;
   GnArgs a{};
   a.x = x; a.dy = dy; a.out = dx; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.in_bias = in_bias; a.in_bias_stride = in_bias_stride;
   a.stats = const_cast<float*>(stats);
@@ -1680,14 +1675,14 @@ extern "C" int nhmc_gn_bwd(int mode, int layout, int dtype, const void* x, const
 extern "C" int nhmc_gn_cat_fwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, void* y,
                                const float* gamma, const float* beta, const float* scale, const float* shift,
                                int64_t film_stride, float* stats_out, int batch, int64_t hw, int groups, float eps,
-                               nhmc_stream_t stream) {
+                               void* workspace, size_t workspace_bytes, unsigned int flags, nhmc_stream_t stream) {
   const int channels = c0 + c1;
   if (int e = check_common(mode, NHMC_LAYOUT_NHWC, dtype, x0, y, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   const int V = dtype == NHMC_F32 ? 4 : 8;
   NHMC_CHECK_ARG(x1 && c0 > 0 && c1 > 0 && c0 % V == 0 && c1 % V == 0 && aligned16(x1), "both blocks need C % (16B/elem) == 0 and 16-byte alignment");
   NHMC_CHECK_ARG(stats_out, "stats_out required");
   GnScratch s;
-  if (int e = get_scratch(batch, groups, s)) return e;
+  if (int e = get_scratch(workspace, workspace_bytes, flags, batch, s)) return e;
   GnArgs a{};
   a.x = x0; a.x1 = x1; a.c_split = c0; a.out = y; a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = stats_out;
   a.partials = s.partials; a.tickets = s.tickets; a.C = channels; a.G = groups; a.HW = hw; a.eps = eps;
@@ -1698,7 +1693,8 @@ extern "C" int nhmc_gn_cat_fwd(int mode, int dtype, const void* x0, const void* 
 extern "C" int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* x1, int c0, int c1, const void* dy,
                                void* dx0, void* dx1, const float* gamma, const float* beta, const float* scale,
                                const float* shift, int64_t film_stride, const float* stats, const void* add0,
-                               const void* add1, int batch, int64_t hw, int groups, nhmc_stream_t stream) {
+                               const void* add1, int batch, int64_t hw, int groups, void* workspace, size_t workspace_bytes,
+                               unsigned int flags, nhmc_stream_t stream) {
   const int channels = c0 + c1;
   if (int e = check_common(mode, NHMC_LAYOUT_NHWC, dtype, x0, dx0, gamma, beta, scale, shift, batch, channels, hw, groups)) return e;
   const int V = dtype == NHMC_F32 ? 4 : 8;
@@ -1707,7 +1703,7 @@ extern "C" int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* 
   NHMC_CHECK_ARG(dy && stats && aligned16(dy), "dy (16-byte aligned) and stats required");
   NHMC_CHECK_ARG((!add0 || aligned16(add0)) && (!add1 || aligned16(add1)), "add blocks must be 16-byte aligned");
   GnScratch s;
-  if (int e = get_scratch(batch, groups, s)) return e;
+  if (int e = get_scratch(workspace, workspace_bytes, flags, batch, s)) return e;
   GnArgs a{};
   a.x = x0; a.x1 = x1; a.c_split = c0; a.dy = dy; a.out = dx0; a.out1 = dx1; a.add = add0; a.add1 = add1;
   a.gamma = gamma; a.beta = beta; a.scale = scale; a.shift = shift; a.stats = const_cast<float*>(stats); a.bstats = s.bstats;
@@ -1716,39 +1712,17 @@ extern "C" int nhmc_gn_cat_bwd(int mode, int dtype, const void* x0, const void* 
   return dispatch<1>(mode, NHMC_LAYOUT_NHWC, dtype, a, s, batch, (cudaStream_t)stream);
 }
 
-extern "C" int nhmc_gn_check(void) {
-  // 0 = no wait of the resident GroupNorm path ever timed out on the current device (synchronises)
-  int dev = 0;
-  if (int e = cuda_status(cudaGetDevice(&dev), "cudaGetDevice")) return e;
-  if (dev < 0 || dev >= 16) return NHMC_OK;
-  for (int lane = 0; lane < kMaxLanes; ++lane) {
-    if (!g_scratch[dev][lane].res) continue;
-    unsigned int flag = 0;
-    if (int e = cuda_status(cudaMemcpy(&flag, g_scratch[dev][lane].res + 1, sizeof(flag), cudaMemcpyDeviceToHost), "gn check")) return e;
-    if (flag) { set_error("resident GroupNorm: a per-sample barrier timed out (results of that call are invalid)"); return NHMC_ERR_CUDA; }
-  }
-  return NHMC_OK;
+extern "C" size_t nhmc_gn_workspace_bytes(int max_batch) {
+  // room for 8 accumulator replicas per sample (samples spanning many CTAs), never below 64 slots
+  size_t nb = (size_t)(max_batch > 0 ? max_batch : 1) * 8;
+  if (nb < 64) nb = 64;
+  return kGnWsHeader + kGnWsPerSample * nb;
 }
 
-extern "C" int nhmc_gn_set_solo(int on) {
-  const int prev = solo_mode();
-  g_solo_mode = on < 0 ? 0 : (on > 2 ? 2 : on);
-  return prev;
-}
-
-extern "C" int nhmc_gn_set_lane(int lane, int n_lanes) {
-  // The GroupNorm calls that follow (from any host thread) belong to `lane` of `n_lanes` concurrently running streams.
-  NHMC_CHECK_ARG(n_lanes >= 1 && n_lanes <= kMaxLanes && lane >= 0 && lane < n_lanes, "lane out of range (at most 8 lanes)");
-  g_lane = lane; g_lanes = n_lanes;
-  return NHMC_OK;
-}
-
-extern "C" int nhmc_gn_set_resident(int on) {
-  // 0: statistics + apply kernels only; 1: + resident kernel with the global per-sample barrier; 2 (default): + the
-  // thread-block-cluster variant for samples that fit in 8 CTAs; 3 (default): + the resident-by-channel-slice kernel for large tensors
-  const int prev = resident_mode() ? (cluster_mode() ? (slice_mode() ? 3 : 2) : 1) : 0;
-  g_resident_mode = on ? 1 : 0;
-  g_cluster_mode = on >= 2 ? 1 : 0;
-  g_slice_mode = on >= 3 ? 2 : 0;
-  return prev;
+extern "C" int nhmc_gn_check(const void* workspace, size_t workspace_bytes, int32_t* flag_out, nhmc_stream_t stream) {
+  // Copies the workspace's timeout flag (0 = no barrier wait of the resident GroupNorm kernels ever timed out) to
+  // *flag_out (device or pinned host memory) on `stream`; nothing synchronises.
+  NHMC_CHECK_ARG(workspace && flag_out && workspace_bytes >= kGnWsHeader, "workspace and flag_out required");
+  const unsigned int* res = reinterpret_cast<const unsigned int*>(workspace);
+  return cuda_status(cudaMemcpyAsync(flag_out, res + 1, sizeof(int32_t), cudaMemcpyDefault, (cudaStream_t)stream), "gn check");
 }

@@ -19,6 +19,8 @@ int sepmat_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_
 int sepmat_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t, bool pinv);
 int sepmat_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
 size_t sepmat_workspace_bytes(const nhmc_op*, int);
+size_t spectral_tables_bytes(const nhmc_op*);
+int spectral_prepare_tables(const nhmc_op*, float*, cudaStream_t);
 int cs_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int cs_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int cs_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
@@ -385,6 +387,17 @@ extern "C" int64_t nhmc_op_meas_size(const nhmc_op* op) {
     case NHMC_OP_SEPMAT: return op->ratio > 0 ? C * (D / op->ratio) * (D / op->ratio) : -1;
     default: return -1;
   }
+}
+
+extern "C" size_t nhmc_op_tables_bytes(const nhmc_op* op) {
+  if (!op || (op->kind != NHMC_OP_DEBLUR2D && op->kind != NHMC_OP_SEPMAT)) return 0;
+  return spectral_tables_bytes(op);
+}
+
+extern "C" int nhmc_op_prepare_tables(const nhmc_op* op, void* tables, nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(op && tables && aligned16(tables), "operator and a 16-byte aligned table buffer required");
+  NHMC_CHECK_ARG(nhmc_op_tables_bytes(op) > 0, "this operator has no derived tables");
+  return spectral_prepare_tables(op, reinterpret_cast<float*>(tables), (cudaStream_t)stream);
 }
 
 extern "C" size_t nhmc_op_workspace_bytes(const nhmc_op* op, int n_chains) {

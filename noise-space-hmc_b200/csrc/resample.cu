@@ -139,13 +139,13 @@ static inline unsigned grid_for(int64_t total) {
 }
 
 template <typename T>
-static int run_pool(bool gather, const void* in, void* out, int batch, int h, int w, int C, float scale, cudaStream_t st) {
+static int run_pool(bool gather, const void* in, void* out, int batch, int h, int w, int C, float scale, bool pdl, cudaStream_t st) {
   constexpr int V = V16<T>::N;
   NHMC_CHECK_ARG(C % V == 0, "channels must be a multiple of the 16-byte vector width");
   const int64_t total = (int64_t)batch * h * w * (C / V);
   const dim3 g(grid_for(total)), b(256);
-  if (gather) return cuda_status(launch_pdl(pool2_kernel<T, true>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
-  return cuda_status(launch_pdl(pool2_kernel<T, false>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
+  if (gather) return cuda_status(launch_pdl(pdl, pool2_kernel<T, true>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
+  return cuda_status(launch_pdl(pdl, pool2_kernel<T, false>, g, b, 0, st, (const T*)in, (T*)out, h, w, C / V, total, scale), "pool2 launch");
 }
 
 }  // namespace nhmc
@@ -153,26 +153,27 @@ static int run_pool(bool gather, const void* in, void* out, int batch, int h, in
 using namespace nhmc;
 
 static int pool_dispatch(bool gather, int dtype, const void* in, void* out, int batch, int h, int w, int C, float scale,
-                         nhmc_stream_t stream) {
+                         unsigned int flags, nhmc_stream_t stream) {
+  const bool pdl = !(flags & NHMC_F_NO_PDL);
   NHMC_CHECK_ARG(in && out && batch > 0 && h > 0 && w > 0 && C > 0, "bad arguments");
   NHMC_CHECK_ARG(aligned16(in) && aligned16(out), "pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case NHMC_F32: return run_pool<float>(gather, in, out, batch, h, w, C, scale, st);
-    case NHMC_BF16: return run_pool<__nv_bfloat16>(gather, in, out, batch, h, w, C, scale, st);
-    case NHMC_F16: return run_pool<__half>(gather, in, out, batch, h, w, C, scale, st);
+    case NHMC_F32: return run_pool<float>(gather, in, out, batch, h, w, C, scale, pdl, st);
+    case NHMC_BF16: return run_pool<__nv_bfloat16>(gather, in, out, batch, h, w, C, scale, pdl, st);
+    case NHMC_F16: return run_pool<__half>(gather, in, out, batch, h, w, C, scale, pdl, st);
   }
   set_error("pool2: unknown dtype %d", dtype);
   return NHMC_ERR_ARG;
 }
 
 extern "C" int nhmc_pool2_gather(int dtype, const void* in_big, void* out_small, int batch, int h_small, int w_small,
-                                 int channels, float scale, nhmc_stream_t stream) {
-  return pool_dispatch(true, dtype, in_big, out_small, batch, h_small, w_small, channels, scale, stream);
+                                 int channels, float scale, unsigned int flags, nhmc_stream_t stream) {
+  return pool_dispatch(true, dtype, in_big, out_small, batch, h_small, w_small, channels, scale, flags, stream);
 }
 extern "C" int nhmc_pool2_scatter(int dtype, const void* in_small, void* out_big, int batch, int h_small, int w_small,
-                                  int channels, float scale, nhmc_stream_t stream) {
-  return pool_dispatch(false, dtype, in_small, out_big, batch, h_small, w_small, channels, scale, stream);
+                                  int channels, float scale, unsigned int flags, nhmc_stream_t stream) {
+  return pool_dispatch(false, dtype, in_small, out_big, batch, h_small, w_small, channels, scale, flags, stream);
 }
 
 extern "C" int nhmc_split2(int dtype, const void* in, void* out1, void* out2, int64_t rows, int c1, int c2,
@@ -193,27 +194,27 @@ extern "C" int nhmc_split2(int dtype, const void* in, void* out1, void* out2, in
 }
 
 template <typename T>
-static int run_bias_add(const void* a, const void* b, const void* c, const float* bias, void* out, int64_t rows, int C, cudaStream_t st) {
+static int run_bias_add(const void* a, const void* b, const void* c, const float* bias, void* out, int64_t rows, int C, bool pdl, cudaStream_t st) {
   constexpr int V = V16<T>::N;
   NHMC_CHECK_ARG(C % V == 0, "channels must be a multiple of the 16-byte vector width");
   const int64_t total = rows * (C / V);
   const unsigned g = grid_for(total);
-#define BA(HB, HBI) return cuda_status(launch_pdl(bias_add_kernel<T, HB, HBI>, dim3(g), dim3(256), 0, st, (const T*)a, (const T*)b, (const T*)c, bias, (T*)out, total, C / V), "bias_add launch")
+#define BA(HB, HBI) return cuda_status(launch_pdl(pdl, bias_add_kernel<T, HB, HBI>, dim3(g), dim3(256), 0, st, (const T*)a, (const T*)b, (const T*)c, bias, (T*)out, total, C / V), "bias_add launch")
   if (b) { if (bias) BA(true, true); else BA(true, false); }
   else   { if (bias) BA(false, true); else BA(false, false); }
 #undef BA
 }
 
 extern "C" int nhmc_bias_add(int dtype, const void* a, const void* b, const void* c, const float* bias, void* out,
-                             int64_t rows, int channels, nhmc_stream_t stream) {
+                             int64_t rows, int channels, unsigned int flags, nhmc_stream_t stream) {
   NHMC_CHECK_ARG(a && out && rows > 0 && channels > 0, "bad arguments");
   NHMC_CHECK_ARG(!c || b, "a third addend needs the second");
   NHMC_CHECK_ARG(aligned16(a) && aligned16(out) && (!b || aligned16(b)) && (!c || aligned16(c)), "pointers must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case NHMC_F32: return run_bias_add<float>(a, b, c, bias, out, rows, channels, st);
-    case NHMC_BF16: return run_bias_add<__nv_bfloat16>(a, b, c, bias, out, rows, channels, st);
-    case NHMC_F16: return run_bias_add<__half>(a, b, c, bias, out, rows, channels, st);
+    case NHMC_F32: return run_bias_add<float>(a, b, c, bias, out, rows, channels, !(flags & NHMC_F_NO_PDL), st);
+    case NHMC_BF16: return run_bias_add<__nv_bfloat16>(a, b, c, bias, out, rows, channels, !(flags & NHMC_F_NO_PDL), st);
+    case NHMC_F16: return run_bias_add<__half>(a, b, c, bias, out, rows, channels, !(flags & NHMC_F_NO_PDL), st);
   }
   set_error("bias_add: unknown dtype %d", dtype);
   return NHMC_ERR_ARG;

@@ -55,6 +55,30 @@ def gather_chains(local, n_chains, dst=0):
     return torch.cat([bufs[r][: b - a] for r, (a, b) in enumerate(sizes)], dim=0)
 
 
+def gather_samples(local, n_chains, sample_shape, device, dtype=torch.float32, dst=0):
+    """Final gather of the collected samples (the only collective of a run).  local: [n_local, S_local, *sample_shape] of
+    this rank's chains, or None / empty when the rank owns no chain (chains < world) or collected nothing.  EVERY rank
+    makes the same collective calls: the ranks first agree on S = min over ranks that own chains (a run cut short by
+    --max_iters can leave ranks with different counts), then all_gather [n_max, S, ...] blocks.  Returns
+    [n_chains, S, *sample_shape] on dst (None elsewhere; None everywhere if S == 0)."""
+    have = local is not None and local.numel() > 0
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local if have else None
+    big = 1 << 30
+    s_loc = torch.tensor([local.shape[1] if have else (0 if (local is not None and local.shape[0] > 0) else big)],
+                         dtype=torch.int64, device=device)
+    dist.all_reduce(s_loc, op=dist.ReduceOp.MIN)
+    S = int(s_loc.item())
+    if S >= big or S == 0:
+        return None
+    a, b = chain_shard(n_chains, dist.get_rank(), dist.get_world_size())
+    if have:
+        block = local[:, :S].to(device=device, dtype=dtype).contiguous()
+    else:
+        block = torch.zeros((b - a, S) + tuple(sample_shape), dtype=dtype, device=device)
+    return gather_chains(block, n_chains, dst)
+
+
 def max_over_ranks(value, device):
     """Device-timed durations are reported as the max over ranks."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

@@ -1,4 +1,6 @@
 """Torch-tensor wrappers around the C ABI (raw device pointers + torch's current stream)."""
+import threading
+
 import torch
 
 from . import _lib
@@ -78,15 +80,111 @@ class _timed:
         return False
 
 
-LANE = 0             # lane (group of chains evaluated on its own stream) the calls that follow belong to
+# ---- GroupNorm workspaces and the per-call flag word ---------------------------------------------------------------
+# The library keeps no scratch and no switches of its own (include/nhmc.h): the accumulators / tickets / barrier counters
+# of the GroupNorm kernels live in a caller-owned workspace, and the execution-path choices travel with every call.
+# Here the "caller" is this module: a thread-local scope (HMCSampler opens one per lane around its launches, so two
+# samplers on two host threads never share accumulators) and, outside any scope, one workspace per (device, stream).
+GN_MAX_BATCH = 64     # samples one workspace is sized for (nhmc_gn_workspace_bytes); larger batches get a larger one
+FLAGS = 0             # process-wide default flag word (tests / A-B tools set it through set_flags); scopes OR theirs in
+_tls = threading.local()
+_default_ws = {}      # (device index, stream id) -> GnWorkspace
 
 
-def set_lane(lane, n_lanes):
-    """Announce that the calls that follow run on lane `lane` of `n_lanes` concurrent streams: per-lane GroupNorm
-    scratch in the library, per-lane operator workspaces here."""
-    global LANE
-    check(lib().nhmc_gn_set_lane(int(lane), int(n_lanes)), "nhmc_gn_set_lane")
-    LANE = int(lane)
+class GnWorkspace:
+    """Device scratch of the GroupNorm kernels + a pinned host word for its timeout flag."""
+
+    def __init__(self, device, max_batch=GN_MAX_BATCH):
+        self.max_batch = int(max_batch)
+        self.nbytes = int(lib().nhmc_gn_workspace_bytes(self.max_batch))
+        self.buf = torch.zeros((self.nbytes + 7) // 8, dtype=torch.int64, device=device)
+        self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._pending = False
+
+    def poll(self):
+        """Queue a copy of the timeout flag to pinned host memory on the current stream (no synchronisation)."""
+        check(lib().nhmc_gn_check(self.buf.data_ptr(), self.nbytes, self.flag.data_ptr(), _stream()), "nhmc_gn_check")
+        self._pending = True
+
+    def raise_if_timed_out(self):
+        """After a synchronisation that covers the last poll(): raise (and reset the workspace) if a barrier timed out."""
+        if self._pending and int(self.flag[0]) != 0:
+            self.buf.zero_()
+            self.flag.zero_()
+            raise _lib.NhmcError("resident GroupNorm: a per-sample barrier timed out; the results of the affected calls are "
+                                 "invalid (workspace reset)")
+        self._pending = False
+
+
+def set_flags(flags):
+    """Process-wide default flag word (NHMC_F_NO_PDL, NHMC_GN_F_*); returns the previous one.  For tests and A/B tools."""
+    global FLAGS
+    prev, FLAGS = FLAGS, int(flags)
+    return prev
+
+
+class gn_scope:
+    """with gn_scope(ws, n_lanes, flags): the GroupNorm / pooling / residual-add calls of this thread use `ws` and carry
+    `flags` (lane count included) until the scope closes."""
+
+    def __init__(self, ws, n_lanes=1, flags=0):
+        self.state = (ws, int(flags) | ((max(1, min(int(n_lanes), 8)) - 1) << _lib.GN_F_LANES_SHIFT))
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "scope", None)
+        _tls.scope = self.state
+        return self
+
+    def __exit__(self, *exc):
+        _tls.scope = self.prev
+        return False
+
+
+def current_scope():
+    """The calling thread's scope state (or None): autograd Functions save it in forward and re-enter it in backward,
+    because autograd runs backward nodes on its own device thread where this thread's scope is not visible."""
+    return getattr(_tls, "scope", None)
+
+
+class _reenter:
+    def __init__(self, state):
+        self.state = state
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "scope", None)
+        if self.state is not None:
+            _tls.scope = self.state
+        return self
+
+    def __exit__(self, *exc):
+        _tls.scope = self.prev
+        return False
+
+
+def scope_of(state):
+    """Context manager re-entering a scope state saved with current_scope() (no-op for None)."""
+    return _reenter(state)
+
+
+def _flags():
+    sc = getattr(_tls, "scope", None)
+    return FLAGS | (sc[1] if sc is not None else 0)
+
+
+def _gn_ws(device, batch):
+    sc = getattr(_tls, "scope", None)
+    if sc is not None and sc[0] is not None:
+        ws = sc[0]
+        if batch > ws.max_batch:
+            raise _lib.NhmcError("GroupNorm workspace of this scope is sized for %d samples, got %d" % (ws.max_batch, batch))
+        return ws
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    ws = _default_ws.get(key)
+    if ws is None or ws.max_batch < batch:
+        if torch.cuda.is_current_stream_capturing():
+            raise _lib.NhmcError("no GroupNorm workspace for this stream yet: warm up once before capturing, or open a kernels.gn_scope")
+        ws = _default_ws[key] = GnWorkspace(device, max(GN_MAX_BATCH, batch))
+    return ws
 
 
 def _stream():
@@ -215,10 +313,12 @@ def gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, groups, eps, channels_l
     """x,y: [B,C,H,W] tensors, either contiguous (NCHW) or channels_last memory format."""
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
+    ws = _gn_ws(x.device, B)
     with _timed("gn_fwd", 1, 2 * x.numel() * x.element_size()):
         check(lib().nhmc_gn_fwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(y),
                                 _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc), _p(in_bias),
-                                _in_bias_stride(in_bias, Cc), _p(stats), B, Cc, hw, groups, float(eps), _stream()), "nhmc_gn_fwd")
+                                _in_bias_stride(in_bias, Cc), _p(stats), B, Cc, hw, groups, float(eps), ws.buf.data_ptr(), ws.nbytes,
+                                _flags(), _stream()), "nhmc_gn_fwd")
 
 
 def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_last, in_bias=None, dx_add=None, dx_add2=None):
@@ -227,16 +327,25 @@ def gn_bwd(mode, x, dy, dx, gamma, beta, scale, shift, stats, groups, channels_l
     B, Cc = x.shape[0], x.shape[1]
     hw = x[0, 0].numel()
     n_add = (1 if dx_add is not None else 0) + (1 if dx_add2 is not None else 0)
+    ws = _gn_ws(x.device, B)
     with _timed("gn_bwd", 1, (3 + n_add) * x.numel() * x.element_size()):
         check(lib().nhmc_gn_bwd(mode, _lib.LAYOUT_NHWC if channels_last else _lib.LAYOUT_NCHW, _DT[x.dtype], _p(x), _p(dy),
                                 _p(dx), _p(gamma), _p(beta), _p(scale), _p(shift), _film_stride(scale, shift, Cc),
                                 _p(in_bias), _in_bias_stride(in_bias, Cc), _p(stats), 0, 0, _p(dx_add), _p(dx_add2), B, Cc, hw,
-                                groups, _stream()), "nhmc_gn_bwd")
+                                groups, ws.buf.data_ptr(), ws.nbytes, _flags(), _stream()), "nhmc_gn_bwd")
 
 
-def gn_check():
-    """Raises if a per-sample barrier of the resident GroupNorm path ever timed out (synchronises)."""
-    check(lib().nhmc_gn_check(), "nhmc_gn_check")
+def gn_check(ws=None):
+    """Raises if a per-sample barrier of the resident GroupNorm path timed out in `ws` (default: every workspace this
+    module created for the plain per-stream use, plus the current scope's).  Synchronises; the hot loop uses
+    GnWorkspace.poll() + raise_if_timed_out() around the synchronisation it has anyway."""
+    sc = getattr(_tls, "scope", None)
+    todo = [ws] if ws is not None else list(_default_ws.values()) + ([sc[0]] if sc is not None and sc[0] is not None else [])
+    for w in todo:
+        w.poll()
+    torch.cuda.synchronize()
+    for w in todo:
+        w.raise_if_timed_out()
 
 
 def softmax_fwd(logits, probs, scale):
@@ -259,14 +368,14 @@ def pool2_gather(in_big, out_small, scale):
     """channels-last 4-D tensors; out_small[b,:,i,j] = scale * sum of the 2x2 block of in_big."""
     B, Cc, h, w = out_small.shape
     with _timed("pool2_gather", 1, (in_big.numel() + out_small.numel()) * in_big.element_size()):
-        check(lib().nhmc_pool2_gather(_DT[in_big.dtype], _p(in_big), _p(out_small), B, h, w, Cc, float(scale), _stream()),
+        check(lib().nhmc_pool2_gather(_DT[in_big.dtype], _p(in_big), _p(out_small), B, h, w, Cc, float(scale), _flags(), _stream()),
               "nhmc_pool2_gather")
 
 
 def pool2_scatter(in_small, out_big, scale):
     B, Cc, h, w = in_small.shape
     with _timed("pool2_scatter", 1, (in_small.numel() + out_big.numel()) * in_small.element_size()):
-        check(lib().nhmc_pool2_scatter(_DT[in_small.dtype], _p(in_small), _p(out_big), B, h, w, Cc, float(scale), _stream()),
+        check(lib().nhmc_pool2_scatter(_DT[in_small.dtype], _p(in_small), _p(out_big), B, h, w, Cc, float(scale), _flags(), _stream()),
               "nhmc_pool2_scatter")
 
 
@@ -282,27 +391,29 @@ def bias_add(a, b, bias, out, c=None):
     B, Cc, H, W = a.shape
     nb = (a.numel() * (2 + (1 if b is not None else 0) + (1 if c is not None else 0))) * a.element_size()
     with _timed("bias_add", 1, nb):
-        check(lib().nhmc_bias_add(_DT[a.dtype], _p(a), _p(b), _p(c), _p(bias), _p(out), B * H * W, Cc, _stream()), "nhmc_bias_add")
+        check(lib().nhmc_bias_add(_DT[a.dtype], _p(a), _p(b), _p(c), _p(bias), _p(out), B * H * W, Cc, _flags(), _stream()), "nhmc_bias_add")
 
 
 def gn_cat_fwd(mode, x0, x1, y, gamma, beta, scale, shift, stats, groups, eps):
     """GroupNorm (+ follow-up) over the virtual concatenation cat([x0, x1], 1); all tensors channels-last."""
     B, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
     hw = x0[0, 0].numel()
+    ws = _gn_ws(x0.device, B)
     with _timed("gn_fwd", 2, 2 * y.numel() * y.element_size()):
         check(lib().nhmc_gn_cat_fwd(mode, _DT[x0.dtype], _p(x0), _p(x1), c0, c1, _p(y), _p(gamma), _p(beta), _p(scale),
                                     _p(shift), _film_stride(scale, shift, c0 + c1), _p(stats), B, hw, groups, float(eps),
-                                    _stream()), "nhmc_gn_cat_fwd")
+                                    ws.buf.data_ptr(), ws.nbytes, _flags(), _stream()), "nhmc_gn_cat_fwd")
 
 
 def gn_cat_bwd(mode, x0, x1, dy, dx0, dx1, gamma, beta, scale, shift, stats, groups, add0=None, add1=None):
     B, c0, c1 = x0.shape[0], x0.shape[1], x1.shape[1]
     hw = x0[0, 0].numel()
     n_add = (add0.numel() if add0 is not None else 0) + (add1.numel() if add1 is not None else 0)
+    ws = _gn_ws(x0.device, B)
     with _timed("gn_bwd", 2, (3 * dy.numel() + n_add) * dy.element_size()):
         check(lib().nhmc_gn_cat_bwd(mode, _DT[x0.dtype], _p(x0), _p(x1), c0, c1, _p(dy), _p(dx0), _p(dx1), _p(gamma), _p(beta),
                                     _p(scale), _p(shift), _film_stride(scale, shift, c0 + c1), _p(stats), _p(add0), _p(add1),
-                                    B, hw, groups, _stream()), "nhmc_gn_cat_bwd")
+                                    B, hw, groups, ws.buf.data_ptr(), ws.nbytes, _flags(), _stream()), "nhmc_gn_cat_bwd")
 
 
 def vq_nearest(z, codebook, zq, idx=None):

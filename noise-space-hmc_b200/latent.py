@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, kernels
-from .unet import (UNetModel, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_bias, _conv_nobias, group_norm_act,
+from .unet import (UNetModel, _derived, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_bias, _conv_nobias, group_norm_act,
                    group_norm_act_skip)
 
 VQ_GN_EPS = 1e-6          # model.py:37-38 Normalize()
@@ -86,15 +86,15 @@ class ResnetBlock(nn.Module):
             self.nin_shortcut = nn.Conv2d(in_channels, out_channels, 1)
 
     def _biases(self):
-        c = getattr(self, "_bias_cache", None)
-        b1 = self.conv1.bias
-        if c is None or c[0].device != b1.device:
-            b_out = self.conv2.bias.detach().float()
-            if self.in_channels != self.out_channels:
+        b1, b2 = self.conv1.bias, self.conv2.bias
+        has_nin = self.in_channels != self.out_channels
+
+        def build():
+            b_out = b2.detach().float()
+            if has_nin:
                 b_out = b_out + self.nin_shortcut.bias.detach().float()
-            c = (b1.detach().float().contiguous(), b_out.contiguous())
-            self._bias_cache = c
-        return c
+            return b1.detach().float().contiguous(), b_out.contiguous()
+        return _derived(self, "_bias_cache", (b1, b2) + ((self.nin_shortcut.bias,) if has_nin else ()), build)
 
     def forward(self, x):
         b1, b_out = self._biases()

@@ -44,8 +44,30 @@ class Operator:
     def meas_shape(self, B):
         return (B, self.meas_size())
 
+    def unclamped(self):
+        """A view of this operator whose loss_grad skips clamp(x_hat, -1, 1) and its mask (the latent path feeds the
+        un-clipped decoder output, main_sampling_latent.py:651): own descriptor and workspaces, shared tables.  The
+        original object is not modified."""
+        import copy
+        o = copy.copy(self)
+        o.desc = OpDesc.from_buffer_copy(self.desc)
+        o.desc.no_clamp = 1
+        o._ws = {}
+        return o
+
+    def _prepare_tables(self):
+        """Operator-owned derived tables (the tf32 hi/lo splits of the SVD factors the tensor-core GEMMs read), built once
+        by the library into a buffer this object owns; without them every call rebuilds them in its workspace."""
+        nb = int(lib().nhmc_op_tables_bytes(ctypes.byref(self.desc)))
+        if nb:
+            self._tc_tables = torch.empty((nb + 3) // 4, dtype=torch.float32, device=self.device)
+            check(lib().nhmc_op_prepare_tables(ctypes.byref(self.desc), self._tc_tables.data_ptr(), kernels._stream()),
+                  "nhmc_op_prepare_tables")
+            self.desc.tc_tables = self._tc_tables.data_ptr()
+
     def _workspace(self, B):
-        key = (B, kernels.LANE)       # lanes run concurrently: never share reduction scratch between them
+        # calls that may run concurrently (lanes / host threads on their own streams) never share reduction scratch
+        key = (B, torch.cuda.current_stream(self.device).cuda_stream)
         if key not in self._ws:
             self._ws[key] = kernels.zeros_workspace(lib().nhmc_op_workspace_bytes(ctypes.byref(self.desc), B), self.device)
         return self._ws[key]
@@ -198,7 +220,7 @@ def gaussian_taps(sigma, half=4):
 class Deblurring2D(Operator):
     """Y_c = U1 (G_c .* (V1^T X_c V2)) U2^T (Hfuncs.py:448-523, tiled-singulars quirk included)."""
     kind = _lib.OP_DEBLUR2D
-    loss_grad_launches = 9
+    loss_grad_launches = 10    # split of clamp(x_hat) + 8 tensor-core products + the clamped copy
 
     def __init__(self, kernel1, kernel2, channels, img_dim, device, tables=None, zero=3e-2):
         super().__init__(channels, img_dim, device)
@@ -226,6 +248,7 @@ class Deblurring2D(Operator):
         d = self.desc
         d.U1, d.V1, d.U2, d.V2 = (t.data_ptr() for t in (self.U_small1, self.V_small1, self.U_small2, self.V_small2))
         d.gain, d.gain_pinv = self.gain.data_ptr(), self.gain_pinv.data_ptr()
+        self._prepare_tables()
 
 
 class Deblurring(Deblurring2D):
@@ -300,6 +323,7 @@ class SRConv(Operator):
         self.P = ((Vd * Sinv[None, :]) @ U.t()).contiguous().to(self.device)         # [D, d]
         self.desc.ratio = self.ratio
         self.desc.U1, self.desc.V1 = self.L.data_ptr(), self.P.data_ptr()
+        self._prepare_tables()
 
 
 class WalshHadamardCS(Operator):

@@ -13,7 +13,9 @@ work runs:
     counter in a device array, so B independent replicas of the (batch-1-only) reference algorithm
     advance in lock step with no host round trip inside an iteration.
 """
+import copy
 import math
+import warnings
 
 import numpy as np
 import torch
@@ -167,36 +169,37 @@ class HMCSampler:
         self._last = {}              # mode -> [(lo, hi, g_a, g_b)] of that step variant's evaluation (static buffers under graphs)
         self.n_lanes = max(1, min(int(lanes), self.B, 8))
         self.lanes = None
+        # GroupNorm scratch of the score network's fused epilogues: owned by THIS sampler (one per lane), so samplers on
+        # other host threads / streams never share accumulators with it (include/nhmc.h: the library keeps no state)
+        self.gn_ws = kernels.GnWorkspace(dev, self.B)
         if self.n_lanes > 1:
             bounds = [(i * self.B) // self.n_lanes for i in range(self.n_lanes + 1)]
             self.lanes = [dict(idx=i, lo=lo, hi=hi, ev=e, chains=self.chains.view(lo, hi - lo),
-                               ws=kernels.leapfrog_workspace(hi - lo, dev), stream=torch.cuda.Stream(device=dev))
+                               ws=kernels.leapfrog_workspace(hi - lo, dev), stream=torch.cuda.Stream(device=dev),
+                               gn_ws=kernels.GnWorkspace(dev, hi - lo))
                           for i, (lo, hi, e) in enumerate(zip(bounds[:-1], bounds[1:], evaluator.split(bounds)))]
 
     # ---- one gradient evaluation + leapfrog kernel, eager or as a replayed CUDA graph -------------------
     def _step_eager(self, mode):
         src = self.x if mode == _lib.LF_FIRST else self.x_prop
         if self.lanes is None:
-            loss, g_a, g_b, _ = self.ev(src)
+            with kernels.gn_scope(self.gn_ws, 1):
+                loss, g_a, g_b, _ = self.ev(src)
             self._last[mode] = [(0, self.B, g_a, g_b)]
             kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
             return
         cur = torch.cuda.current_stream()
         last = []
-        try:
-            for ln in self.lanes:                       # fork: every group on its own stream
-                lo, hi = ln["lo"], ln["hi"]
-                ln["stream"].wait_stream(cur)
-                kernels.set_lane(ln["idx"], self.n_lanes)
-                with torch.cuda.stream(ln["stream"]):
-                    loss, g_a, g_b, _ = ln["ev"](src[lo:hi])
-                    kernels.leapfrog(mode, src[lo:hi], self.x_prop[lo:hi], self.p[lo:hi], g_a, g_b, loss, ln["chains"],
-                                     self.mass, ln["ws"])
-                last.append((lo, hi, g_a, g_b))
-            for ln in self.lanes:                       # join
-                cur.wait_stream(ln["stream"])
-        finally:
-            kernels.set_lane(0, 1)
+        for ln in self.lanes:                           # fork: every group on its own stream, with its own GroupNorm scratch
+            lo, hi = ln["lo"], ln["hi"]
+            ln["stream"].wait_stream(cur)
+            with torch.cuda.stream(ln["stream"]), kernels.gn_scope(ln["gn_ws"], self.n_lanes):
+                loss, g_a, g_b, _ = ln["ev"](src[lo:hi])
+                kernels.leapfrog(mode, src[lo:hi], self.x_prop[lo:hi], self.p[lo:hi], g_a, g_b, loss, ln["chains"],
+                                 self.mass, ln["ws"])
+            last.append((lo, hi, g_a, g_b))
+        for ln in self.lanes:                           # join
+            cur.wait_stream(ln["stream"])
         self._last[mode] = last
         self.ev.n_net_fwd = sum(ln["ev"].n_net_fwd for ln in self.lanes) // self.n_lanes
         self.ev.n_net_vjp = sum(ln["ev"].n_net_vjp for ln in self.lanes) // self.n_lanes
@@ -301,6 +304,18 @@ class HMCSampler:
         loss_h = self.ev.loss.cpu()               # synchronises: the step's result is on the host
         return {"loss": loss_h, "bytes": 2 * x_host.numel() * 4 + loss_h.numel() * 8}
 
+    def gn_workspaces(self):
+        return [self.gn_ws] + ([ln["gn_ws"] for ln in self.lanes] if self.lanes else [])
+
+    def poll_gn(self):
+        """Queue copies of the GroupNorm workspaces' timeout flags (no sync); check_gn() after the next synchronisation."""
+        for w in self.gn_workspaces():
+            w.poll()
+
+    def check_gn(self):
+        for w in self.gn_workspaces():
+            w.raise_if_timed_out()
+
     def collected(self):
         """[B, S, ...] samples in collection order (S = min(n_collected, n_slots), same for all finished chains)."""
         st = self.chains.read()
@@ -331,7 +346,9 @@ def _run(sampler, momentum, uniform, max_iters, on_iteration):
             break
         p = momentum(sampler.x)
         xc = sampler.iteration(p, uniform(sampler.B))
+        sampler.poll_gn()
         st = sampler.chains.read()                             # the one host sync per iteration
+        sampler.check_gn()                                     # a barrier timeout of the resident GroupNorm kernels raises here
         if on_iteration is not None:
             on_iteration(it, st, xc)
         it += 1
@@ -346,8 +363,108 @@ def _model_of(algo):
     return algo.model
 
 
+def _unconditional_step(xt, eps, at, at_next):
+    """Unconditional.cal_x0 + map_back in closed form (algos/unconditional.py:17-28)."""
+    x0 = ((xt - eps * (1 - at).sqrt()) / at.sqrt()).clip(-1, 1)
+    return at_next.sqrt() * x0 + (1 - at_next).sqrt() * eps
+
+
+def plugin_is_unconditional(algo, channels, device, noise="ddpm"):
+    """True when `algo` has no cal_x0 / map_back of its own (a bare object with `.model`) or when its cal_x0 + map_back
+    reproduce Unconditional's (algos/unconditional.py:9-28) on a probe: random xt through the plugin with a stub score
+    network against the closed form the fused epilogue kernels implement.  A Base_Algo subclass that does anything else
+    (base_algo.py:3-16) is NOT silently replaced by the fused epilogue: hmc() then differentiates the plugin itself."""
+    if not (callable(getattr(algo, "cal_x0", None)) and callable(getattr(algo, "map_back", None))):
+        return True
+    gen = torch.Generator().manual_seed(7)
+    n, d = 2, 8
+    xt = (3.0 * torch.randn(n, channels, d, d, generator=gen)).to(device)
+    eps = torch.randn(n, 2 * channels, d, d, generator=gen).to(device)
+    y_0 = torch.zeros(n, channels * d * d, device=device)
+    at = torch.full((n, 1, 1, 1), 0.0778, device=device)
+    at_next = torch.full((n, 1, 1, 1), 0.5214, device=device)
+    t = torch.ones(n, device=device) * 500
+    real = algo.model
+    try:
+        try:
+            algo.model = lambda x_, t_, *a, **k: eps
+        except Exception:
+            return False                                   # cannot probe: treat as a custom plugin
+        with torch.no_grad():
+            x0_t, add_up = algo.cal_x0(xt, t, at, at_next, y_0, noise)
+            out = algo.map_back(x0_t, y_0, add_up, at_next, at)
+    except Exception:
+        return False
+    finally:
+        try:
+            algo.model = real
+        except Exception:
+            pass
+    want = _unconditional_step(xt, eps[:, :channels], at, at_next)
+    return out.shape == want.shape and bool((out.float() - want).abs().max() <= 1e-5 * float(want.abs().max()))
+
+
+class PluginGradEvaluator:
+    """loss and gradient through ANY Base_Algo plugin: cal_x0 / map_back are called exactly as iterative_sampling does
+    (main_sampling.py:898-915) and differentiated by autograd; only the measurement loss + adjoint run in the fused
+    operator kernel.  The slow but faithful route for plugins that are not `Unconditional`."""
+
+    def __init__(self, algo, b, seq, seq_next, op, y, y_0, example_x, noise):
+        self.algo, self.b, self.seq, self.seq_next, self.op, self.y, self.y_0, self.noise = algo, b, list(seq), list(seq_next), op, y, y_0, noise
+        self.B, self.N = example_x.shape[0], example_x[0].numel()
+        self.g_hat = torch.empty_like(example_x)
+        self.xc = torch.empty_like(example_x)
+        self.loss = torch.zeros(self.B, dtype=torch.float64, device=example_x.device)
+        self.n_net_fwd = self.n_net_vjp = 0
+        # (t, at, at_next) of every step, formed once exactly as iterative_sampling forms them per call
+        # (main_sampling.py:903-906): constants of the run, and host->device copies could not be captured into a graph
+        self.sched = []
+        dev = example_x.device
+        for i, j in zip(reversed(self.seq), reversed(self.seq_next)):
+            t = (torch.ones(self.B) * i).to(dev)
+            next_t = (torch.ones(self.B) * j).to(dev)
+            self.sched.append((t, schedule.compute_alpha(b.to(dev), t.long()), schedule.compute_alpha(b.to(dev), next_t.long())))
+
+    def split(self, bounds):
+        raise _lib.NhmcError("lanes are not available with a custom algo plugin")
+
+    def __call__(self, x):
+        xk = x.detach().requires_grad_(True)
+        with torch.enable_grad():
+            xt = xk
+            for t, at, at_next in self.sched:
+                x0_t, add_up = self.algo.cal_x0(xt, t, at, at_next, self.y_0, self.noise)
+                xt = self.algo.map_back(x0_t, self.y_0, add_up, at_next, at)
+                self.n_net_fwd += 1
+        self.op.loss_grad(xt.detach().float().contiguous(), self.y, g=self.g_hat, xc=self.xc, loss=self.loss)
+        (g,) = torch.autograd.grad(xt, xk, self.g_hat.to(xt.dtype))
+        self.n_net_vjp += len(self.seq)
+        return self.loss, g.float().contiguous(), None, self.xc
+
+
+def _capture(smp, cuda_graphs, model):
+    """cuda_graphs True: capture (errors propagate); False: eager; None (default): capture, and fall back to eager
+    launches with a warning if the score network cannot be captured (host syncs / data-dependent control flow inside a
+    third-party model) -- our own networks always capture."""
+    if cuda_graphs is False:
+        return
+    if cuda_graphs is True:
+        smp.capture_graphs()
+        return
+    try:
+        smp.capture_graphs()
+    except Exception as e:                                     # noqa: BLE001  (third-party model code)
+        from . import unet
+        if isinstance(model, unet.UNetModel):
+            raise
+        smp._graphs = None
+        torch.cuda.synchronize()
+        warnings.warn("nhmc_b200: the score network could not be captured into CUDA graphs (%s: %s); running eager "
+                      "launches (slower)" % (type(e).__name__, e))
+
+
 def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=False, reuse_gradient=False, lanes=1):
+        max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=None, reuse_gradient=False, lanes=1):
     """Drop-in for main_sampling.hmc (main_sampling.py:660-774).
 
     x: [B,3,H,W] initial noise; b: fp32 betas [1000]; seq/seq_next: timestep lists; algo: object with
@@ -355,7 +472,13 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
     doubled by prepare_measurement, main_sampling.py:348); y_0: measurement; H_funcs: a reference
     operator object or one of nhmc_b200.operators.  Returns the 20 collected samples, `[20,3,H,W]` for
     B == 1 (exactly the reference's return) and `[B,20,3,H,W]` for B > 1 (B independent chains -- the
-    reference itself cannot run B > 1, main_sampling.py:719-720).
+    reference itself cannot run B > 1, main_sampling.py:719-720; if the chains collected different numbers of
+    samples -- max_iters cut them short -- every chain is truncated to the smallest count).
+
+    The three step variants are captured as CUDA graphs by default (cuda_graphs=None: with an eager fallback for
+    score networks that cannot be captured; True: capture or raise; False / opt.cuda_graphs == False: eager).
+    A plugin whose cal_x0 / map_back are not Unconditional's (algos/unconditional.py) is differentiated by autograd
+    instead of being replaced by the fused DDIM epilogue (PluginGradEvaluator).
     """
     if not x.is_cuda:
         raise _lib.NhmcError("hmc() runs on a CUDA device (sm_100a); there is no CPU fallback")
@@ -363,25 +486,33 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
     assert n == B, "n must equal the batch size (main_sampling.py:472)"
     model = _model_of(algo)
     op = operators.from_reference(H_funcs, C, D, x.device)
-    steps = schedule.ddim_steps(schedule.alpha_table(b), seq, seq_next)
     y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
     m = float(getattr(opt, "m", 1.0))
-    ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
+    noise = getattr(opt, "noise", "ddpm")
+    if plugin_is_unconditional(algo, C, x.device, noise):
+        steps = schedule.ddim_steps(schedule.alpha_table(b), seq, seq_next)
+        ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
+    else:
+        ev = PluginGradEvaluator(algo, b, seq, seq_next, op, y, y_0, x.detach().float().contiguous(), noise)
     smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_PIXEL, n_slots=20,
                      reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False),
                      lanes=max(int(lanes), int(getattr(opt, "lanes", 1) or 1)))
-    if cuda_graphs or getattr(opt, "cuda_graphs", False):
-        smp.capture_graphs()
+    if cuda_graphs is None and getattr(opt, "cuda_graphs", None) is not None:
+        cuda_graphs = bool(opt.cuda_graphs)
+    _capture(smp, cuda_graphs, model)
     dm, du = _default_draws(m)
     _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
     if return_sampler:
         return smp
     out = smp.collected()
-    return out[0] if B == 1 else torch.stack(out)
+    if B == 1:
+        return out[0]
+    s_min = min(o.shape[0] for o in out)
+    return torch.stack([o[:s_min] for o in out])
 
 
 def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
-               max_iters=None, on_iteration=None, return_sampler=False, image_size=256, reuse_gradient=False):
+               max_iters=None, on_iteration=None, return_sampler=False, image_size=256, reuse_gradient=False, cuda_graphs=None):
     """Drop-in for main_sampling_latent.hmc_latent (main_sampling_latent.py:623-762).
 
     algo.model is an LDM object exposing `.apply_model(z,t,None)` (no-grad, ddpm.py:892-893),
@@ -393,8 +524,9 @@ def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum
     B = x.shape[0]
     assert n == B
     ldm = _model_of(algo)
-    op = operators.from_reference(H_funcs, 3, image_size, x.device)
-    op.set_clamp(False)        # the decoded image is NOT clipped in the latent loss (main_sampling_latent.py:651)
+    # the decoded image is NOT clipped in the latent loss (main_sampling_latent.py:651): an unclamped VIEW of the operator
+    # (own descriptor, shared tables) -- the caller's object keeps its clamp for any pixel-space use
+    op = operators.from_reference(H_funcs, 3, image_size, x.device).unclamped()
     table = schedule.latent_alpha_table(ldm.alphas_cumprod, ldm.alphas_cumprod_prev)
     steps = schedule.ddim_steps(table, seq, seq_next)
     y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
@@ -405,6 +537,9 @@ def hmc_latent(x, n, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum
     smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=m, sched=_lib.SCHED_LATENT,
                      sigma_y=opt.sigma_y, n_slots=10,
                      reuse_gradient=reuse_gradient or getattr(opt, "reuse_gradient", False))
+    if cuda_graphs is None and getattr(opt, "cuda_graphs", None) is not None:
+        cuda_graphs = bool(opt.cuda_graphs)
+    _capture(smp, cuda_graphs, ldm)
     dm, du = _default_draws(m)
     _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
     if return_sampler:

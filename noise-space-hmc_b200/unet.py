@@ -48,7 +48,7 @@ class _GroupNormAct(torch.autograd.Function):
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
         kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, eps, cl, in_bias)
         ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
-        ctx.mode, ctx.cl = mode, cl
+        ctx.mode, ctx.cl, ctx.scope = mode, cl, kernels.current_scope()
         return y
 
     @staticmethod
@@ -56,7 +56,8 @@ class _GroupNormAct(torch.autograd.Function):
         x, gamma, beta, scale, shift, stats, in_bias = ctx.saved_tensors
         dy = dy.contiguous(memory_format=torch.channels_last) if ctx.cl else dy.contiguous()
         dx = torch.empty_like(x)
-        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, ctx.cl, in_bias)
+        with kernels.scope_of(ctx.scope):
+            kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, ctx.cl, in_bias)
         return dx, None, None, None, None, None, None, None
 
 
@@ -74,7 +75,7 @@ class _CatGroupNormAct(torch.autograd.Function):
         stats = torch.empty(B, GROUPS, 2, dtype=torch.float32, device=x0.device)
         kernels.gn_cat_fwd(mode, x0, x1, y, gamma, beta, None, None, stats, GROUPS, GN_EPS)
         ctx.save_for_backward(x0, x1, gamma, beta, stats)
-        ctx.mode = mode
+        ctx.mode, ctx.scope = mode, kernels.current_scope()
         return y, x0.view_as(x0), x1.view_as(x1)
 
     @staticmethod
@@ -84,7 +85,8 @@ class _CatGroupNormAct(torch.autograd.Function):
         d0 = _cl(d0) if d0 is not None else None
         d1 = _cl(d1) if d1 is not None else None
         dx0, dx1 = torch.empty_like(x0), torch.empty_like(x1)
-        kernels.gn_cat_bwd(ctx.mode, x0, x1, dy, dx0, dx1, gamma, beta, None, None, stats, GROUPS, add0=d0, add1=d1)
+        with kernels.scope_of(ctx.scope):
+            kernels.gn_cat_bwd(ctx.mode, x0, x1, dy, dx0, dx1, gamma, beta, None, None, stats, GROUPS, add0=d0, add1=d1)
         return dx0, dx1, None, None, None
 
 
@@ -175,7 +177,7 @@ class _GroupNormActSkip(torch.autograd.Function):
         stats = torch.empty(x.shape[0], GROUPS, 2, dtype=torch.float32, device=x.device)
         kernels.gn_fwd(mode, x, y, gamma, beta, scale, shift, stats, GROUPS, eps, True, in_bias)
         ctx.save_for_backward(x, gamma, beta, scale, shift, stats, in_bias)
-        ctx.mode, ctx.fork = mode, fork
+        ctx.mode, ctx.fork, ctx.scope = mode, fork, kernels.current_scope()
         if fork:
             return y, x.view_as(x), x.view_as(x)
         return y, x.view_as(x)
@@ -189,8 +191,9 @@ class _GroupNormActSkip(torch.autograd.Function):
             return ((adds[0] + adds[1]) if len(adds) == 2 else (adds[0] if adds else None),) + none
         dy = _cl(dy)
         dx = torch.empty_like(x)
-        kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias,
-                       dx_add=adds[0] if adds else None, dx_add2=adds[1] if len(adds) == 2 else None)
+        with kernels.scope_of(ctx.scope):
+            kernels.gn_bwd(ctx.mode, x, dy, dx, gamma, beta, scale, shift, stats, GROUPS, True, in_bias,
+                           dx_add=adds[0] if adds else None, dx_add2=adds[1] if len(adds) == 2 else None)
         return (dx,) + none
 
 
@@ -203,6 +206,7 @@ class _AvgPool2(torch.autograd.Function):
         B, C, H, W = x.shape
         y = torch.empty((B, C, H // 2, W // 2), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         kernels.pool2_gather(x, y, 0.25)
+        ctx.scope = kernels.current_scope()
         return y
 
     @staticmethod
@@ -210,7 +214,8 @@ class _AvgPool2(torch.autograd.Function):
         dy = _cl(dy)
         B, C, h, w = dy.shape
         dx = torch.empty((B, C, 2 * h, 2 * w), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
-        kernels.pool2_scatter(dy, dx, 0.25)
+        with kernels.scope_of(ctx.scope):
+            kernels.pool2_scatter(dy, dx, 0.25)
         return dx
 
 
@@ -223,6 +228,7 @@ class _Upsample2(torch.autograd.Function):
         B, C, h, w = x.shape
         y = torch.empty((B, C, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         kernels.pool2_scatter(x, y, 1.0)
+        ctx.scope = kernels.current_scope()
         return y
 
     @staticmethod
@@ -230,7 +236,8 @@ class _Upsample2(torch.autograd.Function):
         dy = _cl(dy)
         B, C, H, W = dy.shape
         dx = torch.empty((B, C, H // 2, W // 2), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
-        kernels.pool2_gather(dy, dx, 1.0)
+        with kernels.scope_of(ctx.scope):
+            kernels.pool2_gather(dy, dx, 1.0)
         return dx
 
 
@@ -290,6 +297,18 @@ def group_norm_act_skip(x, norm, mode, fork=False):
     return _GroupNormActSkip.apply(x, norm.weight, norm.bias, None, None, mode, None, getattr(norm, "eps", GN_EPS), fork)
 
 
+def _derived(owner, name, sources, build):
+    """A tensor derived from frozen parameters (fp32 bias copies, split / concatenated weights), cached on `owner` and
+    keyed on (storage, version, device, dtype) of every source: load_state_dict, .to() and in-place edits of a
+    parameter all invalidate it, so a warm-up before the checkpoint is loaded cannot leave stale biases behind."""
+    key = tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in sources)
+    c = owner.__dict__.get(name)
+    if c is None or c[0] != key:
+        c = (key, build())
+        owner.__dict__[name] = c
+    return c[1]
+
+
 def _conv_nobias(conv, x):
     return F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
 
@@ -297,10 +316,7 @@ def _conv_nobias(conv, x):
 def _conv_bias(conv, x):
     """conv(x) + bias with the bias added by our channels-last kernel: on large maps PyTorch adds a convolution's
     bias as a separate broadcast TensorIterator pass at ~1.6 TB/s (324 us on the [8,256,256,256] decoder map)."""
-    b32 = getattr(conv, "_bias_f32", None)
-    if b32 is None or b32.device != conv.bias.device:
-        b32 = conv.bias.detach().float().contiguous()
-        conv._bias_f32 = b32
+    b32 = _derived(conv, "_bias_f32", (conv.bias,), lambda: conv.bias.detach().float().contiguous())
     return _BiasAdd.apply(_conv_nobias(conv, x), None, b32)
 
 
@@ -384,24 +400,21 @@ class ResBlock(nn.Module):
     def _split_skip_weights(self, c0):
         """The skip 1x1 convolution's (frozen) weight split at input channel c0, as two dense channels-last filters."""
         w = self.skip_connection.weight
-        cache = getattr(self, "_skip_split", None)
-        if cache is None or cache[0] != c0 or cache[1].device != w.device or cache[1].dtype != w.dtype:
-            cl = torch.channels_last
-            cache = (c0, w.detach()[:, :c0].contiguous(memory_format=cl), w.detach()[:, c0:].contiguous(memory_format=cl))
-            self._skip_split = cache
-        return cache[1], cache[2]
+        cl = torch.channels_last
+        return _derived(self, "_skip_split%d" % c0, (w,),
+                        lambda: (w.detach()[:, :c0].contiguous(memory_format=cl), w.detach()[:, c0:].contiguous(memory_format=cl)))
 
     def _fp32_biases(self):
         """fp32 copies of the conv biases (weights are frozen; cached after the first call)."""
-        cache = getattr(self, "_bias_cache", None)
-        b = self.in_layers[2].bias
-        if cache is None or cache[0].device != b.device:
-            b_out = self.out_layers[3].bias.detach().float()
-            if not isinstance(self.skip_connection, nn.Identity):
+        b, b2 = self.in_layers[2].bias, self.out_layers[3].bias
+        has_skip = not isinstance(self.skip_connection, nn.Identity)
+
+        def build():
+            b_out = b2.detach().float()
+            if has_skip:
                 b_out = b_out + self.skip_connection.bias.detach().float()
-            cache = (b.detach().float().contiguous(), b_out.contiguous())
-            self._bias_cache = cache
-        return cache
+            return b.detach().float().contiguous(), b_out.contiguous()
+        return _derived(self, "_bias_cache", (b, b2) + ((self.skip_connection.bias,) if has_skip else ()), build)
 
 
 class Downsample(nn.Module):
@@ -442,9 +455,7 @@ class AttentionBlock(nn.Module):
         # Every operand is a VIEW handed to a (strided-)batched GEMM, forward and backward (_AttentionCore)
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
         h = _AttentionCore.apply(tok, self.qkv.weight[:, :, 0], self.qkv.bias, self.proj_out.weight[:, :, 0], None, nh)
-        b32 = getattr(self, "_proj_bias_f32", None)
-        if b32 is None or b32.device != x.device:
-            b32 = self._proj_bias_f32 = self.proj_out.bias.detach().float().contiguous()
+        b32 = _derived(self, "_proj_bias_f32", (self.proj_out.bias,), lambda: self.proj_out.bias.detach().float().contiguous())
         # x + proj_out(a) (unet_ffhq.py:365): residual and proj_out's bias in ONE pass; h [B, T, C] IS channels-last [B, C, H, W]
         return _BiasAdd.apply(x, h.view(B, H, W, C).permute(0, 3, 1, 2), b32)
 
@@ -509,18 +520,14 @@ class UNetModel(nn.Module):
 
     def _first_bias(self):
         b = self.input_blocks[0][0].bias
-        c = getattr(self, "_first_bias_cache", None)
-        if c is None or c.device != b.device:
-            c = b.detach().float().contiguous()
-            self._first_bias_cache = c
-        return c
+        return _derived(self, "_first_bias_cache", (b,), lambda: b.detach().float().contiguous())
 
     def _emb_projection(self, emb_act):
         """All ResBlocks' emb_layers Linear (unet_ffhq.py:263-270) as ONE GEMM on concatenated (frozen) weights;
         returns {block: fp32 view [B, n_out]} into the single result (29 GEMMs + 87 copy kernels -> 1 + 1)."""
         cache = getattr(self, "_emb_cache", None)
-        w0 = self.time_embed[0].weight
-        if cache is None or cache[0].device != w0.device or cache[0].dtype != w0.dtype:
+        wkey = self._emb_weights_key()
+        if cache is None or cache[4] != wkey:
             blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
             W = torch.cat([m.emb_layers[1].weight.detach() for m in blocks], 0).contiguous()
             b = torch.cat([m.emb_layers[1].bias.detach() for m in blocks], 0).contiguous()
@@ -535,13 +542,25 @@ class UNetModel(nn.Module):
                 n = m.emb_layers[1].weight.shape[0]
                 offs.append((m, o, n))
                 o += n
-            cache = (W, b, offs, b1_all)
+            cache = (W, b, offs, b1_all, wkey)
             self._emb_cache = cache
-        W, b, offs, b1_all = cache
+        W, b, offs, b1_all, _ = cache
         e_all = F.linear(emb_act, W, b).float()
         if b1_all is not None:
             e_all = e_all + b1_all
         return {m: e_all[:, o: o + n] for m, o, n in offs}
+
+    def _emb_weights_key(self):
+        """(storage, version, device, dtype) of every parameter the embedding path reads: any reload / cast / in-place
+        edit invalidates the concatenated projection and the per-timestep memo."""
+        blocks = getattr(self, "_res_blocks", None)
+        if blocks is None:
+            blocks = [m for m in self.modules() if isinstance(m, ResBlock)]
+            self.__dict__["_res_blocks"] = blocks
+        ps = [self.time_embed[0].weight, self.time_embed[0].bias, self.time_embed[2].weight, self.time_embed[2].bias]
+        for m in blocks:
+            ps += [m.emb_layers[1].weight, m.emb_layers[1].bias, m.in_layers[2].bias]
+        return tuple((t.data_ptr(), t._version, t.device, t.dtype) for t in ps)
 
     def _embeddings(self, timesteps):
         """{block: emb_layers(time_embed(timestep_embedding(t)))} (unet_ffhq.py:716, 263-270).  The sampler calls the
@@ -551,32 +570,23 @@ class UNetModel(nn.Module):
         memo = getattr(self, "_emb_memo", None)
         if memo is None:
             memo = self._emb_memo = []
-        w0 = self.time_embed[0].weight
-        for t_ref, ver, dev, dtp, embs in memo:
-            if t_ref is timesteps and ver == timesteps._version and dev == w0.device and dtp == w0.dtype:
+        wkey = self._emb_weights_key()
+        for t_ref, ver, key, embs in memo:
+            if t_ref is timesteps and ver == timesteps._version and key == wkey:
                 return embs
         with torch.no_grad():
             emb = self.time_embed(timestep_embedding(timesteps, self.model_channels).to(self.compute_dtype))
             emb_act = F.silu(emb)                              # the SiLU that opens every emb_layers (unet_ffhq.py:263)
             embs = self._emb_projection(emb_act)
         if not torch.cuda.is_current_stream_capturing():       # never keep graph-pool memory alive from here
-            memo.append((timesteps, timesteps._version, w0.device, w0.dtype, embs))
+            memo.append((timesteps, timesteps._version, wkey, embs))
             del memo[:-32]
         return embs
 
     def load_state_dict(self, *args, **kwargs):
         r = super().load_state_dict(*args, **kwargs)
-        self._first_bias_cache = None
-        self._emb_cache = None
+        self._emb_cache = None      # (the bias / split-weight caches are keyed on their parameters' versions: _derived)
         self._emb_memo = None
-        for m in self.modules():
-            if isinstance(m, ResBlock):
-                m._bias_cache = None
-                m._skip_split = None
-            if isinstance(m, nn.Conv2d) and hasattr(m, "_bias_f32"):
-                m._bias_f32 = None
-            if isinstance(m, AttentionBlock):
-                m._proj_bias_f32 = None
         return r
 
     def prepare(self, device="cuda"):

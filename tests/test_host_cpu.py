@@ -30,7 +30,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_struct_layouts_match():
     l = nhmc_b200.lib()
     assert l.nhmc_sizeof_chain() == chain.CHAIN_DTYPE.itemsize == 144
-    assert ctypes.sizeof(_lib.OpDesc) == l.nhmc_sizeof_op() == 144
+    assert ctypes.sizeof(_lib.OpDesc) == l.nhmc_sizeof_op() == 152
     st = chain.new_host_state(3, 1.0, 0.05, 0.1)
     assert st["active"].tolist() == [1, 1, 1] and st["slot"].tolist() == [-1, -1, -1]
 

@@ -386,3 +386,99 @@ def test_hmc_latent_drop_in_call(golden):
     out = smp.collected()[0]
     assert out.shape[1:] == (3, 16, 16) and out.shape[0] == int(st["n_collected"][0]) <= 10
     assert torch.isfinite(smp.x).all()
+
+
+class _Unconditional:
+    """The reference's plugin, restated for the test (algos/unconditional.py:4-28, base_algo.py:3-16)."""
+
+    def __init__(self, model, H_funcs=None, sigma_0=0.0, cls_fn=None):
+        self.model, self.H_funcs, self.sigma_0, self.cls_fn = model, H_funcs, sigma_0, cls_fn
+
+    @torch.enable_grad()
+    def cal_x0(self, xt, t, at, at_next, y_0, noise="ddpm", classes=None):
+        et = self.model(xt, t)
+        if et.size(1) == 6:
+            et = et[:, :3]
+        x0_t = ((xt - et * (1 - at).sqrt()) / at.sqrt()).clip(-1, 1)
+        return x0_t, (1 - at_next).sqrt() * et
+
+    def map_back(self, x0_t, y_0, add_up, at_next, at):
+        return at_next.sqrt() * x0_t + add_up
+
+
+class _SoftClipPlugin(_Unconditional):
+    """A Base_Algo subclass that is NOT Unconditional: tanh instead of the hard clip."""
+
+    @torch.enable_grad()
+    def cal_x0(self, xt, t, at, at_next, y_0, noise="ddpm", classes=None):
+        et = self.model(xt, t)[:, :3]
+        x0_t = torch.tanh((xt - et * (1 - at).sqrt()) / at.sqrt())
+        return x0_t, (1 - at_next).sqrt() * et
+
+
+def test_plugin_honesty_custom_algo_is_differentiated_not_replaced(golden):
+    """hmc() used to ignore algo.cal_x0 / map_back.  Now a plugin that reproduces Unconditional takes
+    the fused DDIM epilogue, any other Base_Algo subclass is run through its own cal_x0 / map_back under autograd
+    (main_sampling.py:898-915) -- checked against a plain torch restatement of that plugin on the CPU."""
+    import nhmc_b200
+    from nhmc_b200 import sampler, schedule
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    dev = torch.device("cuda")
+    assert sampler.plugin_is_unconditional(types.SimpleNamespace(model=net, cls_fn=None), 3, dev)
+    assert sampler.plugin_is_unconditional(_Unconditional(net), 3, dev)
+    soft = _SoftClipPlugin(net)
+    assert not sampler.plugin_is_unconditional(soft, 3, dev)
+    assert soft.model is net                                              # the probe restores the plugin's model
+    B = 2
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    y = T(g["y_0"]).repeat(B, 1) + 0.05 * torch.randn(B, g["y_0"].shape[1], generator=gen)
+    b = _betas()
+    ev = sampler.PluginGradEvaluator(soft, b.cuda(), SEQ, SEQ_NEXT, op, y.cuda(), y.cuda(), x.cuda(), "ddpm")
+    loss, ga, gb, xc = ev(x.cuda())
+    assert gb is None
+    # plain torch on the CPU: the same plugin with the CPU copy of the network, loss through the oracle operator
+    cpu = _SoftClipPlugin(net_cpu)
+    xk = x.clone().requires_grad_(True)
+    xt = xk
+    for i, j in zip(reversed(SEQ), reversed(SEQ_NEXT)):
+        t = torch.ones(B) * i
+        at = schedule.compute_alpha(b, t.long()); at_next = schedule.compute_alpha(b, (torch.ones(B) * j).long())
+        x0_t, add_up = cpu.cal_x0(xt, t, at, at_next, y)
+        xt = cpu.map_back(x0_t, y, add_up, at_next, at)
+    r = y - oop.H(xt.clip(-1, 1))
+    ref_loss = (r ** 2).sum(1)
+    (ref_g,) = torch.autograd.grad(ref_loss.sum(), xk)
+    np.testing.assert_allclose(xc.cpu().numpy(), xt.detach().clip(-1, 1).numpy(), atol=1e-4)
+    np.testing.assert_allclose(loss.cpu().numpy(), ref_loss.detach().double().numpy(), rtol=1e-4)
+    np.testing.assert_allclose(ga.cpu().numpy(), ref_g.numpy(), atol=2e-4 * float(ref_g.abs().max()))
+    # and the drop-in call takes that route end to end (two iterations, graphs by default)
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=0.1, algo="hmc", noise="ddpm")
+    smp = nhmc_b200.hmc(x[:1].cuda(), 1, b.cuda(), SEQ, SEQ_NEXT, soft, opt, y[:1].cuda(), op, None, max_iters=2, return_sampler=True)
+    assert isinstance(smp.ev, sampler.PluginGradEvaluator) and smp._graphs is not None
+    assert torch.isfinite(smp.x).all()
+
+
+def test_drop_in_defaults_to_cuda_graphs(golden):
+    """the two-line swap of INTEGRATION.md gets the benchmarked (graph-replay) mode by default;
+    cuda_graphs=False / opt.cuda_graphs=False opt out; both give the same chain under the same draws."""
+    import nhmc_b200
+    g, net_cpu, net, op, oop, tab = _setup(golden)
+    x = T(g["x_init"]).cuda(); y = T(g["y_0"]).cuda()
+    algo = types.SimpleNamespace(model=net, cls_fn=None)
+    res = {}
+    det = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        for name, kw, optkw in (("default", {}, {}), ("eager", dict(cuda_graphs=False), {}), ("opt_eager", {}, dict(cuda_graphs=False))):
+            opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=float(g["sigma_0"]), algo="hmc", noise="ddpm", **optkw)
+            torch.manual_seed(99)
+            gen = torch.Generator(device="cuda").manual_seed(3)
+            mom = lambda x_: torch.randn(x_.shape, device=x_.device, generator=gen)
+            smp = nhmc_b200.hmc(x, 1, _betas().cuda(), SEQ, SEQ_NEXT, algo, opt, y, op, None, max_iters=3, momentum=mom,
+                                return_sampler=True, **kw)
+            res[name] = (smp._graphs is not None, smp.x.cpu().clone(), smp.chains.read()["accept"].copy())
+    finally:
+        torch.backends.cudnn.deterministic = det
+    assert res["default"][0] and not res["eager"][0] and not res["opt_eager"][0]
+    _close_up_to_clip_flips(res["default"][1].numpy(), res["eager"][1].numpy(), atol=1e-4, max_frac=0.02)

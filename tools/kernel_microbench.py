@@ -82,9 +82,8 @@ def main():
     dev = torch.device("cuda")
     flush = None if a.warm else torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     want = lambda k: (not a.only) or a.only in k
-    _lib.lib().nhmc_gn_set_resident(a.resident)
-    _lib.lib().nhmc_gn_set_solo(a.solo)
-    _lib.lib().nhmc_set_pdl(a.pdl)
+    kernels.set_flags((0 if a.resident else _lib.GN_F_NO_RESIDENT) | (_lib.GN_F_NO_SOLO if a.solo == 0 else (_lib.GN_F_NO_SOLO_CLUSTER if a.solo == 1 else 0))
+                      | (0 if a.pdl else _lib.F_NO_PDL))
 
     if want("gn"):
         shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]

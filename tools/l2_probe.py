@@ -38,8 +38,7 @@ for mb in (8, 16, 32, 48, 64, 96, 128, 192, 256):
     print(json.dumps({"probe": "sum_twice", "MB": mb, "cold_us": round(c, 1), "warm_us": round(w, 1),
                       "cold_GBps": round(mb * 1.048576 / c * 1e3, 0), "warm_GBps": round(mb * 1.048576 / w * 1e3, 0)}), flush=True)
 
-_lib.lib().nhmc_gn_set_resident(0)
-_lib.lib().nhmc_gn_set_solo(0)
+kernels.set_flags(_lib.GN_F_NO_RESIDENT | _lib.GN_F_NO_SOLO)
 for B in (1, 2, 3, 4, 6, 8):
     C, H = 128, 256
     x = torch.randn(B, C, H, H, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
