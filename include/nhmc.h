@@ -73,13 +73,14 @@ typedef struct nhmc_chain {
   int32_t collect;     /* 1 if the last iteration stored a sample                       */
   int32_t slot;        /* ring-buffer slot written by the last iteration, or -1         */
   int32_t active;      /* 0 once the chain's schedule is complete                       */
-  int32_t reserved;
+  int32_t reserved;    /* leapfrog step index l inside the running trajectory (diagonal-mass variant)   */
 } nhmc_chain;
 
 size_t nhmc_sizeof_chain(void);
 
 #define NHMC_SCHED_PIXEL 0  /* main_sampling.py:681-749        */
 #define NHMC_SCHED_LATENT 1 /* main_sampling_latent.py:646-733 */
+#define NHMC_SCHED_COND 2   /* hmc_test_conditioning, main_sampling.py:776-894 (adaptive diagonal mass) */
 
 /* Top of an iteration: sigma_y / tau / epsilon for this epoch.
  * Replaces main_sampling.py:683-689 (pixel).  The latent schedule sets sigma_y on accept
@@ -104,6 +105,16 @@ size_t nhmc_leapfrog_workspace_bytes(int n_chains);
 int nhmc_leapfrog(int mode, const float* x_in, float* x_out, float* p, const float* g_a,
                   const float* g_b, const double* loss_in, nhmc_chain* chains, double mass,
                   int n_chains, int64_t n_per_chain, void* workspace, nhmc_stream_t stream);
+
+/* Diagonal-mass variant of the fused leapfrog step (hmc_test_conditioning, main_sampling.py:776-894): inv_mass [B, N]
+ * fp32 is the per-element inverse mass; the kinetic sums become sum(inv_mass * p^2) (use mass = 1 in nhmc_accept), the
+ * drift x + (eps * p) * inv_mass (:835).  wf_mean / wf_m2 ([B, N] fp32, zero-filled by the caller at the top of every
+ * iteration; both NULL: no running variance): in the MIDDLE / LAST modes the Welford mean and M2 of the trajectory's
+ * positions (:845-849) are updated in the same pass for chains with epoch - 5 > 13, with step count
+ * chains[b].reserved + 1 (reset by nhmc_begin_iteration, advanced here after every MIDDLE / LAST step). */
+int nhmc_leapfrog_diag(int mode, const float* x_in, float* x_out, float* p, const float* g_a, const float* g_b,
+                       const double* loss_in, nhmc_chain* chains, const float* inv_mass, float* wf_mean, float* wf_m2,
+                       int n_chains, int64_t n_per_chain, void* workspace, nhmc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 DDIM epilogue forward (algos/unconditional.py:17-28; formula of functions/denoising.py:62)

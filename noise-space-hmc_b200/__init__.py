@@ -6,8 +6,8 @@ There is no CPU fallback: calls raise if the library is missing or the tensors a
 from . import _lib, schedule, chain                       # noqa: F401
 from ._lib import NhmcError, build, lib                   # noqa: F401
 from . import kernels, operators, sampler                 # noqa: F401
-from .sampler import hmc, hmc_latent, HMCSampler, GradEvaluator   # noqa: F401
+from .sampler import hmc, hmc_latent, hmc_test_conditioning, HMCSampler, GradEvaluator   # noqa: F401
 from .schedule import get_beta_schedule, compute_alpha    # noqa: F401
 
-__all__ = ["hmc", "hmc_latent", "HMCSampler", "GradEvaluator", "operators", "kernels", "schedule", "build", "lib",
+__all__ = ["hmc", "hmc_latent", "hmc_test_conditioning", "HMCSampler", "GradEvaluator", "operators", "kernels", "schedule", "build", "lib",
            "NhmcError", "get_beta_schedule", "compute_alpha"]

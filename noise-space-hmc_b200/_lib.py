@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 # constants of include/nhmc.h
 F32, BF16, F16 = 0, 1, 2
 LF_FIRST, LF_MIDDLE, LF_LAST = 0, 1, 2
-SCHED_PIXEL, SCHED_LATENT = 0, 1
+SCHED_PIXEL, SCHED_LATENT, SCHED_COND = 0, 1, 2
 OP_INPAINT, OP_SR, OP_HDR, OP_DEBLUR2D, OP_PHASE, OP_DENOISE, OP_COLOR, OP_SEPMAT, OP_CS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 GN_PLAIN, GN_SILU, GN_FILM_SILU = 0, 1, 2
 LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
@@ -55,6 +55,8 @@ _SIGS = {
     "nhmc_leapfrog_workspace_bytes": (C.c_size_t, [C.c_int]),
     "nhmc_leapfrog": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nhmc_leapfrog_diag": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "nhmc_ddim_mask_bytes": (C.c_size_t, [C.c_int64]),
     "nhmc_ddim_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64, C.c_void_p]),

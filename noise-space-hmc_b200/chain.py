@@ -44,6 +44,12 @@ class ChainState:
         """Chains [start, start + n) of this array as an object the kernel wrappers accept (ptr(), n)."""
         return _ChainView(self, start, n)
 
+    def field_i32(self, name):
+        """Device view [n] of a 4-byte integer field (no copy, no sync): e.g. "accept" or "epoch" for device-side masks."""
+        off = CHAIN_DTYPE.fields[name][1]
+        assert CHAIN_DTYPE.fields[name][0] == np.dtype("<i4") and off % 4 == 0
+        return self.dev.view(torch.int32)[:, off // 4]
+
     def read(self):
         """Host copy (synchronises)."""
         return self.dev.cpu().numpy().reshape(-1).view(CHAIN_DTYPE).copy()

@@ -43,6 +43,23 @@ __global__ void accept_kernel(nhmc_chain* chains, const float* __restrict__ u, d
       c.rejected += 1;
       if (c.rejected >= 2) { c.tau *= 0.95; c.epsilon *= 0.95; }
     }
+  } else if (sched == NHMC_SCHED_COND) {
+    // hmc_test_conditioning (main_sampling.py:856-892): burn 5, epochs 40, sampling 10, 85 accepted iterations in all
+    const int burn = 5, epochs = 40, sampling = 10;
+    if (acc) {
+      c.accepted += 1;
+      c.rejected = 0;
+      if (c.epoch >= epochs + sampling) {
+        c.collect = 1;
+        c.slot = c.n_collected % n_slots;
+        c.n_collected += 1;
+      }
+      c.epoch += 1;
+      if (c.epoch >= burn + epochs + 4 * sampling) c.active = 0;
+    } else {
+      c.rejected += 1;
+      if (c.rejected >= 2) { c.tau *= 0.95; c.epsilon *= 0.95; }
+    }
   } else {
     const int epochs = 50, sampling = 10;
     if (acc) {
@@ -85,7 +102,7 @@ commit_kernel(const nhmc_chain* __restrict__ chains, float* __restrict__ x, cons
   for (int64_t v = (int64_t)blockIdx.x * kThreads + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * kThreads) {
     st_stream(xb + v, ld_ro(xp + v));
     const float4 h = ld_ro(xh + v);
-    if (sched == NHMC_SCHED_PIXEL) {
+    if (sched != NHMC_SCHED_LATENT) {
       if (sm) st_stream(sm + v, h);
     } else {
       if (sm) st_stream(sm + v, ld_stream(xk + v));  // one accept behind (main_sampling_latent.py:705-713)
@@ -136,7 +153,7 @@ extern "C" int nhmc_commit_grad(const nhmc_chain* chains, float* g_state, const 
 extern "C" int nhmc_accept(nhmc_chain* chains, const float* u, double mass, int sched, int n_slots, int n_chains,
                            nhmc_stream_t stream) {
   NHMC_CHECK_ARG(chains && u && n_chains > 0 && n_slots > 0 && mass > 0.0, "bad arguments");
-  NHMC_CHECK_ARG(sched == NHMC_SCHED_PIXEL || sched == NHMC_SCHED_LATENT, "unknown schedule");
+  NHMC_CHECK_ARG(sched == NHMC_SCHED_PIXEL || sched == NHMC_SCHED_LATENT || sched == NHMC_SCHED_COND, "unknown schedule");
   accept_kernel<<<(n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chains, u, mass, sched, n_slots, n_chains);
   return NHMC_LAUNCH_CHECK();
 }
@@ -146,7 +163,7 @@ extern "C" int nhmc_commit(const nhmc_chain* chains, float* x, const float* x_pr
                            nhmc_stream_t stream) {
   NHMC_CHECK_ARG(chains && x && x_prop && x_hat && n_chains > 0 && n_slots > 0, "bad arguments");
   NHMC_CHECK_ARG(n_per_chain > 0 && n_per_chain % 4 == 0, "n_per_chain must be a positive multiple of 4");
-  NHMC_CHECK_ARG(sched == NHMC_SCHED_PIXEL || x_keep, "x_keep required for the latent schedule");
+  NHMC_CHECK_ARG(sched != NHMC_SCHED_LATENT || x_keep, "x_keep required for the latent schedule");
   NHMC_CHECK_ARG(aligned16(x) && aligned16(x_prop) && aligned16(x_hat) && (!x_keep || aligned16(x_keep)) &&
                      (!samples || aligned16(samples)), "pointers must be 16-byte aligned");
   const int64_t n_vec = n_per_chain / 4;

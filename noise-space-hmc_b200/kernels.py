@@ -232,6 +232,19 @@ def leapfrog(mode, x_in, x_out, p, g_a, g_b, loss, chains, mass, ws):
                                   float(mass), B, N, _p(ws), _stream()), "nhmc_leapfrog")
 
 
+def leapfrog_diag(mode, x_in, x_out, p, g_a, g_b, loss, chains, inv_mass, wf_mean, wf_m2, ws):
+    """Diagonal-mass leapfrog step (hmc_test_conditioning): per-element inverse mass + the trajectory's Welford mean / M2."""
+    B = x_in.shape[0]
+    N = x_in[0].numel()
+    for t, nm in ((x_in, "x_in"), (p, "p"), (g_a, "g_a"), (inv_mass, "inv_mass")):
+        _req(t, torch.float32, nm)
+    if g_b is not None: _req(g_b, torch.float32, "g_b")
+    nb = B * N * 4 * ((4 if mode == _lib.LF_LAST else 6) + (1 if g_b is not None else 0) + (4 if (wf_mean is not None and mode != _lib.LF_FIRST) else 0))
+    with _timed("leapfrog_diag", 1 if mode == _lib.LF_FIRST else 2, nb):
+        check(lib().nhmc_leapfrog_diag(mode, _p(x_in), _p(x_out), _p(p), _p(g_a), _p(g_b), _p(loss), chains.ptr(), _p(inv_mass),
+                                       _p(wf_mean), _p(wf_m2), B, N, _p(ws), _stream()), "nhmc_leapfrog_diag")
+
+
 def ddim_mask_words(n_per_chain):
     return lib().nhmc_ddim_mask_bytes(n_per_chain) // 4
 

@@ -138,7 +138,7 @@ class HMCSampler:
     """State + one-iteration stepper shared by hmc() and hmc_latent()."""
 
     def __init__(self, x, evaluator, tau, epsilon, sigma_0, mass=1.0, sched=_lib.SCHED_PIXEL, sigma_y=None,
-                 n_slots=20, reuse_gradient=False, lanes=1):
+                 n_slots=20, reuse_gradient=False, lanes=1, diag_mass=False):
         """lanes > 1: the chains are cut into that many contiguous groups, each evaluated (score network, epilogues,
         operator, VJP, leapfrog kernel) on its own stream; in a captured step the groups are parallel branches of the
         graph, so one group's bandwidth-bound / latency-bound kernels overlap the other's convolutions.  Per-chain
@@ -167,6 +167,15 @@ class HMCSampler:
         self.loss_state = torch.zeros(self.B, dtype=torch.float64, device=dev) if self.reuse_gradient else None
         self._state_valid = False    # (loss_state, g_state) hold the values at self.x
         self._last = {}              # mode -> [(lo, hi, g_a, g_b)] of that step variant's evaluation (static buffers under graphs)
+        # diagonal mass (hmc_test_conditioning, main_sampling.py:776-894): per-element mass re-estimated from the
+        # trajectory's running variance on accepted iterations; M = 1 until the first update
+        self.diag = bool(diag_mass)
+        if self.diag:
+            assert not reuse_gradient and int(lanes) <= 1, "the diagonal-mass variant runs single-lane without gradient reuse"
+            self.inv_mass = torch.ones_like(self.x)
+            self.std_mass = torch.ones_like(self.x)
+            self.wf_mean = torch.zeros_like(self.x)
+            self.wf_m2 = torch.zeros_like(self.x)
         self.n_lanes = max(1, min(int(lanes), self.B, 8))
         self.lanes = None
         # GroupNorm scratch of the score network's fused epilogues: owned by THIS sampler (one per lane), so samplers on
@@ -186,7 +195,11 @@ class HMCSampler:
             with kernels.gn_scope(self.gn_ws, 1):
                 loss, g_a, g_b, _ = self.ev(src)
             self._last[mode] = [(0, self.B, g_a, g_b)]
-            kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
+            if self.diag:
+                kernels.leapfrog_diag(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.inv_mass, self.wf_mean,
+                                      self.wf_m2, self.ws)
+            else:
+                kernels.leapfrog(mode, src, self.x_prop, self.p, g_a, g_b, loss, self.chains, self.mass, self.ws)
             return
         cur = torch.cuda.current_stream()
         last = []
@@ -223,7 +236,7 @@ class HMCSampler:
         kernel: several thousand launches each) as CUDA graphs sharing one memory pool.  Per-chain scalars live
         in device memory (nhmc_chain), so the graphs stay valid for every iteration of every chain.  The sampler
         state touched while warming up / capturing is restored afterwards."""
-        keep = [t.clone() for t in (self.x, self.x_prop, self.p, self.chains.dev)]
+        keep = [t.clone() for t in self._state_tensors()]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -241,10 +254,32 @@ class HMCSampler:
             graphs[mode] = (g, kernels.LAUNCHES - n0)
             pool = g.pool()
         torch.cuda.synchronize()
-        for dst, src in zip((self.x, self.x_prop, self.p, self.chains.dev), keep):
+        for dst, src in zip(self._state_tensors(), keep):
             dst.copy_(src)
         self._graphs = graphs
         return self
+
+    def _state_tensors(self):
+        """Everything a step variant mutates (restored after warm-up / capture)."""
+        return (self.x, self.x_prop, self.p, self.chains.dev) + ((self.wf_mean, self.wf_m2) if self.diag else ())
+
+    def _mass_update(self):
+        """Accepted iterations from epoch > epochs // 3 on re-estimate the diagonal mass from the trajectory's variance
+        (main_sampling.py:857-868): variance = M2 / (L - 1), rank transform to scores in [-1, 1], M = exp(scores).  Per
+        chain, on device, masked by the accept decision; the sort (ties: the all-zero variance of the first updates) is
+        torch.sort, the reference's own call -- its tie order is implementation-defined and taken as is."""
+        B, N = self.B, self.x[0].numel()
+        epoch_after = self.chains.field_i32("epoch")
+        upd = (self.chains.field_i32("accept") != 0) & ((epoch_after - 1) > 40 // 3)           # epoch before the increment
+        variance = (self.wf_m2 / (self.L - 1)).reshape(B, N)
+        _, sorted_idx = torch.sort(variance, dim=1)
+        ranks = torch.empty(B, N, dtype=torch.float32, device=self.x.device)
+        ranks.scatter_(1, sorted_idx, torch.arange(N, dtype=torch.float32, device=self.x.device).expand(B, N).contiguous())
+        scores = 2.0 * (ranks / (N - 1)) - 1.0
+        M = torch.exp(1 * scores).view_as(self.x)
+        m = upd.view(B, *([1] * (self.x.dim() - 1)))
+        self.std_mass.copy_(torch.where(m, torch.sqrt(M), self.std_mass))
+        self.inv_mass.copy_(torch.where(m, 1.0 / M, self.inv_mass))
 
     def capture_profiled_step(self, mode=_lib.LF_MIDDLE, events=True):
         """One step variant captured as a CUDA graph WITH a pair of timing events around every kernel of ours
@@ -252,7 +287,7 @@ class HMCSampler:
         per-kernel CUDA-event times of that replay -- measured in situ (warm L2, back-to-back launches) on the
         launching stream.  Sampler state is restored after the capture.  events=False: the same capture without the
         event nodes (e.g. with other library settings than the sampler's own graphs, for A/B or profiler passes)."""
-        keep = [t.clone() for t in (self.x, self.x_prop, self.p, self.chains.dev)]
+        keep = [t.clone() for t in self._state_tensors()]
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         pool = next(iter(self._graphs.values()))[0].pool() if self._graphs else None
@@ -262,7 +297,7 @@ class HMCSampler:
             self._step_eager(mode)
         records = kernels.profile_take() if events else {}
         torch.cuda.synchronize()
-        for dst, src in zip((self.x, self.x_prop, self.p, self.chains.dev), keep):
+        for dst, src in zip(self._state_tensors(), keep):
             dst.copy_(src)
         return g, records
 
@@ -271,6 +306,9 @@ class HMCSampler:
         ev, ch, m = self.ev, self.chains, self.mass
         kernels.begin_iteration(ch, self.sched)
         self.p.copy_(p)
+        if self.diag:
+            self.p.mul_(self.std_mass)                                           # p ~ N(0, M) (main_sampling.py:819)
+            self.wf_mean.zero_(); self.wf_m2.zero_()                             # :806-807
         if self.reuse_gradient and self._state_valid:
             self._first_from_state()                                             # no evaluation #0
         else:
@@ -285,8 +323,10 @@ class HMCSampler:
         xc = ev.xc
         self.leapfrog_steps_done += self.L
         self.u_dev.copy_(torch.as_tensor(u, dtype=torch.float32).reshape(self.B), non_blocking=True)
-        kernels.accept(ch, self.u_dev, m, self.sched, self.n_slots)              # main_sampling.py:717-749
+        kernels.accept(ch, self.u_dev, 1.0 if self.diag else m, self.sched, self.n_slots)   # main_sampling.py:717-749
         kernels.commit(ch, self.x, self.x_prop, xc, self.x_keep, self.samples, self.sched, self.n_slots)
+        if self.diag:
+            self._mass_update()
         if self.reuse_gradient:
             for lo, hi, g_a, g_b in self._last[_lib.LF_LAST]:                    # evaluation at the proposal
                 kernels.commit_grad(ch.view(lo, hi - lo), self.g_state[lo:hi], g_a, g_b, self.loss_state[lo:hi], ev.loss[lo:hi])
@@ -501,6 +541,42 @@ def hmc(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=Non
         cuda_graphs = bool(opt.cuda_graphs)
     _capture(smp, cuda_graphs, model)
     dm, du = _default_draws(m)
+    _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
+    if return_sampler:
+        return smp
+    out = smp.collected()
+    if B == 1:
+        return out[0]
+    s_min = min(o.shape[0] for o in out)
+    return torch.stack([o[:s_min] for o in out])
+
+
+def hmc_test_conditioning(x, n, b, seq, seq_next, algo, opt, y_0, H_funcs, x_orig, *, momentum=None, uniform=None,
+                          max_iters=None, on_iteration=None, return_sampler=False, cuda_graphs=None):
+    """Drop-in for main_sampling.hmc_test_conditioning (main_sampling.py:776-894): HMC with an adaptive DIAGONAL mass.
+    Same signature and schedule (burn 5, epochs 40, 85 accepted iterations, sigma_y = sigma_0 + 0.9 (1 - (e - 5)/40)^3);
+    the momentum is drawn as randn * sqrt(M), the kinetic energy is sum(p^2 / M), the drift x + eps p / M, and every
+    accepted iteration from epoch 14 on sets M = exp(rank-transformed variance of the trajectory's positions), the
+    variance coming from the Welford pass fused into the leapfrog kernel (nhmc_leapfrog_diag).  Returns the 35 samples
+    collected from epoch 50 on ([35,3,H,W] for B == 1, [B,35,3,H,W] for B > 1 independent chains)."""
+    if not x.is_cuda:
+        raise _lib.NhmcError("hmc_test_conditioning() runs on a CUDA device (sm_100a); there is no CPU fallback")
+    B, C, D = x.shape[0], x.shape[1], x.shape[2]
+    assert n == B, "n must equal the batch size"
+    model = _model_of(algo)
+    op = operators.from_reference(H_funcs, C, D, x.device)
+    y = y_0.detach().float().contiguous().reshape(op.meas_shape(B))
+    noise = getattr(opt, "noise", "ddpm")
+    if plugin_is_unconditional(algo, C, x.device, noise):
+        steps = schedule.ddim_steps(schedule.alpha_table(b), seq, seq_next)
+        ev = GradEvaluator(model, steps, op, y, x.detach().float().contiguous(), net_grad=True)
+    else:
+        ev = PluginGradEvaluator(algo, b, seq, seq_next, op, y, y_0, x.detach().float().contiguous(), noise)
+    smp = HMCSampler(x, ev, opt.tau, opt.epsilon, opt.sigma_0, mass=1.0, sched=_lib.SCHED_COND, n_slots=35, diag_mass=True)
+    if cuda_graphs is None and getattr(opt, "cuda_graphs", None) is not None:
+        cuda_graphs = bool(opt.cuda_graphs)
+    _capture(smp, cuda_graphs, model)
+    dm, du = _default_draws(1.0)
     _run(smp, momentum or dm, uniform or du, max_iters, on_iteration)
     if return_sampler:
         return smp

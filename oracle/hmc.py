@@ -197,3 +197,78 @@ def run_latent_chain(z, eps_net, alpha_tab, seq, seq_next, op, y, decode, tau, e
         it += 1
     samples = samples[-10:]
     return (torch.stack(samples) if samples else torch.empty(0)), z
+
+
+# ----------------------------------------------------------------------------------------
+# adaptive diagonal mass: hmc_test_conditioning (main_sampling.py:776-894)
+# ----------------------------------------------------------------------------------------
+def rank_mass(m2, L):
+    """Diagonal mass of main_sampling.py:858-868 from the trajectory's Welford M2 (one chain, flat [N] fp32):
+    variance = M2 / (L - 1); rank transform to scores in [-1, 1]; M = exp(scores).  The sort of tied values (the
+    all-zero variance of the first updates) follows torch.sort's own order -- implementation-defined, as in the reference."""
+    variance = (m2 / (L - 1)).reshape(-1)
+    _, sorted_idx = torch.sort(variance)
+    ranks = torch.zeros_like(sorted_idx, dtype=torch.float)
+    ranks[sorted_idx] = torch.arange(len(variance), dtype=torch.float)
+    scores = 2.0 * (ranks / (variance.numel() - 1)) - 1.0
+    return torch.exp(1 * scores)
+
+
+def hmc_cond_iteration(x, p, u, sigma_y, epsilon, L, inv_m, welford, eval_fn):
+    """One iteration of hmc_test_conditioning from state x with momentum p (already scaled by sqrt(M)) and uniform u.
+    inv_m: [1,C,H,W] fp32 inverse diagonal mass.  welford: accumulate the running mean / M2 of the positions
+    (main_sampling.py:845-849).  fp32 op by op in the reference's order."""
+    dt = x.dtype
+    _, loss0, g = eval_fn(x)
+    H0 = (_f(0.5, dt) * torch.sum(x ** 2, dim=(1, 2, 3)) + _f(1 / (2 * sigma_y ** 2), dt) * loss0.to(dt)
+          + _f(0.5, dt) * torch.sum(inv_m * p ** 2))
+    xp = x.clone()
+    p = kick(p, xp, g, sigma_y, epsilon / 2)
+    mean, m2 = torch.zeros_like(x), torch.zeros_like(x)
+    x_hat = None
+    for l in range(L):
+        xp = xp + _f(epsilon, dt) * p * inv_m                       # main_sampling.py:835
+        x_hat, loss, g = eval_fn(xp)
+        p = kick(p, xp, g, sigma_y, epsilon)
+        if welford:
+            delta = xp - mean
+            mean = mean + delta / (l + 1)
+            delta2 = xp - mean
+            m2 = m2 + delta * delta2
+    p = kick(p, xp, g, sigma_y, -(epsilon / 2))
+    H1 = (_f(0.5, dt) * torch.sum(xp ** 2, dim=(1, 2, 3)) + _f(1 / (2 * sigma_y ** 2), dt) * loss.to(dt)
+          + _f(0.5, dt) * torch.sum(inv_m * p ** 2))
+    prob = accept_prob(H0, H1)
+    accept = None if u is None else (torch.as_tensor(u, dtype=prob.dtype) < prob)
+    return dict(x_prop=xp, p_prop=p, x_hat=x_hat, H0=H0, H1=H1, prob=prob, accept=accept, loss0=loss0, loss1=loss, m2=m2, mean=mean)
+
+
+def run_cond_chain(x, eps_net, alpha_tab, seq, seq_next, op, y, tau, epsilon, sigma_0, draw_p=None, draw_u=None,
+                   max_iters=None, trace=None):
+    """hmc_test_conditioning() for one chain (x: [1,C,H,W]); returns ([S,C,H,W] collected samples, final x, final M)."""
+    from .schedule import CondSchedule
+    draw_p = draw_p or (lambda x_: torch.randn_like(x_))
+    draw_u = draw_u or (lambda: torch.rand(1))
+    sch = CondSchedule(tau, epsilon, sigma_0)
+    eval_fn = lambda x_: grad_eval(x_, eps_net, alpha_tab, seq, seq_next, op, y)
+    M = torch.ones_like(x)
+    samples, it = [], 0
+    while not sch.done():
+        if max_iters is not None and it >= max_iters:
+            break
+        sigma_y, eps_now = sch.begin_iteration()
+        p = draw_p(x) * torch.sqrt(M)
+        out = hmc_cond_iteration(x, p, draw_u(), sigma_y, eps_now, sch.L, 1.0 / M, sch.welford_on(), eval_fn)
+        acc = bool(out["accept"].item())
+        if trace is not None:
+            trace.append(dict(it=it, epoch=sch.epoch, sigma_y=sigma_y, epsilon=eps_now, H0=float(out["H0"]), H1=float(out["H1"]),
+                              prob=float(out["prob"]), accept=acc))
+        if acc and sch.mass_update_on():
+            M = rank_mass(out["m2"], sch.L).view_as(x)
+        collect = sch.end_iteration(acc)
+        if acc:
+            x = out["x_prop"].detach().clone()
+            if collect:
+                samples.append(out["x_hat"][0].detach().clone())
+        it += 1
+    return (torch.stack(samples) if samples else torch.empty(0)), x, M

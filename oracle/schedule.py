@@ -182,3 +182,64 @@ class LatentSchedule:
                 self.rejected = 0
         self.epoch += 1
         return collect
+
+
+class CondSchedule:
+    """Host-side state machine of hmc_test_conditioning (main_sampling.py:776-894) for ONE chain: the adaptive-mass
+    variant.  burn = 5, epochs = 40, sampling = 10; the `while` runs until epoch reaches burn + epochs + 4 * sampling
+    = 85 accepted iterations; sigma_y = sigma_0 + 0.9 for epoch < burn, sigma_0 + 0.9 (1 - (epoch - burn)/epochs)^3 for
+    epoch < epochs, sigma_0 from epoch == epochs on (tau, epsilon clamped to 0.1 / 0.01 there); accepted samples are
+    collected from epoch >= epochs + sampling; rejects decay tau / epsilon by 0.95 once rejected >= 2."""
+    BURN = 5
+    EPOCHS = 40
+    SAMPLING = 10
+    DECAY = 0.95
+
+    def __init__(self, tau, epsilon, sigma_0):
+        self.tau = float(tau)
+        self.epsilon = float(epsilon)
+        self.sigma_0 = float(sigma_0)
+        self.L = max(1, math.floor(self.tau / self.epsilon))
+        self.epoch = 0
+        self.accepted = 0
+        self.rejected = 0
+        self.sigma_y = None
+
+    def done(self):
+        return self.epoch >= self.BURN + self.EPOCHS + 4 * self.SAMPLING
+
+    def begin_iteration(self):
+        """main_sampling.py:809-817."""
+        if self.epoch < self.BURN:
+            self.sigma_y = self.sigma_0 + 0.9
+        elif self.epoch < self.EPOCHS:
+            self.sigma_y = self.sigma_0 + 0.9 * (1 - (self.epoch - self.BURN) / self.EPOCHS) ** 3
+        elif self.epoch == self.EPOCHS:
+            self.sigma_y = self.sigma_0
+            if self.tau > 0.1:
+                self.tau = 0.1
+                self.epsilon = 0.01
+        return self.sigma_y, self.epsilon
+
+    def welford_on(self):
+        """main_sampling.py:845: the trajectory's running variance is accumulated only from here on."""
+        return (self.epoch - self.BURN) > self.EPOCHS // 3
+
+    def mass_update_on(self):
+        """main_sampling.py:857: an ACCEPTED iteration re-estimates the diagonal mass from here on (note: a few epochs
+        earlier than welford_on, so those updates see an all-zero variance: ranks = the sort's tie order)."""
+        return self.epoch > self.EPOCHS // 3
+
+    def end_iteration(self, accept):
+        """main_sampling.py:856-892.  Returns True iff the accepted xt is a collected sample."""
+        if accept:
+            self.accepted += 1
+            self.rejected = 0
+            collect = self.epoch >= self.EPOCHS + self.SAMPLING
+            self.epoch += 1
+            return collect
+        self.rejected += 1
+        if self.rejected >= 2:
+            self.tau *= self.DECAY
+            self.epsilon *= self.DECAY
+        return False

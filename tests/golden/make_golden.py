@@ -324,6 +324,77 @@ def gold_hmc_trace():
          samples=out.detach(), seed=np.array(777))
 
 
+# ---------------------------------------------------------------------------- hmc_test_conditioning() trace
+def gold_hmc_cond_trace():
+    """The adaptive-mass variant (main_sampling.py:776-894) run for real with the tiny eps-net: per-iteration start state,
+    uniform draws, acceptance ratios, the variance handed to torch.sort at every mass update (and the iteration it
+    happened in), the images saved on accept and the returned samples."""
+    D = 32
+    net = TinyEpsNet()
+    torch.manual_seed(99)
+    missing_r = 3 * torch.randperm(D ** 2)[: int(D ** 2 * 0.92)].long()
+    missing = torch.cat([missing_r, missing_r + 1, missing_r + 2], dim=0)
+    H = Hfuncs.Inpainting(3, D, missing, "cpu")
+    sigma_0 = 0.1
+    algo = Unconditional(net, H, sigma_0)
+    betas = ms.get_beta_schedule("linear", beta_start=1e-4, beta_end=0.02, num_diffusion_timesteps=1000)
+    b = torch.from_numpy(betas).float()
+    g = torch.Generator().manual_seed(31)
+    x_orig = torch.rand(1, 3, D, D, generator=g) * 2 - 1
+    y_0 = H.H(x_orig) + sigma_0 * torch.randn(1, H.kept_indices.shape[0], generator=g)
+    x = torch.randn(1, 3, D, D, generator=g)
+    opt = types.SimpleNamespace(tau=1.0, epsilon=0.05, m=1.0, sigma_0=sigma_0, algo="hmc", noise="ddpm",
+                                image_folder="/tmp/nhmc_golden_unused")
+    seq, seq_next = [250, 500, 750], [-1, 250, 500]
+    rec = dict(x_start=[], prob=[], u=[], saved=[], var=[], var_it=[])
+    real_randn_like, real_rand, real_save, real_sort = torch.randn_like, torch.rand, ms.tvu.save_image, torch.sort
+
+    def randn_like(t, *a, **kw):
+        rec["x_start"].append(t.detach().clone())
+        return real_randn_like(t, *a, **kw)
+
+    def rand(*a, **kw):
+        v = real_rand(*a, **kw)
+        rec["u"].append(float(v))
+        return v
+
+    def rec_min(one, ratio):
+        rec["prob"].append(float(ratio))
+        return min(one, ratio)
+
+    def save_image(img, path, *a, **kw):
+        rec["saved"].append(img.detach().clone())
+
+    def sort(t, *a, **kw):
+        rec["var"].append(t.detach().clone())
+        rec["var_it"].append(len(rec["u"]) - 1)          # the iteration whose accept triggered this update
+        return real_sort(t, *a, **kw)
+
+    torch.randn_like, torch.rand, ms.tvu.save_image, torch.sort = randn_like, rand, save_image, sort
+    ms.min = rec_min
+    ms.print = lambda *a, **k: None
+    try:
+        torch.manual_seed(778)
+        out = ms.hmc_test_conditioning(x, 1, b, seq, seq_next, algo, opt, y_0, H, x_orig)
+    finally:
+        torch.randn_like, torch.rand, ms.tvu.save_image, torch.sort = real_randn_like, real_rand, real_save, real_sort
+        del ms.min, ms.print
+    n_it = len(rec["u"])
+    accept = np.array([rec["u"][i] < min(1.0, rec["prob"][i]) for i in range(n_it)])
+    print("hmc_test_conditioning trace: iterations", n_it, "accepted", int(accept.sum()), "mass updates", len(rec["var"]),
+          "samples", tuple(out.shape))
+    # keep the iterations up to a few mass updates past the point where the running variance switches on (epoch 19)
+    acc_cum = np.cumsum(accept)
+    K = int(min(n_it, np.searchsorted(acc_cum, 26) + 1))
+    print("kept iterations", K, "first mass update at iteration", rec["var_it"][0] if rec["var_it"] else None)
+    keep_var = [i for i, it in enumerate(rec["var_it"]) if it < K]
+    save("hmc_cond_trace.npz", missing=missing, x_orig=x_orig, y_0=y_0, x_init=x, sigma_0=np.array(sigma_0),
+         u=np.array(rec["u"]), prob=np.array(rec["prob"]), accept=accept,
+         x_start=torch.cat(rec["x_start"][:K]), saved=torch.stack(rec["saved"][:K]),
+         var=torch.stack([rec["var"][i] for i in keep_var]), var_it=np.array([rec["var_it"][i] for i in keep_var]),
+         n_samples=np.array(out.shape[0]), last_sample=out[-1].detach(), seed=np.array(778))
+
+
 # ---------------------------------------------------------------------------- full hmc_latent() trace
 def gold_hmc_latent_trace():
     """The REAL hmc_latent (main_sampling_latent.py:623-762) driven with a tiny stand-in LDM."""
@@ -457,6 +528,6 @@ def gold_latent_models():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "operators_ext", "ddim", "unet", "hmc_trace", "hmc_latent_trace", "latent_models"]
+    which = sys.argv[1:] or ["schedule", "inpaint_mask", "operators", "operators_ext", "ddim", "unet", "hmc_trace", "hmc_cond_trace", "hmc_latent_trace", "latent_models"]
     for w in which:
         globals()["gold_" + w]()

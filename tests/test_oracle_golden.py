@@ -274,3 +274,66 @@ def test_latent_schedule_and_teacher_forced_iterations(golden):
     assert outliers <= 2, outliers
     assert sch.done() and sch.accepted == int(g["accept"].sum())
     assert collected == g["samples"].shape[0]
+
+
+def test_hmc_cond_teacher_forced_iterations_and_schedule(golden):
+    """hmc_test_conditioning (main_sampling.py:776-894, the adaptive diagonal-mass variant): the oracle under the recorded
+    draws of the REAL function reproduces its acceptance ratios / decisions / saved images iteration by iteration, the
+    trajectory variance it hands to torch.sort at every mass update, and -- CondSchedule replay over the whole recorded
+    accept sequence -- its length (85 accepted epochs) and sample count (35)."""
+    g = golden("hmc_cond_trace.npz")
+    op, tab, eps_net = _trace_setup(g)
+    y = T(g["y_0"]); sigma_0 = float(g["sigma_0"])
+    seq, seq_next = [250, 500, 750], [-1, 250, 500]
+    sch = osch.CondSchedule(1.0, 0.05, sigma_0)
+    torch.manual_seed(int(g["seed"]))
+    eval_fn = lambda x_: ohmc.grad_eval(x_, eps_net, tab, seq, seq_next, op, y)
+    K = g["x_start"].shape[0]
+    M = torch.ones(1, 3, 32, 32)
+    var_at = {int(it): i for i, it in enumerate(g["var_it"])}
+    n_saved = n_img_ok = outliers = n_var = 0
+    for it in range(K):
+        x = T(g["x_start"][it:it + 1])
+        p = torch.randn_like(x) * torch.sqrt(M)
+        sig, eps_now = sch.begin_iteration()
+        out = ohmc.hmc_cond_iteration(x, p, None, sig, eps_now, sch.L, 1.0 / M, sch.welford_on(), eval_fn)
+        u = torch.rand(1)
+        assert abs(float(u) - g["u"][it]) < 1e-7
+        acc = bool(g["accept"][it])
+        prob_ref = min(1.0, float(g["prob"][it]))
+        dH = float(out["H1"] - out["H0"])
+        dH_ref = -float(np.log(max(g["prob"][it], 1e-300)))
+        ok = (dH > 80.0) if g["prob"][it] == 0.0 else abs(dH - dH_ref) <= 0.03 * max(1.0, abs(dH_ref))
+        if not ok:
+            outliers += 1                                  # a clip-boundary flip inside the trajectory (see the hmc() test)
+        else:
+            if abs(float(u) - prob_ref) > 0.03 * max(prob_ref, 1e-3) + 1e-6:
+                assert (float(u) < float(out["prob"])) == acc, it
+            if acc:
+                img = ((out["x_hat"][0] + 1) / 2).clamp(0, 1)
+                np.testing.assert_allclose(img.numpy(), g["saved"][n_saved], atol=1e-3)
+                n_img_ok += 1
+        if acc and sch.mass_update_on():
+            assert it in var_at, it                        # the real function updated its mass in exactly these iterations
+            var_ref = T(g["var"][var_at[it]])
+            if ok:
+                np.testing.assert_allclose((out["m2"] / (sch.L - 1)).reshape(-1).numpy(), var_ref.numpy(), atol=2e-4 * float(var_ref.max()) + 1e-9)
+                n_var += 1
+            M = ohmc.rank_mass(var_ref * (sch.L - 1), sch.L).view(1, 3, 32, 32)     # teacher forcing: the reference's variance
+        else:
+            assert it not in var_at, it
+        n_saved += acc
+        sch.end_iteration(acc)
+    assert outliers <= 4, outliers
+    assert n_img_ok >= 20 and n_var >= 5, (n_img_ok, n_var)
+    # the first updates (epochs 14..18) see an all-zero variance; from epoch 19 on the Welford pass is live
+    assert float(T(g["var"][0]).abs().max()) == 0.0 and float(T(g["var"][-1]).max()) > 0.0
+    # schedule replay over the whole run
+    sch = osch.CondSchedule(1.0, 0.05, sigma_0)
+    n = collected = 0
+    for a in g["accept"]:
+        assert not sch.done()
+        sch.begin_iteration()
+        collected += bool(sch.end_iteration(bool(a)))
+        n += 1
+    assert sch.done() and n == len(g["accept"]) and sch.accepted == 85 and collected == int(g["n_samples"]) == 35

@@ -398,6 +398,8 @@ def test_programmatic_dependent_launch_does_not_change_results():
         return s, y, p, dx, yb
 
     outs = {}
+    scope = kernels.gn_scope(kernels.GnWorkspace(x.device, 8))    # one caller-owned GroupNorm workspace for eager calls and captures alike
+    scope.__enter__()
     for pdl in (0, 1):
         prev = kernels.set_flags(0 if pdl else _lib.F_NO_PDL)
         try:
@@ -411,6 +413,7 @@ def test_programmatic_dependent_launch_does_not_change_results():
         finally:
             kernels.set_flags(prev)
     kernels.gn_check()
+    scope.__exit__(None, None, None)
     ref = outs[(0, "eager")]
     for key, val in outs.items():
         for a, b in zip(ref, val):

@@ -85,6 +85,8 @@ def main():
     kernels.set_flags((0 if a.resident else _lib.GN_F_NO_RESIDENT) | (_lib.GN_F_NO_SOLO if a.solo == 0 else (_lib.GN_F_NO_SOLO_CLUSTER if a.solo == 1 else 0))
                       | (0 if a.pdl else _lib.F_NO_PDL))
 
+    gn_scope = kernels.gn_scope(kernels.GnWorkspace(dev, 64))      # caller-owned GroupNorm scratch, shared by eager calls and graph captures
+    gn_scope.__enter__()
     if want("gn"):
         shapes = [(8, 128, 256), (8, 256, 256), (8, 256, 128), (8, 384, 128), (8, 512, 64), (8, 768, 64), (8, 1024, 32), (8, 1024, 16), (8, 512, 8), (1, 128, 256)]
         if a.small:
