@@ -207,6 +207,17 @@ int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, flo
                       float* xc_out, double* loss, int n_chains, void* workspace,
                       nhmc_stream_t stream);
 
+/* Deblurring operators (kind NHMC_OP_DEBLUR2D on the tensor-core path), for callers that evaluate many times against ONE
+ * measurement (a sampler run): with the orthogonal left factors U1, U2, |Y - U1 Z U2^T|^2 = |U1^T Y U2 - Z|^2, so the
+ * residual never has to return to the image domain.  prepare_measurement writes Y^ = U1^T Y U2 (two products, same
+ * shape as y) once; loss_grad_prepared then needs four products per evaluation instead of the eight of
+ * nhmc_op_loss_grad (which does the same internally with six).  Results equal nhmc_op_loss_grad's up to the fp32
+ * orthogonality defect of the SVD factors.  NHMC_ERR_UNSUPPORTED for operators without a prepared form. */
+int nhmc_op_prepare_measurement(const nhmc_op* op, const float* y, float* y_prepared, int n_chains, void* workspace,
+                                nhmc_stream_t stream);
+int nhmc_op_loss_grad_prepared(const nhmc_op* op, const float* x_hat, const float* y_prepared, float* g, float* xc_out,
+                               double* loss, int n_chains, void* workspace, nhmc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K7 Metropolis decision + schedule update, on device (main_sampling.py:697,717-731,743-749;
  * latent main_sampling_latent.py:676-733).  u: device float[B] uniform draws.

@@ -71,6 +71,9 @@ _SIGS = {
     "nhmc_op_pinv": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "nhmc_op_loss_grad": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p, C.c_void_p]),
+    "nhmc_op_prepare_measurement": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "nhmc_op_loss_grad_prepared": (C.c_int, [C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_int, C.c_void_p, C.c_void_p]),
     "nhmc_accept": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nhmc_commit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                               C.c_int, C.c_int, C.c_int64, C.c_void_p]),

@@ -265,21 +265,63 @@ __global__ void clamp_copy_kernel(const float* __restrict__ x, float* __restrict
     y[e] = nc ? x[e] : fminf(fmaxf(x[e], -1.0f), 1.0f);
 }
 
+// Spectral-domain form of the loss.  U1 and U2 are the (square, orthogonal) left singular vectors of the two blur
+// matrices, so with Y^ = U1^T Y U2 (constant for a fixed measurement) and Z = gain .* (V1^T Xc V2):
+//   loss = |Y - U1 Z U2^T|^2 = |Y^ - Z|^2 ,      g = -2 H^T (Y - H Xc) = -2 V1 (gain .* (Y^ - Z)) V2^T
+// -- four products per evaluation instead of eight (the residual never returns to the image domain).  Equal to the
+// image-domain evaluation up to the fp32 orthogonality defect of torch.svd's factors (~1e-6 relative).
+int deblur_spectral_measurement(const nhmc_op* op, const float* y, float* y_spec, int n_chains, void* ws, cudaStream_t st) {
+  const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  NHMC_CHECK_ARG(use_tc(op), "spectral measurement needs the tensor-core path (img_dim % 4 == 0)");
+  const TcWs w = tc_ws(op, reinterpret_cast<float*>(ws), mats, D);
+  if (int e = tc_tables(op, w, false, st)) return e;
+  if (int e = tc_split_launch(y, w.xs, w.xs + w.P, w.P, 0, st)) return e;
+  TcGemm g1 = tc_base(dat_op(w.xs, D, D, mats), tab_op(w.tab[4], D, D), mats, C, w.t0, true, true);         // S^T = (Y U2)^T
+  if (int e = tc_gemm_launch(g1, st)) return e;
+  TcGemm g2 = tc_base(tab_op(w.tab[5], D, D), dat_op(w.t0, D, D, mats), mats, C, y_spec, false, false);     // Y^ = U1^T S
+  return tc_gemm_launch(g2, st);
+}
+
+int deblur_loss_grad_spec(const nhmc_op* op, const float* x_hat, const float* y_spec, float* g, float* xc_out, double* loss,
+                          int n_chains, void* workspace, cudaStream_t st) {
+  const int D = op->img_dim, C = op->channels, mats = n_chains * C;
+  NHMC_CHECK_ARG(use_tc(op), "the spectral loss needs the tensor-core path (img_dim % 4 == 0)");
+  const RedWs rw = red_ws(workspace, n_chains);
+  float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
+  const TcWs w = tc_ws(op, scratch, mats, D);
+  if (int e = tc_tables(op, w, true, st)) return e;
+  if (int e = tc_tables(op, w, false, st)) return e;
+  if (int e = tc_split_launch(x_hat, w.xs, w.xs + w.P, w.P, op->no_clamp ? 0 : 1, st)) return e;            // clamp(x_hat), split
+  TcGemm g1 = tc_base(dat_op(w.xs, D, D, mats), tab_op(w.tab[0], D, D), mats, C, w.t0, true, true);         // S^T = (Xc V2)^T
+  if (int e = tc_gemm_launch(g1, st)) return e;
+  TcGemm g2 = tc_base(tab_op(w.tab[1], D, D), dat_op(w.t0, D, D, mats), mats, C, w.t1, true, true);         // (gain .* (Y^ - gain .* V1^T S))^T, loss
+  g2.epi = TC_EPI_SPEC; g2.gain = op->gain; g2.y = y_spec; g2.loss = loss; g2.ws = rw;
+  if (int e = tc_gemm_launch(g2, st)) return e;
+  TcGemm g3 = tc_base(tab_op(w.tab[6], D, D), dat_op(w.t1, D, D, mats), mats, C, w.t0, true, false);        // T = V1 W
+  if (int e = tc_gemm_launch(g3, st)) return e;
+  TcGemm g4 = tc_base(dat_op(w.t0, D, D, mats), tab_op(w.tab[7], D, D), mats, C, g, false, false);          // g = -2 (T V2^T) .* mask
+  g4.epi = TC_EPI_GRAD; g4.xhat = x_hat; g4.no_clamp = op->no_clamp;
+  if (int e = tc_gemm_launch(g4, st)) return e;
+  if (xc_out) {
+    const int64_t total = (int64_t)mats * D * D;
+    clamp_copy_kernel<<<cta_count(total, kThreads * 4, 1), kThreads, 0, st>>>(x_hat, xc_out, total, op->no_clamp);
+  }
+  return NHMC_LAUNCH_CHECK();
+}
+
 int deblur_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
                      int n_chains, void* workspace, cudaStream_t st) {
   const int D = op->img_dim, C = op->channels, mats = n_chains * C;
   const RedWs rw = red_ws(workspace, n_chains);
   float* scratch = reinterpret_cast<float*>((char*)workspace + red_ws_aligned(n_chains));
   if (use_tc(op)) {
+    // measurement in the image domain: its spectral form is built here (two products), then the four-product evaluation;
+    // callers that evaluate many times against one measurement prepare it once (nhmc_op_prepare_measurement)
     const TcWs w = tc_ws(op, scratch, mats, D);
-    if (int e = tc_tables(op, w, true, st)) return e;
-    if (int e = tc_tables(op, w, false, st)) return e;
-    if (int e = tc_split_launch(x_hat, w.xs, w.xs + w.P, w.P, op->no_clamp ? 0 : 1, st)) return e;   // clamp(x_hat), split
-    TcGemm f{}; f.epi = TC_EPI_RESID; f.y = y; f.loss = loss; f.ws = rw; f.out_hi = w.rr; f.out_lo = w.rr + w.P;
-    if (int e = tc_chain(op, w, w.xs, op->gain, true, f, mats, st)) return e;                          // R = y - H(xc), loss
-    TcGemm b{}; b.epi = TC_EPI_GRAD; b.xhat = x_hat; b.no_clamp = op->no_clamp; b.out_hi = g;
-    if (int e = tc_chain(op, w, w.rr, op->gain, false, b, mats, st)) return e;                         // g = -2 H^T R .* mask
-  } else {
+    if (int e = deblur_spectral_measurement(op, y, w.rr, n_chains, scratch, st)) return e;
+    return deblur_loss_grad_spec(op, x_hat, w.rr, g, xc_out, loss, n_chains, workspace, st);
+  }
+  {
     NHMC_CHECK_ARG(((D + TM - 1) / TM) * ((D + TN - 1) / TN) * C <= kMaxBlocksPerChain, "image too large for the deblur loss reduction");
     float* t0 = scratch;
     float* t1 = t0 + (size_t)mats * D * D;

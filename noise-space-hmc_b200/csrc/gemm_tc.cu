@@ -98,6 +98,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+  // tail of the previous product of the chain; its results are visible from here on
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -165,6 +169,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       }
+      if (EPI == TC_EPI_SPEC) {
+        // spectral-domain residual of the deblurring operators (deblur.cu): r = y_spec - gain * v, loss += r^2, out = gain * r
+        const float4* gp = reinterpret_cast<const float4*>(a.gain + (int64_t)c * MN + row);
+        const float4* yp = reinterpret_cast<const float4*>(a.y + (int64_t)mat * MN + row);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          if (nb + j4 * 4 < a.N) {
+            const float4 g = __ldg(gp + j4), yv = __ldg(yp + j4);
+            const float g4[4] = {g.x, g.y, g.z, g.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float rr = __fsub_rn(y4[i], __fmul_rn(g4[i], v[j4 * 4 + i]));
+              lsum += (double)rr * (double)rr;
+              v[j4 * 4 + i] = __fmul_rn(g4[i], rr);
+            }
+          }
+        }
+      }
       if (EPI == TC_EPI_RESID) {
         const float4* yp = reinterpret_cast<const float4*>(a.y + (int64_t)mat * MN + row);
 #pragma unroll
@@ -221,7 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       }
     }
-    if (EPI == TC_EPI_RESID) {
+    if (EPI == TC_EPI_RESID || EPI == TC_EPI_SPEC) {
       lsum = warp_sum(lsum);
       if (lane == 0) red[q] = lsum;
     }
@@ -229,7 +251,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc<BN>(tmem); }
-  if (EPI == TC_EPI_RESID) {
+  if (EPI == TC_EPI_RESID || EPI == TC_EPI_SPEC) {
     double v[1] = {red[0] + red[1] + red[2] + red[3]};
     const int chain = mat / a.channels, c = mat % a.channels;
     const int tiles_c = gridDim.x * gridDim.y;
@@ -289,8 +311,7 @@ int launch_epi_bn(const CUtensorMap& ma, const CUtensorMap& mb, const TcKernelAr
   static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcTile<BN>::SMEM);
   if (attr != cudaSuccess) return cuda_status(attr, "tc_gemm smem attribute");
   const dim3 grid((k.N + BN - 1) / BN, (k.M + BM - 1) / BM, mats);
-  kern<<<grid, TC_THREADS, TcTile<BN>::SMEM, st>>>(ma, mb, k);
-  return NHMC_LAUNCH_CHECK();
+  return cuda_status(launch_pdl(true, kern, grid, dim3(TC_THREADS), (size_t)TcTile<BN>::SMEM, st, ma, mb, k), "tc_gemm launch");
 }
 
 static inline int pick_bn(int M, int N, int mats) {
@@ -334,6 +355,9 @@ int tc_gemm_launch(const TcGemm& g, cudaStream_t st) {
       NHMC_CHECK_ARG(g.y && g.loss && ((N + 127) / 128) * ((M + BM - 1) / BM) * k.channels <= kMaxBlocksPerChain, "residual epilogue arguments");
       return launch_epi<TC_EPI_RESID>(g, k, st);
     case TC_EPI_GRAD: NHMC_CHECK_ARG(g.xhat, "xhat required"); return launch_epi<TC_EPI_GRAD>(g, k, st);
+    case TC_EPI_SPEC:
+      NHMC_CHECK_ARG(g.y && g.gain && g.loss && ((N + 127) / 128) * ((M + BM - 1) / BM) * k.channels <= kMaxBlocksPerChain, "spectral residual epilogue arguments");
+      return launch_epi<TC_EPI_SPEC>(g, k, st);
   }
   set_error("tc_gemm: unknown epilogue %d", g.epi);
   return NHMC_ERR_ARG;

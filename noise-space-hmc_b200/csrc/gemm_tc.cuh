@@ -9,7 +9,7 @@
 
 namespace nhmc {
 
-enum { TC_EPI_NONE = 0, TC_EPI_GAIN = 1, TC_EPI_RESID = 2, TC_EPI_GRAD = 3 };
+enum { TC_EPI_NONE = 0, TC_EPI_GAIN = 1, TC_EPI_RESID = 2, TC_EPI_GRAD = 3, TC_EPI_SPEC = 4 };
 
 // A plane pair in global memory: plane p (0 = hi, 1 = lo) of matrix `mat` starts at base + p*plane_stride + mat*mat_stride
 // (elements); rows are dense (row stride = cols).  mat_stride 0 = one table shared by all matrices.
@@ -29,6 +29,7 @@ struct TcGemm {
   int64_t out_mat_stride;
   const float* gain;         // [channels][M][N]                (TC_EPI_GAIN)   indexed in C's logical (m, n)
   const float* y;            // [mats][M][N] measurement        (TC_EPI_RESID): v = y - v, loss += v^2
+                             //                                 (TC_EPI_SPEC):  r = y - gain v, loss += r^2, v = gain r   (spectral-domain residual)
   const float* xhat;         // [mats][M][N] unclamped image    (TC_EPI_GRAD):  v = -2 v 1[-1 <= xhat <= 1]
   double* loss;              // [chains]
   int no_clamp;

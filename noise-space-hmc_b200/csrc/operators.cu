@@ -21,6 +21,8 @@ int sepmat_loss_grad(const nhmc_op*, const float*, const float*, float*, float*,
 size_t sepmat_workspace_bytes(const nhmc_op*, int);
 size_t spectral_tables_bytes(const nhmc_op*);
 int spectral_prepare_tables(const nhmc_op*, float*, cudaStream_t);
+int deblur_spectral_measurement(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
+int deblur_loss_grad_spec(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
 int cs_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int cs_adjoint(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int cs_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
@@ -589,4 +591,23 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
       return phase_loss_grad(op, x_hat, y, g, xc_out, loss, n_chains, workspace, st);
   }
   return NHMC_LAUNCH_CHECK();
+}
+
+extern "C" int nhmc_op_prepare_measurement(const nhmc_op* op, const float* y, float* y_prepared, int n_chains, void* workspace,
+                                           nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(op && y && y_prepared && workspace && n_chains > 0, "bad arguments");
+  if (op->kind != NHMC_OP_DEBLUR2D || nhmc_op_tables_bytes(op) == 0) {
+    set_error("this operator evaluates against the measurement as it is (no prepared form)");
+    return NHMC_ERR_UNSUPPORTED;
+  }
+  NHMC_CHECK_ARG(aligned16(y) && aligned16(y_prepared), "measurements must be 16-byte aligned");
+  return deblur_spectral_measurement(op, y, y_prepared, n_chains, (char*)workspace + red_ws_aligned(n_chains), (cudaStream_t)stream);
+}
+
+extern "C" int nhmc_op_loss_grad_prepared(const nhmc_op* op, const float* x_hat, const float* y_prepared, float* g, float* xc_out,
+                                          double* loss, int n_chains, void* workspace, nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(op && x_hat && y_prepared && g && loss && workspace && n_chains > 0, "bad arguments");
+  NHMC_CHECK_ARG(op->kind == NHMC_OP_DEBLUR2D && nhmc_op_tables_bytes(op) > 0, "only the spectral deblurring operators have a prepared measurement");
+  NHMC_CHECK_ARG(aligned16(x_hat) && aligned16(y_prepared) && aligned16(g) && (!xc_out || aligned16(xc_out)), "buffers must be 16-byte aligned");
+  return deblur_loss_grad_spec(op, x_hat, y_prepared, g, xc_out, loss, n_chains, workspace, (cudaStream_t)stream);
 }

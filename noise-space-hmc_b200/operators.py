@@ -113,11 +113,33 @@ class Operator:
         xc = torch.empty_like(x_hat) if xc is None else xc
         loss = torch.empty(B, dtype=torch.float64, device=x_hat.device) if loss is None else loss
         nb = (3 * x_hat.numel() + y.numel()) * 4          # read x_hat + y, write g + clamped image
+        yp = self._prepared(y, B)
         with kernels._timed("op_loss_grad_" + type(self).__name__, self.loss_grad_launches, nb):
-            check(lib().nhmc_op_loss_grad(ctypes.byref(self.desc), x_hat.data_ptr(), y.data_ptr(), g.data_ptr(),
-                                          xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
-                                          kernels._stream()), "nhmc_op_loss_grad")
+            if yp is not None:
+                check(lib().nhmc_op_loss_grad_prepared(ctypes.byref(self.desc), x_hat.data_ptr(), yp.data_ptr(), g.data_ptr(),
+                                                       xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
+                                                       kernels._stream()), "nhmc_op_loss_grad_prepared")
+            else:
+                check(lib().nhmc_op_loss_grad(ctypes.byref(self.desc), x_hat.data_ptr(), y.data_ptr(), g.data_ptr(),
+                                              xc.data_ptr(), loss.data_ptr(), B, self._workspace(B).data_ptr(),
+                                              kernels._stream()), "nhmc_op_loss_grad")
         return loss, g, xc
+
+    def _prepared(self, y, B):
+        """Operators with a prepared measurement form (the spectral deblurring operators: nhmc_op_prepare_measurement) keep
+        it per measurement tensor (storage, version): a sampler evaluates thousands of times against one y."""
+        if not getattr(self, "has_prepared_measurement", False) or getattr(self, "_tc_tables", None) is None:
+            return None
+        key = (y.data_ptr(), y._version, tuple(y.shape))
+        c = self.__dict__.get("_prep")
+        if c is None or c[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                return None                                  # a new measurement inside a capture: the self-contained entry point
+            yp = torch.empty_like(y)
+            check(lib().nhmc_op_prepare_measurement(ctypes.byref(self.desc), y.data_ptr(), yp.data_ptr(), B,
+                                                    self._workspace(B).data_ptr(), kernels._stream()), "nhmc_op_prepare_measurement")
+            c = self.__dict__["_prep"] = (key, yp)
+        return c[1]
 
 
 class Inpainting(Operator):
@@ -220,7 +242,8 @@ def gaussian_taps(sigma, half=4):
 class Deblurring2D(Operator):
     """Y_c = U1 (G_c .* (V1^T X_c V2)) U2^T (Hfuncs.py:448-523, tiled-singulars quirk included)."""
     kind = _lib.OP_DEBLUR2D
-    loss_grad_launches = 10    # split of clamp(x_hat) + 8 tensor-core products + the clamped copy
+    loss_grad_launches = 6     # split of clamp(x_hat) + 4 tensor-core products (prepared measurement) + the clamped copy
+    has_prepared_measurement = True
 
     def __init__(self, kernel1, kernel2, channels, img_dim, device, tables=None, zero=3e-2):
         super().__init__(channels, img_dim, device)
