@@ -183,6 +183,44 @@ __device__ __forceinline__ bool grid_finish(double (&v)[NV], double* partials /*
   return false;
 }
 
+// Deterministic cross-block finish with the whole last block: thread t adds partials t, t + 256, ... in fp64, then one
+// fixed-shape block reduction -- the result depends on nblk only, never on arrival order, and the tail costs one
+// block-reduce instead of a serial walk over nblk L2 round trips.
+template <int NV>
+__device__ __forceinline__ bool grid_finish_par(double (&v)[NV], double* partials, unsigned int* ticket, int blk, int nblk,
+                                                double* red /* [NV*32] */) {
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) partials[blk * NV + i] = v[i];
+    __threadfence();
+    is_last = atomicInc(ticket, (unsigned int)(nblk - 1)) == (unsigned int)(nblk - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.0;
+  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += __ldcg(&partials[k * NV + i]);
+  }
+  block_sum<double, NV>(v, red);
+  return threadIdx.x == 0;
+}
+
+// CTAs per chain for a streaming kernel that ENDS in a cross-block reduction: one resident wave (8 CTAs of 256 threads per
+// SM over all chains), so that the block reduce + ticket of every CTA is amortised over >= ~10 vectors per thread.
+static inline int reduce_cta_count(int64_t items, int64_t per_cta, int n_chains) {
+  int64_t want = (items + per_cta - 1) / per_cta;
+  int64_t cap = (int64_t)kSMs * 8 / (n_chains > 0 ? n_chains : 1);
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  if (want > 256) want = 256;
+  return (int)want;
+}
+
 static inline int blocks_per_chain(int64_t n_vec, int n_chains, int vec_per_thread) {
   // enough CTAs to cover the chain once with `vec_per_thread` vectors per thread, but keep the
   // whole grid within ~4 resident waves of the 148 SMs (8 CTAs of 256 threads each per SM).

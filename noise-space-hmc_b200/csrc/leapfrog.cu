@@ -28,32 +28,6 @@ struct LfDiag {
   float* wf_m2;            // [B, N]
 };
 
-// Deterministic cross-block finish with the whole last block: thread t adds partials t, t + 256, ... in fp64, then one
-// fixed-shape block reduction -- the result depends on nblk only, never on arrival order, and the tail costs one
-// block-reduce instead of a serial walk over nblk L2 round trips.
-template <int NV>
-__device__ __forceinline__ bool grid_finish_par(double (&v)[NV], double* partials, unsigned int* ticket, int blk, int nblk,
-                                                double* red /* [NV*32] */) {
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) partials[blk * NV + i] = v[i];
-    __threadfence();
-    is_last = atomicInc(ticket, (unsigned int)(nblk - 1)) == (unsigned int)(nblk - 1);
-  }
-  __syncthreads();
-  if (!is_last) return false;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) v[i] = 0.0;
-  for (int k = threadIdx.x; k < nblk; k += blockDim.x) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] += __ldcg(&partials[k * NV + i]);
-  }
-  block_sum<double, NV>(v, red);
-  return threadIdx.x == 0;
-}
-
 template <int MODE, bool HAS_GB, bool DIAG>
 __global__ void __launch_bounds__(kThreads)
 leapfrog_kernel(const float* __restrict__ x_in, float* x_out, float* p, const float* __restrict__ g_a,

@@ -75,32 +75,55 @@ inpaint_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__
   const float* xb = xh + (int64_t)b * N;
   const float* yb = y + (int64_t)b * M;
   double acc = 0.0;
-  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
-    const int64_t e0 = v * 4;
-    const int c = (int)(e0 / P);
-    const int64_t pix0 = e0 - (int64_t)c * P;
-    const float4 xv = ld_ro(reinterpret_cast<const float4*>(xb + e0));
-    const int4 kv = __ldg(reinterpret_cast<const int4*>(p2k + pix0));
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    const int ks[4] = {kv.x, kv.y, kv.z, kv.w};
-    float gs[4], cs[4];
+  constexpr int U = 4;          // vectors in flight per thread: x and the pixel -> kept-rank table first, then the gathered y
+  const int64_t stride = (int64_t)nblk * kThreads;
+  for (int64_t v0 = (int64_t)blk * kThreads + threadIdx.x; v0 < n_vec; v0 += stride * U) {
+    float4 xv[U]; int4 kv[U]; int cc[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      cs[j] = clampx(xs[j], nc);
-      gs[j] = 0.0f;
-      if (ks[j] >= 0) {
-        const float r = __fsub_rn(__ldg(yb + (int64_t)ks[j] * C + c), cs[j]);
-        acc += (double)r * (double)r;
-        gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      xv[u] = make_float4(0, 0, 0, 0); kv[u] = make_int4(-1, -1, -1, -1); cc[u] = 0;
+      if (v < n_vec) {
+        const int64_t e0 = v * 4;
+        cc[u] = (int)(e0 / P);
+        xv[u] = ld_ro(reinterpret_cast<const float4*>(xb + e0));
+        kv[u] = __ldg(reinterpret_cast<const int4*>(p2k + (e0 - (int64_t)cc[u] * P)));
       }
     }
-    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N + e0), make_float4(gs[0], gs[1], gs[2], gs[3]));
-    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N + e0), make_float4(cs[0], cs[1], cs[2], cs[3]));
+    float yv[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ks[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) yv[u][j] = ks[j] >= 0 ? __ldg(yb + (int64_t)ks[j] * C + cc[u]) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= n_vec) continue;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const int ks[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
+      float gs[4], cs[4];
+      double a4 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cs[j] = clampx(xs[j], nc);
+        gs[j] = 0.0f;
+        if (ks[j] >= 0) {
+          const float r = __fsub_rn(yv[u][j], cs[j]);
+          a4 += (double)r * (double)r;
+          gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+        }
+      }
+      acc += a4;
+      st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+      if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+    }
   }
   __shared__ double red[32];
   double vsum[1] = {acc};
   block_sum<double, 1>(vsum, red);
-  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+  if (grid_finish_par<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk, red)) loss[b] = vsum[0];
 }
 
 // =====================================================================================
@@ -196,6 +219,63 @@ sr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, f
   if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, strip, nstrips)) loss[b] = vsum[0];
 }
 
+// r in {4, 8, 16}: no shared memory, no block barrier.  A cell's row is r/4 float4 = LPC lanes; a lane keeps its float4 of
+// all r rows of the cell in registers (r independent 16-byte loads in flight), the cell sum is r adds per lane + log2(LPC)
+// shuffles, and the same lane writes the gradient (and the clamped copy) of the r x 4 pixels it loaded.  A warp covers
+// 32 / LPC neighbouring cells of one cell row: every load / store instruction touches whole 128-byte lines.
+template <int R>
+__global__ void __launch_bounds__(kThreads)
+sr_loss_grad_reg_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
+                        float* __restrict__ xc_out, int C, int D, double* loss, RedWs ws, int nc) {
+  constexpr int LPC = R / 4;                       // lanes per cell row
+  const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+  const int yd = D / R;
+  const int64_t N = (int64_t)C * D * D, M = (int64_t)C * yd * yd;
+  const int64_t n_items = M * LPC;                 // one item = (cell, lane-in-cell)
+  const float inv = 1.0f / (float)(R * R);
+  double acc = 0.0;
+  const float* xb = xh + (int64_t)b * N;
+  for (int64_t it = (int64_t)blk * kThreads + threadIdx.x; it < ((n_items + 31) / 32) * 32; it += (int64_t)nblk * kThreads) {
+    const bool ok = it < n_items;                  // whole warps stay in the loop for the shuffles
+    const int64_t cell = ok ? it / LPC : 0;
+    const int q = (int)(it % LPC);
+    const int c = (int)(cell / ((int64_t)yd * yd));
+    const int rem = (int)(cell - (int64_t)c * yd * yd);
+    const int ci = rem / yd, cj = rem - ci * yd;
+    const int64_t off = ((int64_t)c * D + (int64_t)ci * R) * D + (int64_t)cj * R + q * 4;
+    float4 v[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) v[u] = ok ? ld_ro(reinterpret_cast<const float4*>(xb + off + (int64_t)u * D)) : make_float4(0, 0, 0, 0);
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      float rs = clampx(v[u].x, nc) + clampx(v[u].y, nc);
+      rs += clampx(v[u].z, nc); rs += clampx(v[u].w, nc);
+      s += rs;
+    }
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float res = ok ? __fsub_rn(__ldg(y + (int64_t)b * M + cell), s * inv) : 0.f;
+    if (ok && q == 0) acc += (double)res * (double)res;
+    if (ok) {
+      const float gv = -(2.0f * res) * inv;
+      float* gd = g + (int64_t)b * N + off;
+      float* cd = xc_out ? xc_out + (int64_t)b * N + off : nullptr;
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        st_stream(reinterpret_cast<float4*>(gd + (int64_t)u * D),
+                  make_float4(gv * maskx(v[u].x, nc), gv * maskx(v[u].y, nc), gv * maskx(v[u].z, nc), gv * maskx(v[u].w, nc)));
+        if (cd) st_stream(reinterpret_cast<float4*>(cd + (int64_t)u * D),
+                          make_float4(clampx(v[u].x, nc), clampx(v[u].y, nc), clampx(v[u].z, nc), clampx(v[u].w, nc)));
+      }
+    }
+  }
+  __shared__ double red[32];
+  double vsum[1] = {acc};
+  block_sum<double, 1>(vsum, red);
+  if (grid_finish_par<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk, red)) loss[b] = vsum[0];
+}
+
 // =====================================================================================
 // HDR
 // =====================================================================================
@@ -215,26 +295,41 @@ hdr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, 
   const float4* xb = reinterpret_cast<const float4*>(xh + (int64_t)b * N);
   const float4* yb = reinterpret_cast<const float4*>(y + (int64_t)b * N);
   double acc = 0.0;
-  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
-    const float4 xv = ld_ro(xb + v), yv = ld_ro(yb + v);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
-    float gs[4], cs[4];
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)nblk * kThreads;
+  for (int64_t v0 = (int64_t)blk * kThreads + threadIdx.x; v0 < n_vec; v0 += stride * U) {
+    float4 xv[U], yv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      cs[j] = clampx(xs[j], nc);
-      const float h = __fdiv_rn(cs[j], 0.5f);
-      const float r = __fsub_rn(ys[j], clamp1(h));
-      acc += (double)r * (double)r;
-      // -2 r * d clip(h)/dh * dh/dx * d clamp(x)/dx
-      gs[j] = -(2.0f * r) * inr(h, -1.0f, 1.0f) * 2.0f * maskx(xs[j], nc);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      xv[u] = yv[u] = make_float4(0, 0, 0, 0);
+      if (v < n_vec) { xv[u] = ld_ro(xb + v); yv[u] = ld_ro(yb + v); }
     }
-    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
-    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= n_vec) continue;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ys[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+      float gs[4], cs[4];
+      double a4 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cs[j] = clampx(xs[j], nc);
+        const float h = __fdiv_rn(cs[j], 0.5f);
+        const float r = __fsub_rn(ys[j], clamp1(h));
+        a4 += (double)r * (double)r;
+        // -2 r * d clip(h)/dh * dh/dx * d clamp(x)/dx
+        gs[j] = -(2.0f * r) * inr(h, -1.0f, 1.0f) * 2.0f * maskx(xs[j], nc);
+      }
+      acc += a4;
+      st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+      if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+    }
   }
   __shared__ double red[32];
   double vsum[1] = {acc};
   block_sum<double, 1>(vsum, red);
-  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+  if (grid_finish_par<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk, red)) loss[b] = vsum[0];
 }
 
 // =====================================================================================
@@ -242,30 +337,45 @@ hdr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, 
 // =====================================================================================
 __global__ void __launch_bounds__(kThreads)
 denoise_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
-                         float* __restrict__ xc_out, int64_t N, double* loss, RedWs ws, int nc) {
+                     float* __restrict__ xc_out, int64_t N, double* loss, RedWs ws, int nc) {
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int64_t n_vec = N / 4;
   const float4* xb = reinterpret_cast<const float4*>(xh + (int64_t)b * N);
   const float4* yb = reinterpret_cast<const float4*>(y + (int64_t)b * N);
   double acc = 0.0;
-  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
-    const float4 xv = ld_ro(xb + v), yv = ld_ro(yb + v);
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
-    float gs[4], cs[4];
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)nblk * kThreads;
+  for (int64_t v0 = (int64_t)blk * kThreads + threadIdx.x; v0 < n_vec; v0 += stride * U) {
+    float4 xv[U], yv[U];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      cs[j] = clampx(xs[j], nc);
-      const float r = __fsub_rn(ys[j], cs[j]);
-      acc += (double)r * (double)r;
-      gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      xv[u] = yv[u] = make_float4(0, 0, 0, 0);
+      if (v < n_vec) { xv[u] = ld_ro(xb + v); yv[u] = ld_ro(yb + v); }
     }
-    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
-    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = v0 + u * stride;
+      if (v >= n_vec) continue;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, ys[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+      float gs[4], cs[4];
+      double a4 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cs[j] = clampx(xs[j], nc);
+        const float r = __fsub_rn(ys[j], cs[j]);
+        a4 += (double)r * (double)r;
+        gs[j] = -(2.0f * r) * maskx(xs[j], nc);
+      }
+      acc += a4;
+      st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
+      if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
+    }
   }
   __shared__ double red[32];
   double vsum[1] = {acc};
   block_sum<double, 1>(vsum, red);
-  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+  if (grid_finish_par<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk, red)) loss[b] = vsum[0];
 }
 
 // =====================================================================================
@@ -324,7 +434,7 @@ color_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y
   __shared__ double red[32];
   double vsum[1] = {acc};
   block_sum<double, 1>(vsum, red);
-  if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk)) loss[b] = vsum[0];
+  if (grid_finish_par<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, blk, nblk, red)) loss[b] = vsum[0];
 }
 static inline Coef3 coef3(const nhmc_op* op, int first) { Coef3 c; for (int i = 0; i < 3; ++i) c.v[i] = op->coef[first + i]; return c; }
 
@@ -545,12 +655,21 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
   switch (op->kind) {
     case NHMC_OP_INPAINT: {
       NHMC_CHECK_ARG(P % 4 == 0 && aligned16(op->pix_to_kept), "img_dim^2 must be a multiple of 4");
-      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      dim3 grid(reduce_cta_count(N / 4, kThreads * 4, n_chains), n_chains);
       inpaint_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, op->pix_to_kept, op->n_kept, C, P, loss, ws, op->no_clamp);
       break;
     }
     case NHMC_OP_SR: {
-      const int r = op->ratio, TR = sr_tile_rows(D, r);
+      const int r = op->ratio;
+      if ((r == 4 || r == 8 || r == 16) && D % r == 0 && aligned16(x_hat) && aligned16(g)) {
+        const int64_t items = (int64_t)C * (D / r) * (D / r) * (r / 4);
+        dim3 grid(reduce_cta_count(items, kThreads, n_chains), n_chains);
+        if (r == 4) sr_loss_grad_reg_kernel<4><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        else if (r == 8) sr_loss_grad_reg_kernel<8><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        else sr_loss_grad_reg_kernel<16><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        break;
+      }
+      const int TR = sr_tile_rows(D, r);
       NHMC_CHECK_ARG(D % 4 == 0 && D % TR == 0, "img_dim must be a multiple of 4 and of the strip height");
       const int strips = C * (D / TR);
       NHMC_CHECK_ARG(strips <= kMaxBlocksPerChain, "image too large for the SR strip reduction");
@@ -564,19 +683,19 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
     }
     case NHMC_OP_HDR: {
       NHMC_CHECK_ARG(N % 4 == 0 && aligned16(y), "N must be a multiple of 4");
-      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      dim3 grid(reduce_cta_count(N / 4, kThreads * 4, n_chains), n_chains);
       hdr_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, N, loss, ws, op->no_clamp);
       break;
     }
     case NHMC_OP_DENOISE: {
       NHMC_CHECK_ARG(N % 4 == 0 && aligned16(y), "N must be a multiple of 4");
-      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);
+      dim3 grid(reduce_cta_count(N / 4, kThreads * 4, n_chains), n_chains);
       denoise_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, N, loss, ws, op->no_clamp);
       break;
     }
     case NHMC_OP_COLOR: {
       NHMC_CHECK_ARG(P % 4 == 0 && aligned16(y), "img_dim^2 must be a multiple of 4");
-      dim3 grid(cta_count(P / 4, kThreads, n_chains), n_chains);
+      dim3 grid(reduce_cta_count(P / 4, kThreads, n_chains), n_chains);
       color_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, P, coef3(op, 0), coef3(op, 3), loss, ws, op->no_clamp);
       break;
     }

@@ -144,6 +144,15 @@ def main():
                 gg = torch.empty_like(xs); xc = torch.empty_like(xs); ls = torch.zeros(Bo, dtype=torch.float64, device=dev)
                 ms = timeit(lambda: op.loss_grad(xs, y, g=gg, xc=xc, loss=ls), a.reps, flush)
                 report("op_loss_grad_" + nm, [Bo, 3, 256, 256], (3 * xs.numel() + y.numel()) * 4, ms, pk)
+                if nm == "deblur":
+                    # tensor-bound: 4 products of 2 * 256^3 flop per (chain, channel), each issued as 3 tf32 MMAs (3xTF32)
+                    fl = 4 * Bo * 3 * 2 * 256 ** 3
+                    pkf = os.path.join(ROOT, "MEASURED_PEAKS.json")
+                    tf32_peak = (float(json.load(open(pkf))["bf16_tflops"]) if os.path.isfile(pkf) else 1590.0) / 2     # tf32 = half the bf16 rate
+                    print(json.dumps({"kernel": "op_loss_grad_deblur", "bound": "tensor", "shape": [Bo, 3, 256, 256], "us": round(ms * 1e3, 2),
+                                      "fp32_grade_TFLOPs": round(fl / 1e12 / (ms / 1e3), 1), "tf32_issued_TFLOPs": round(3 * fl / 1e12 / (ms / 1e3), 1),
+                                      "tf32_peak_TFLOPs": tf32_peak, "frac_of_tf32_peak": round(3 * fl / 1e12 / (ms / 1e3) / tf32_peak, 3),
+                                      "note": "tf32 peak taken as half the measured cuBLAS bf16 burst peak (MEASURED_PEAKS.json)"}), flush=True)
     if want("pool") or want("split"):
         B, C, H = 8, 256, 128
         big = torch.randn(B, C, 2 * H, 2 * H, device=dev, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
