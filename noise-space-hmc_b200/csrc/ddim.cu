@@ -23,41 +23,27 @@ ddim_fwd_kernel(const float* __restrict__ xt, const TE* __restrict__ eps, int64_
   const TE* eb = eps + (int64_t)b * eps_stride;
   float* ob = out + (int64_t)b * n_per_chain;
   uint32_t* mb = mask ? mask + (int64_t)b * mask_words : nullptr;
-  constexpr int U = 4;   // groups in flight per warp: all loads of a batch are issued before the first use
-  for (int64_t g0 = warp0; g0 < n_groups; g0 += nwarps * U) {
-    float4 xv[U], ev[U];
-    bool okv[U];
+  for (int64_t gidx = warp0; gidx < n_groups; gidx += nwarps) {
+    const int64_t e0 = gidx * 128 + lane * 4;
+    const bool ok = e0 < n_per_chain;  // n_per_chain % 4 == 0 on this path
+    float4 x = ok ? ld_ro(reinterpret_cast<const float4*>(xb + e0)) : make_float4(0, 0, 0, 0);
+    float4 e = ok ? load4<TE>(eb + e0) : make_float4(0, 0, 0, 0);
+    float xs[4] = {x.x, x.y, x.z, x.w};
+    const float es[4] = {e.x, e.y, e.z, e.w};
+    uint32_t bits[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t gidx = g0 + (int64_t)u * nwarps;
-      const int64_t e0 = gidx * 128 + lane * 4;
-      okv[u] = gidx < n_groups && e0 < n_per_chain;  // n_per_chain % 4 == 0 on this path
-      xv[u] = okv[u] ? ld_ro(reinterpret_cast<const float4*>(xb + e0)) : make_float4(0, 0, 0, 0);
-      ev[u] = okv[u] ? load4<TE>(eb + e0) : make_float4(0, 0, 0, 0);
+    for (int j = 0; j < 4; ++j) {
+      // (xt - eps*c1)/sa ; clip ; ss*x0 + c2*eps   -- reference operation order, no contraction
+      const float x0raw = __fdiv_rn(__fsub_rn(xs[j], __fmul_rn(es[j], c1)), sa);
+      const bool in = (x0raw >= -1.0f) && (x0raw <= 1.0f);
+      const float x0 = fminf(fmaxf(x0raw, -1.0f), 1.0f);
+      xs[j] = __fadd_rn(__fmul_rn(ss, x0), __fmul_rn(c2, es[j]));
+      bits[j] = __ballot_sync(0xffffffffu, ok && in);
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t gidx = g0 + (int64_t)u * nwarps;
-      if (gidx >= n_groups) break;                   // warp-uniform
-      const int64_t e0 = gidx * 128 + lane * 4;
-      const bool ok = okv[u];
-      float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-      const float es[4] = {ev[u].x, ev[u].y, ev[u].z, ev[u].w};
-      uint32_t bits[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        // (xt - eps*c1)/sa ; clip ; ss*x0 + c2*eps   -- reference operation order, no contraction
-        const float x0raw = __fdiv_rn(__fsub_rn(xs[j], __fmul_rn(es[j], c1)), sa);
-        const bool in = (x0raw >= -1.0f) && (x0raw <= 1.0f);
-        const float x0 = fminf(fmaxf(x0raw, -1.0f), 1.0f);
-        xs[j] = __fadd_rn(__fmul_rn(ss, x0), __fmul_rn(c2, es[j]));
-        bits[j] = __ballot_sync(0xffffffffu, ok && in);
-      }
-      if (ok) st_stream(reinterpret_cast<float4*>(ob + e0), make_float4(xs[0], xs[1], xs[2], xs[3]));
-      if (mb && lane < 4) {
-        const uint32_t w = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
-        mb[gidx * 4 + lane] = w;
-      }
+    if (ok) st_stream(reinterpret_cast<float4*>(ob + e0), make_float4(xs[0], xs[1], xs[2], xs[3]));
+    if (mb && lane < 4) {
+      const uint32_t w = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
+      mb[gidx * 4 + lane] = w;
     }
   }
 }
@@ -76,52 +62,34 @@ ddim_bwd_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, co
   const uint32_t* mb = mask + (int64_t)b * mask_words;
   float* ox = g_xt + (int64_t)b * n_per_chain;
   TE* oe = HAS_GE ? g_eps + (int64_t)b * eps_stride : nullptr;
-  constexpr int U = 4;
-  for (int64_t g0 = warp0; g0 < n_groups; g0 += nwarps * U) {
-    float4 gv[U], tv[U];
-    uint4 mv[U];
-    bool okv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t gidx = g0 + (int64_t)u * nwarps;
-      const int64_t e0 = gidx * 128 + lane * 4;
-      okv[u] = gidx < n_groups && e0 < n_per_chain;
-      gv[u] = tv[u] = make_float4(0, 0, 0, 0); mv[u] = make_uint4(0, 0, 0, 0);
-      if (okv[u]) {
-        mv[u] = __ldg(reinterpret_cast<const uint4*>(mb + gidx * 4));  // same 16 B for the whole warp
-        gv[u] = ld_ro(reinterpret_cast<const float4*>(ga + e0));
-        if (HAS_GB) tv[u] = ld_ro(reinterpret_cast<const float4*>(gb + e0));
-      }
+  for (int64_t gidx = warp0; gidx < n_groups; gidx += nwarps) {
+    const int64_t e0 = gidx * 128 + lane * 4;
+    if (e0 >= n_per_chain) continue;
+    const uint4 mw = __ldg(reinterpret_cast<const uint4*>(mb + gidx * 4));  // same 16 B for the whole warp
+    float4 g = ld_ro(reinterpret_cast<const float4*>(ga + e0));
+    if (HAS_GB) {
+      const float4 t = ld_ro(reinterpret_cast<const float4*>(gb + e0));
+      g.x = __fadd_rn(g.x, t.x); g.y = __fadd_rn(g.y, t.y); g.z = __fadd_rn(g.z, t.z); g.w = __fadd_rn(g.w, t.w);
     }
+    const float gs[4] = {g.x, g.y, g.z, g.w};
+    const uint32_t ms[4] = {mw.x, mw.y, mw.z, mw.w};
+    float gx[4], ge[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!okv[u]) continue;
-      const int64_t e0 = (g0 + (int64_t)u * nwarps) * 128 + lane * 4;
-      float4 g = gv[u];
-      if (HAS_GB) {
-        const float4 t = tv[u];
-        g.x = __fadd_rn(g.x, t.x); g.y = __fadd_rn(g.y, t.y); g.z = __fadd_rn(g.z, t.z); g.w = __fadd_rn(g.w, t.w);
-      }
-      const float gs[4] = {g.x, g.y, g.z, g.w};
-      const uint32_t ms[4] = {mv[u].x, mv[u].y, mv[u].z, mv[u].w};
-      float gx[4], ge[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float m = ((ms[j] >> lane) & 1u) ? 1.0f : 0.0f;
-        // autograd order: d(ss*x0) -> clamp mask -> /sa ; eps gets c2*g' and -c1 * that
-        const float gx0 = __fmul_rn(__fmul_rn(ss, gs[j]), m);
-        gx[j] = __fdiv_rn(gx0, sa);
-        ge[j] = __fsub_rn(__fmul_rn(c2, gs[j]), __fmul_rn(gx[j], c1));
-      }
-      st_stream(reinterpret_cast<float4*>(ox + e0), make_float4(gx[0], gx[1], gx[2], gx[3]));
-      if (HAS_GE) store4<TE>(oe + e0, make_float4(ge[0], ge[1], ge[2], ge[3]));
+    for (int j = 0; j < 4; ++j) {
+      const float m = ((ms[j] >> lane) & 1u) ? 1.0f : 0.0f;
+      // autograd order: d(ss*x0) -> clamp mask -> /sa ; eps gets c2*g' and -c1 * that
+      const float gx0 = __fmul_rn(__fmul_rn(ss, gs[j]), m);
+      gx[j] = __fdiv_rn(gx0, sa);
+      ge[j] = __fsub_rn(__fmul_rn(c2, gs[j]), __fmul_rn(gx[j], c1));
     }
+    st_stream(reinterpret_cast<float4*>(ox + e0), make_float4(gx[0], gx[1], gx[2], gx[3]));
+    if (HAS_GE) store4<TE>(oe + e0, make_float4(ge[0], ge[1], ge[2], ge[3]));
   }
 }
 
 static inline dim3 ddim_grid(int64_t n_groups, int n_chains) {
-  // one warp per 128-element group and step; 8 warps per CTA, 4 groups in flight per warp
-  return dim3(cta_count(n_groups, 32, n_chains), n_chains);
+  // one warp per 128-element group and step; 8 warps per CTA, 2 groups per warp
+  return dim3(cta_count(n_groups, 16, n_chains), n_chains);
 }
 
 }  // namespace nhmc

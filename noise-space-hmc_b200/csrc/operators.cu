@@ -75,50 +75,27 @@ inpaint_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__
   const float* xb = xh + (int64_t)b * N;
   const float* yb = y + (int64_t)b * M;
   double acc = 0.0;
-  constexpr int U = 4;          // vectors in flight per thread: x and the pixel -> kept-rank table first, then the gathered y
-  const int64_t stride = (int64_t)nblk * kThreads;
-  for (int64_t v0 = (int64_t)blk * kThreads + threadIdx.x; v0 < n_vec; v0 += stride * U) {
-    float4 xv[U]; int4 kv[U]; int cc[U];
+  for (int64_t v = (int64_t)blk * kThreads + threadIdx.x; v < n_vec; v += (int64_t)nblk * kThreads) {
+    const int64_t e0 = v * 4;
+    const int c = (int)(e0 / P);
+    const int64_t pix0 = e0 - (int64_t)c * P;
+    const float4 xv = ld_ro(reinterpret_cast<const float4*>(xb + e0));
+    const int4 kv = __ldg(reinterpret_cast<const int4*>(p2k + pix0));
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const int ks[4] = {kv.x, kv.y, kv.z, kv.w};
+    float gs[4], cs[4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t v = v0 + u * stride;
-      xv[u] = make_float4(0, 0, 0, 0); kv[u] = make_int4(-1, -1, -1, -1); cc[u] = 0;
-      if (v < n_vec) {
-        const int64_t e0 = v * 4;
-        cc[u] = (int)(e0 / P);
-        xv[u] = ld_ro(reinterpret_cast<const float4*>(xb + e0));
-        kv[u] = __ldg(reinterpret_cast<const int4*>(p2k + (e0 - (int64_t)cc[u] * P)));
+    for (int j = 0; j < 4; ++j) {
+      cs[j] = clampx(xs[j], nc);
+      gs[j] = 0.0f;
+      if (ks[j] >= 0) {
+        const float r = __fsub_rn(__ldg(yb + (int64_t)ks[j] * C + c), cs[j]);
+        acc += (double)r * (double)r;
+        gs[j] = -(2.0f * r) * maskx(xs[j], nc);
       }
     }
-    float yv[U][4];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ks[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) yv[u][j] = ks[j] >= 0 ? __ldg(yb + (int64_t)ks[j] * C + cc[u]) : 0.0f;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t v = v0 + u * stride;
-      if (v >= n_vec) continue;
-      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-      const int ks[4] = {kv[u].x, kv[u].y, kv[u].z, kv[u].w};
-      float gs[4], cs[4];
-      double a4 = 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        cs[j] = clampx(xs[j], nc);
-        gs[j] = 0.0f;
-        if (ks[j] >= 0) {
-          const float r = __fsub_rn(yv[u][j], cs[j]);
-          a4 += (double)r * (double)r;
-          gs[j] = -(2.0f * r) * maskx(xs[j], nc);
-        }
-      }
-      acc += a4;
-      st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N) + v, make_float4(gs[0], gs[1], gs[2], gs[3]));
-      if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N) + v, make_float4(cs[0], cs[1], cs[2], cs[3]));
-    }
+    st_stream(reinterpret_cast<float4*>(g + (int64_t)b * N + e0), make_float4(gs[0], gs[1], gs[2], gs[3]));
+    if (xc_out) st_stream(reinterpret_cast<float4*>(xc_out + (int64_t)b * N + e0), make_float4(cs[0], cs[1], cs[2], cs[3]));
   }
   __shared__ double red[32];
   double vsum[1] = {acc};
@@ -655,7 +632,7 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
   switch (op->kind) {
     case NHMC_OP_INPAINT: {
       NHMC_CHECK_ARG(P % 4 == 0 && aligned16(op->pix_to_kept), "img_dim^2 must be a multiple of 4");
-      dim3 grid(reduce_cta_count(N / 4, kThreads * 4, n_chains), n_chains);
+      dim3 grid(cta_count(N / 4, kThreads * 2, n_chains), n_chains);   // gather-bound: many small CTAs hide the dependent y loads best
       inpaint_loss_grad_kernel<<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, op->pix_to_kept, op->n_kept, C, P, loss, ws, op->no_clamp);
       break;
     }

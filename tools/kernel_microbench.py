@@ -29,32 +29,33 @@ GRAPH_CALLS = 1
 
 
 def timeit(fn, reps, flush=None):
-    """Median CUDA-event time of fn() with a cold, CLEAN L2: the flush buffer (> L2) is written, then read back,
-    so that the timed kernel neither hits in L2 nor pays for the write-back of the flush's dirty lines."""
+    """Median CUDA-event time of fn() with a cold, CLEAN L2: the flush buffer (> L2) is written, then read back, so that the
+    timed kernel neither hits in L2 nor pays for the write-back of the flush's dirty lines.  Flush, start event, the call
+    and the stop event are ONE captured CUDA graph (event-record nodes), replayed `reps` times: the host's launch latency
+    (ctypes + python, several microseconds -- comparable to these kernels) never sits between the two events."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    if GRAPH_CALLS > 1:
-        # back-to-back launches replayed from a CUDA graph (as inside the captured sampler step): per-call device time
-        # without host launch gaps
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(GRAPH_CALLS):
-                fn()
-        one = fn
-        fn = g.replay
-        fn(); torch.cuda.synchronize()
-    ms = []
-    for _ in range(reps):
+    calls = max(GRAPH_CALLS, 1)
+    s = torch.cuda.Event(enable_timing=True, external=True)
+    e = torch.cuda.Event(enable_timing=True, external=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
         if flush is not None:
             flush.zero_()
             flush.view(torch.int32).sum()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); fn(); e.record()
+        s.record()
+        for _ in range(calls):
+            fn()
+        e.record()
+    g.replay(); torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        g.replay()
         torch.cuda.synchronize()
         ms.append(s.elapsed_time(e))
     ms.sort()
-    return ms[len(ms) // 2] / max(GRAPH_CALLS, 1)
+    return ms[len(ms) // 2] / calls
 
 
 def report(name, shape, nbytes, ms, pk):
