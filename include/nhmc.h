@@ -139,6 +139,12 @@ int nhmc_ddim_bwd(const float* g_a, const float* g_b, const uint32_t* mask, floa
                   void* g_eps_out, int eps_dtype, int64_t eps_chain_stride, float c1, float sa,
                   float c2, float ss, int n_chains, int64_t n_per_chain, nhmc_stream_t stream);
 
+/* Latent path: the clip of the DDIM output that feeds the decoder, zc = clamp(z, -1, 1) (main_sampling_latent.py:651;
+ * zc_copy nullable: a second destination, the sample the sampler keeps), and its gradient mask behind the decoder's VJP,
+ * out = g * 1[-1 <= z <= 1] with g in the decoder's dtype and out fp32 (autograd of clamp is inclusive). */
+int nhmc_clip_fwd(const float* z, float* zc, float* zc_copy, int64_t n, nhmc_stream_t stream);
+int nhmc_clip_bwd(const void* g, int g_dtype, const float* z, float* out, int64_t n, nhmc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * K4/K5 measurement operators (obs_functions/Hfuncs.py).  All table pointers are DEVICE
  * pointers owned by the caller.

@@ -62,6 +62,8 @@ _SIGS = {
                                 C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64, C.c_void_p]),
     "nhmc_ddim_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int64, C.c_void_p]),
+    "nhmc_clip_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "nhmc_clip_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "nhmc_op_meas_size": (C.c_int64, [C.POINTER(OpDesc)]),
     "nhmc_op_workspace_bytes": (C.c_size_t, [C.POINTER(OpDesc), C.c_int]),
     "nhmc_op_tables_bytes": (C.c_size_t, [C.POINTER(OpDesc)]),

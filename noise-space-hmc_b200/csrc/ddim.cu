@@ -87,6 +87,23 @@ ddim_bwd_kernel(const float* __restrict__ g_a, const float* __restrict__ g_b, co
   }
 }
 
+// Latent path (main_sampling_latent.py:651,670): the clip of the DDIM output in front of the decoder and its gradient
+// mask behind the decoder's VJP, one small kernel each instead of clamp / copy / two compares / and / cast / mul.
+__global__ void clip_fwd_kernel(const float* __restrict__ z, float* __restrict__ zc, float* __restrict__ zc2, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(z[i], -1.0f), 1.0f);
+    zc[i] = v;
+    if (zc2) zc2[i] = v;
+  }
+}
+template <typename TG>
+__global__ void clip_bwd_kernel(const TG* __restrict__ g, const float* __restrict__ z, float* __restrict__ out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float zv = z[i];
+    out[i] = (zv >= -1.0f && zv <= 1.0f) ? Elem<TG>::to_f(g[i]) : 0.0f;
+  }
+}
+
 static inline dim3 ddim_grid(int64_t n_groups, int n_chains) {
   // one warp per 128-element group and step; 8 warps per CTA, 2 groups per warp
   return dim3(cta_count(n_groups, 16, n_chains), n_chains);
@@ -162,4 +179,24 @@ extern "C" int nhmc_ddim_bwd(const float* g_a, const float* g_b, const uint32_t*
     case NHMC_F16: return launch_bwd<__half>(g_a, g_b, mask, g_xt, g_eps_out, eps_chain_stride, c1, sa, c2, ss, n_chains, n_per_chain, st);
     default: set_error("nhmc_ddim_bwd: unknown eps dtype %d", eps_dtype); return NHMC_ERR_ARG;
   }
+}
+
+extern "C" int nhmc_clip_fwd(const float* z, float* zc, float* zc_copy, int64_t n, nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(z && zc && n > 0, "bad arguments");
+  int64_t blocks = (n + 255) / 256; if (blocks > kSMs * 8) blocks = kSMs * 8;
+  clip_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(z, zc, zc_copy, n);
+  return NHMC_LAUNCH_CHECK();
+}
+
+extern "C" int nhmc_clip_bwd(const void* g, int g_dtype, const float* z, float* out, int64_t n, nhmc_stream_t stream) {
+  NHMC_CHECK_ARG(g && z && out && n > 0, "bad arguments");
+  int64_t blocks = (n + 255) / 256; if (blocks > kSMs * 8) blocks = kSMs * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g_dtype) {
+    case NHMC_F32: clip_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)g, z, out, n); break;
+    case NHMC_BF16: clip_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)g, z, out, n); break;
+    case NHMC_F16: clip_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)g, z, out, n); break;
+    default: set_error("nhmc_clip_bwd: unknown dtype %d", g_dtype); return NHMC_ERR_ARG;
+  }
+  return NHMC_LAUNCH_CHECK();
 }

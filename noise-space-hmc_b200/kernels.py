@@ -276,6 +276,20 @@ def ddim_bwd(g_a, g_b, mask, g_xt, g_eps, coef):
                                   _stream()), "nhmc_ddim_bwd")
 
 
+def clip_fwd(z, zc, zc_copy=None):
+    """zc = clamp(z, -1, 1) (and a second copy), fp32."""
+    _req(z, torch.float32, "z"); _req(zc, torch.float32, "zc")
+    with _timed("clip", 1, z.numel() * 4 * (2 + (1 if zc_copy is not None else 0))):
+        check(lib().nhmc_clip_fwd(_p(z), _p(zc), _p(zc_copy), z.numel(), _stream()), "nhmc_clip_fwd")
+
+
+def clip_bwd(g, z, out):
+    """out = g * 1[-1 <= z <= 1]; g in any network dtype, out fp32."""
+    _req(g, None, "g"); _req(z, torch.float32, "z"); _req(out, torch.float32, "out")
+    with _timed("clip", 1, z.numel() * (8 + g.element_size())):
+        check(lib().nhmc_clip_bwd(_p(g), _DT[g.dtype], _p(z), _p(out), z.numel(), _stream()), "nhmc_clip_bwd")
+
+
 def accept(chains, u, mass, sched, n_slots):
     _req(u, torch.float32, "u")
     with _timed("accept", 1, chains.n * 144 * 2):

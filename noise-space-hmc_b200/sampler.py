@@ -121,16 +121,15 @@ class GradEvaluator:
     def _decode_loss_grad(self, z_hat):
         """Latent path: loss = sum (y - H(decode(clip(z_hat))))^2 (main_sampling_latent.py:651,670).
         The decoder and its VJP stay PyTorch; the latent clip mask is applied here."""
-        zc = z_hat.clamp(-1, 1)
-        self.xc.copy_(zc)
-        zv = zc.detach().requires_grad_(True)
+        zc = torch.empty_like(z_hat)
+        kernels.clip_fwd(z_hat, zc, self.xc)                           # clamp + the kept sample, one launch
+        zv = zc.requires_grad_(True)
         with torch.enable_grad():
             img = self.decode(zv)
         img_c = img.detach().float().contiguous()
         _, g_img, _ = self.op.loss_grad(img_c, self.y, loss=self.loss)
         (g_z,) = torch.autograd.grad(img, zv, g_img.to(img.dtype))
-        inr = ((z_hat >= -1) & (z_hat <= 1)).to(g_z.dtype)
-        torch.mul(g_z.float(), inr, out=self.g_hat)
+        kernels.clip_bwd(g_z.contiguous(), z_hat, self.g_hat)          # gradient mask of the clip (+ cast), one launch
         return self.g_hat
 
 
