@@ -5,7 +5,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnhmc.so")
+LIB_PATH = os.environ.get("NHMC_LIB_PATH") or os.path.join(HERE, "libnhmc.so")      # override: tuning sweeps of tools/ only
 CSRC = os.path.join(HERE, "csrc")
 
 # constants of include/nhmc.h

@@ -162,6 +162,22 @@ template <int MODE, typename T> __device__ __forceinline__ float gn_dact(float z
   return s * (1.0f + z * (1.0f - s));
 }
 
+// Tuning constants of the streaming (statistics / apply) kernels: 16-byte loads in flight per thread (one source: U1, two
+// sources: U2 per source) and the resident CTAs per SM the register allocation is held to.  Chosen by measurement
+// (profiles/r2_gn_stream_variants.md); overridable at compile time for that sweep.
+#ifndef NHMC_GN_U1
+#define NHMC_GN_U1 8
+#endif
+#ifndef NHMC_GN_U2
+#define NHMC_GN_U2 4
+#endif
+#ifndef NHMC_GN_MINB_STATS
+#define NHMC_GN_MINB_STATS 3
+#endif
+#ifndef NHMC_GN_MINB_APPLY
+#define NHMC_GN_MINB_APPLY 3
+#endif
+
 // ============================== channels-last ==============================================
 // A CTA owns `rows_per_cta` consecutive pixels of one sample = ONE contiguous byte range of the NHWC
 // tensor.  Thread t always lands on the same VEC channels (a pass of blockDim * 16 B is a whole number of
@@ -219,7 +235,7 @@ __device__ __forceinline__ SegSel seg_select(const void* x1, int c_split, int C,
 template <int NSRC, int NX, bool REV, typename Body>
 __device__ __forceinline__ void stream_rows(const RowPtr x, const RowPtr d, const RowPtr (&ex)[NX], int64_t r_begin,
                                             int64_t r_end, int prow, int rows, Body body) {
-  constexpr int U = NSRC == 2 ? 4 : 8;
+  constexpr int U = NSRC == 2 ? NHMC_GN_U2 : NHMC_GN_U1;
   const int64_t r0 = r_begin + prow;
   const int n = r_end > r0 ? (int)((r_end - r0 + rows - 1) / rows) : 0;      // rows this thread visits
   // REV: last row first (so that a re-read starts on what the previous kernel touched last).  Measured on B200: no gain
@@ -257,7 +273,7 @@ __device__ __forceinline__ void stream_rows(const RowPtr x, const RowPtr d, cons
 // PHASE 0: forward statistics (sum x, sum x^2)            -> fp64 accumulators [B][64][2]
 // PHASE 1: backward statistics (sum du, sum du*u)          -> same accumulators
 template <typename T, int MODE, int PHASE>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, NHMC_GN_MINB_STATS)
 gn_nhwc_stats_kernel(GnArgs a) {
   pdl_wait(); pdl_trigger();
   constexpr int V = VecOf<T>::N;
@@ -353,7 +369,7 @@ gn_nhwc_stats_kernel(GnArgs a) {
 
 // PHASE 0: y = act(ca*x + cb) ; PHASE 1: dx = rstd*(du - S1/n - u*S2/n)
 template <typename T, int MODE, int PHASE, bool ADD2 = false>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, NHMC_GN_MINB_APPLY)
 gn_nhwc_apply_kernel(GnArgs a) {
   pdl_wait(); pdl_trigger();
   constexpr int V = VecOf<T>::N;
