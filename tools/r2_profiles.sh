@@ -17,12 +17,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start o
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-in-situ --no-fp32-line --cuda-profiler-range > $O/r2p_ncu_bench.log 2>&1
 # ncu --set full per family
 python tools/kernel_microbench.py --only gn --shape 8,128,256 --reps 1 --resident 0 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:gn_nhwc -c 16 -o $O/r2p_gn python tools/kernel_microbench.py --only gn --shape 8,128,256 --reps 1 --resident 0 > $O/r2p_ncu_gn.log 2>&1
+ncu --set full --clock-control none -k regex:gn_nhwc -c 12 -o /tmp/r2p_gn python tools/kernel_microbench.py --only gn --shape 8,128,256 --reps 1 --resident 0 > $O/r2p_ncu_gn.log 2>&1
 python tools/kernel_microbench.py --only leapfrog --reps 1 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:leapfrog_kernel -s 9 -c 3 -o $O/r2p_leapfrog python tools/kernel_microbench.py --only leapfrog --reps 1 > $O/r2p_ncu_lf.log 2>&1
+ncu --set full --clock-control none -k regex:leapfrog_kernel -s 9 -c 3 -o /tmp/r2p_leapfrog python tools/kernel_microbench.py --only leapfrog --reps 1 > $O/r2p_ncu_lf.log 2>&1
 python tools/kernel_microbench.py --only ddim --reps 1 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:ddim_ -s 6 -c 2 -o $O/r2p_ddim python tools/kernel_microbench.py --only ddim --reps 1 > $O/r2p_ncu_ddim.log 2>&1
+ncu --set full --clock-control none -k regex:ddim_ -s 6 -c 2 -o /tmp/r2p_ddim python tools/kernel_microbench.py --only ddim --reps 1 > $O/r2p_ncu_ddim.log 2>&1
 python tools/kernel_microbench.py --only op --reps 1 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:"loss_grad|tc_gemm|phase_" -c 40 -o $O/r2p_ops python tools/kernel_microbench.py --only op --reps 1 > $O/r2p_ncu_ops.log 2>&1
-for r in gn leapfrog ddim ops; do ncu -i $O/r2p_$r.ncu-rep --page raw --csv > $O/r2p_${r}_raw.csv 2>/dev/null; done
+ncu --set full --clock-control none -k regex:"loss_grad|tc_gemm|phase_" -c 30 -o /tmp/r2p_ops python tools/kernel_microbench.py --only op --reps 1 > $O/r2p_ncu_ops.log 2>&1
+# the .ncu-rep files stay on the box (gpurun_out is capped at 64 MiB): only the raw-page CSVs travel
+for r in gn leapfrog ddim ops; do ncu -i /tmp/r2p_$r.ncu-rep --page raw --csv > $O/r2p_${r}_raw.csv 2>/dev/null; done
+du -sh $O
 ls -la $O | tail -30
