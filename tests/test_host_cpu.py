@@ -152,3 +152,19 @@ def test_cli_flag_surface_matches_reference():
     assert Hc.meas_size() == 256 * 256
     with pytest.raises(SystemExit):      # needs the un-vendored bkse weights upstream (Hfuncs.py:379,386): out of scope
         cli.prepare_measurement(types.SimpleNamespace(deg="deblur_nonlinear", sigma_0=0.05), ns, "cpu")
+
+
+def test_library_sources_keep_the_abi_contract():
+    """include/nhmc.h promises: no device allocation, no process-wide switches, no environment reads, no synchronisation
+    inside the library (SURVEY.md 8b; VERDICT r1 weak #5).  Pinned on the sources, so a regression fails here, on the CPU."""
+    import glob
+    csrc = os.path.join(ROOT, "noise-space-hmc_b200", "csrc")
+    banned = [r"\bgetenv\s*\(", r"\bcudaMalloc\w*\s*\(", r"\bcudaFree\w*\s*\(", r"\bcudaMemset\s*\(", r"\bcudaMemcpy\s*\(",
+              r"\bcudaDeviceSynchronize\s*\(", r"\bcudaStreamSynchronize\s*\(", r"^static\s+(?!const|constexpr|inline|thread_local|int\s+\w+\(|bool\s+\w+\(|size_t\s+\w+\()[\w:<> ]+\bg_\w+"]   # (the thread-local error text is the one exception)
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))):
+        src = open(path).read()
+        for pat in banned:
+            m = re.search(pat, src, flags=re.M)
+            assert m is None, "%s: %r" % (os.path.basename(path), m.group(0))
+    hdr = open(os.path.join(ROOT, "include", "nhmc.h")).read()
+    assert not re.search(r"nhmc_\w*set_\w+\s*\(", hdr), "no setters in the ABI: execution-path choices are per-call flags"
