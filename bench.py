@@ -344,9 +344,12 @@ def run_ours(args, rank, world, local_rank):
         (dname, dbytes), (dn, dms, dtot) = max(prof_sz.items(), key=lambda kv: kv[1][1])
         ach = (dtot / 1e9) / (dms / 1e3)
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")          # dram bytes per call from the committed ncu --set full capture
-        if os.path.isfile(tp):
-            traffic = json.load(open(tp)).get("%s:%d" % (dname, dbytes))
+        for tn in ("r2_traffic.json", "r1_traffic.json"):               # dram bytes per call from the committed ncu --set full capture
+            tp = os.path.join(ROOT, "profiles", tn)
+            if os.path.isfile(tp):
+                traffic = json.load(open(tp)).get("%s:%d" % (dname, dbytes))
+                if traffic is not None:
+                    break
         roofline = {"kernel": dname, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": ach / pk["hbm"], "traffic": traffic, "peak_source": pk["src"],
                     "algorithmic_bytes_per_call": int(dbytes), "calls_per_step": dn / K, "us_per_call": dms / dn * 1e3,

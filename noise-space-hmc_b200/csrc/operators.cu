@@ -196,15 +196,16 @@ sr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, f
   if (grid_finish<1>(vsum, ws.partials + (int64_t)b * kMaxBlocksPerChain, ws.tickets + b, strip, nstrips)) loss[b] = vsum[0];
 }
 
-// r in {4, 8, 16}: no shared memory, no block barrier.  A cell's row is r/4 float4 = LPC lanes; a lane keeps its float4 of
-// all r rows of the cell in registers (r independent 16-byte loads in flight), the cell sum is r adds per lane + log2(LPC)
-// shuffles, and the same lane writes the gradient (and the clamped copy) of the r x 4 pixels it loaded.  A warp covers
+// r in {4, 8, 16}: no shared memory, no block barrier.  A cell is covered by LPC = (r/4) x RS lanes: r/4 float4 across a row,
+// RS groups of r/RS = 4 rows; a lane keeps its 4 float4 in registers (independent 16-byte loads in flight), the cell sum is
+// 4 row sums per lane + log2(LPC) shuffles, and the same lane writes the gradient (and the clamped copy) of the r x 4 pixels it loaded.  A warp covers
 // 32 / LPC neighbouring cells of one cell row: every load / store instruction touches whole 128-byte lines.
-template <int R>
+template <int R, int RS>
 __global__ void __launch_bounds__(kThreads)
 sr_loss_grad_reg_kernel(const float* __restrict__ xh, const float* __restrict__ y, float* __restrict__ g,
                         float* __restrict__ xc_out, int C, int D, double* loss, RedWs ws, int nc) {
-  constexpr int LPC = R / 4;                       // lanes per cell row
+  constexpr int LPC = (R / 4) * RS;                // lanes per cell: R/4 across a row x RS groups of R/RS rows
+  constexpr int NR = R / RS;                       // rows a lane keeps in registers
   const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
   const int yd = D / R;
   const int64_t N = (int64_t)C * D * D, M = (int64_t)C * yd * yd;
@@ -216,16 +217,17 @@ sr_loss_grad_reg_kernel(const float* __restrict__ xh, const float* __restrict__ 
     const bool ok = it < n_items;                  // whole warps stay in the loop for the shuffles
     const int64_t cell = ok ? it / LPC : 0;
     const int q = (int)(it % LPC);
+    const int qc = q % (R / 4), qr = q / (R / 4);  // column float4 and row group of this lane inside the cell
     const int c = (int)(cell / ((int64_t)yd * yd));
     const int rem = (int)(cell - (int64_t)c * yd * yd);
     const int ci = rem / yd, cj = rem - ci * yd;
-    const int64_t off = ((int64_t)c * D + (int64_t)ci * R) * D + (int64_t)cj * R + q * 4;
-    float4 v[R];
+    const int64_t off = ((int64_t)c * D + (int64_t)ci * R + qr * NR) * D + (int64_t)cj * R + qc * 4;
+    float4 v[NR];
 #pragma unroll
-    for (int u = 0; u < R; ++u) v[u] = ok ? ld_ro(reinterpret_cast<const float4*>(xb + off + (int64_t)u * D)) : make_float4(0, 0, 0, 0);
+    for (int u = 0; u < NR; ++u) v[u] = ok ? ld_ro(reinterpret_cast<const float4*>(xb + off + (int64_t)u * D)) : make_float4(0, 0, 0, 0);
     float s = 0.f;
 #pragma unroll
-    for (int u = 0; u < R; ++u) {
+    for (int u = 0; u < NR; ++u) {
       float rs = clampx(v[u].x, nc) + clampx(v[u].y, nc);
       rs += clampx(v[u].z, nc); rs += clampx(v[u].w, nc);
       s += rs;
@@ -239,7 +241,7 @@ sr_loss_grad_reg_kernel(const float* __restrict__ xh, const float* __restrict__ 
       float* gd = g + (int64_t)b * N + off;
       float* cd = xc_out ? xc_out + (int64_t)b * N + off : nullptr;
 #pragma unroll
-      for (int u = 0; u < R; ++u) {
+      for (int u = 0; u < NR; ++u) {
         st_stream(reinterpret_cast<float4*>(gd + (int64_t)u * D),
                   make_float4(gv * maskx(v[u].x, nc), gv * maskx(v[u].y, nc), gv * maskx(v[u].z, nc), gv * maskx(v[u].w, nc)));
         if (cd) st_stream(reinterpret_cast<float4*>(cd + (int64_t)u * D),
@@ -258,7 +260,7 @@ sr_loss_grad_reg_kernel(const float* __restrict__ xh, const float* __restrict__ 
 // =====================================================================================
 __global__ void hdr_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
-    y[e] = clamp1(__fdiv_rn(x[e], 0.5f));
+    y[e] = clamp1(x[e] * 2.0f);   // x / 0.5 (Hfuncs.py:423) is exactly 2 x in binary floating point
 }
 __global__ void copy_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total) {
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) y[e] = x[e];
@@ -292,7 +294,7 @@ hdr_loss_grad_kernel(const float* __restrict__ xh, const float* __restrict__ y, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         cs[j] = clampx(xs[j], nc);
-        const float h = __fdiv_rn(cs[j], 0.5f);
+        const float h = cs[j] * 2.0f;      // x / 0.5 (Hfuncs.py:423) == 2 x exactly: no IEEE division sequence needed
         const float r = __fsub_rn(ys[j], clamp1(h));
         a4 += (double)r * (double)r;
         // -2 r * d clip(h)/dh * dh/dx * d clamp(x)/dx
@@ -639,11 +641,12 @@ extern "C" int nhmc_op_loss_grad(const nhmc_op* op, const float* x_hat, const fl
     case NHMC_OP_SR: {
       const int r = op->ratio;
       if ((r == 4 || r == 8 || r == 16) && D % r == 0 && aligned16(x_hat) && aligned16(g)) {
-        const int64_t items = (int64_t)C * (D / r) * (D / r) * (r / 4);
+        const int rs = r == 16 ? 4 : (r == 8 ? 2 : 1);                       // a lane keeps 4 rows: ~60 registers, full occupancy
+        const int64_t items = (int64_t)C * (D / r) * (D / r) * (r / 4) * rs;
         dim3 grid(reduce_cta_count(items, kThreads, n_chains), n_chains);
-        if (r == 4) sr_loss_grad_reg_kernel<4><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
-        else if (r == 8) sr_loss_grad_reg_kernel<8><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
-        else sr_loss_grad_reg_kernel<16><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        if (r == 4) sr_loss_grad_reg_kernel<4, 1><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        else if (r == 8) sr_loss_grad_reg_kernel<8, 2><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
+        else sr_loss_grad_reg_kernel<16, 4><<<grid, kThreads, 0, st>>>(x_hat, y, g, xc_out, C, D, loss, ws, op->no_clamp);
         break;
       }
       const int TR = sr_tile_rows(D, r);
