@@ -6,16 +6,20 @@
 // The even-length shifts only multiply X by (-1)^(u+v) (irrelevant under |.| and cancelling between F and
 // F^H), so the kernels run plain orthonormal DFTs and index y at (u + L/2, v + L/2) mod L.
 //
-// FFT: L = r * 2^k (384 = 3*128, 192 = 3*64, 160 = 5*32): one r-point DFT + twiddle stage followed by an
-// in-place radix-2 DIT on the 2^k sub-sequences, NC = 4 lines per CTA in shared memory (fp32, twiddles
-// from sincospi once per CTA).  The zero padding is exploited: only the D non-zero rows are transformed in
-// the row pass and only D output rows are produced by the inverse column pass.  Three kernels per
-// loss/gradient: rows fwd -> columns (fwd, |.|-residual, inverse, all in shared memory) -> rows inverse.
+// FFT: L = r * 2^k (384 = 3*128, 192 = 3*64, 160 = 5*32): one r-point DFT + twiddle stage, then a Stockham
+// autosort FFT of the r sub-sequences of length 2^k in radix-8 / radix-4 passes (2^7 = 8*4*4: three passes instead of the
+// seven radix-2 passes of round 1, each butterfly held in registers, no bit reversal; the last pass stores straight into
+// the interleaved output order), NC lines per CTA ping-ponging between two shared-memory buffers (fp32, twiddles from
+// sincospi once per CTA).  Rows: NC = 8 lines per CTA; columns: NC = 16, so that the strided global accesses of a column
+// block are whole 128-byte lines.  The zero padding is exploited: only the D non-zero rows are transformed in the row
+// pass and only D output rows are produced by the inverse column pass.  Three kernels per loss/gradient: rows fwd ->
+// columns (fwd, |.|-residual, inverse, all in shared memory) -> rows inverse.
 #include "common.cuh"
 
 namespace nhmc {
 
-constexpr int NC = 4;          // lines per CTA
+constexpr int NCR = 8;         // lines per CTA, row kernels
+constexpr int NCC = 16;        // lines per CTA, column kernels (16 columns x 8 B = one 128-byte line per image row)
 constexpr int kFftThreads = 256;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -28,7 +32,7 @@ static bool fft_geom(int L, FftGeom& g) {
   int n2 = 1, lg = 0;
   while (L % (n2 * 2) == 0) { n2 *= 2; ++lg; }
   g.L = L; g.N2 = n2; g.logN2 = lg; g.r = L / n2;
-  return g.r <= 15 && L >= 8 && L % NC == 0;
+  return g.r <= 15 && L >= 16 && L % NCC == 0 && lg >= 2;
 }
 
 __device__ __forceinline__ void make_twiddles(float2* tw, int L) {
@@ -39,15 +43,71 @@ __device__ __forceinline__ void make_twiddles(float2* tw, int L) {
   }
 }
 
-// In-place (buf -> buf) DFT of NC lines of length L held in shared memory. inverse: conjugate twiddles.
+// R-point DFT of v[0..R) in registers; sgn = +1 forward (e^{-i}), -1 inverse.
+template <int R>
+__device__ __forceinline__ void dft_r(float2 (&v)[R], float sgn) {
+  if (R == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  } else if (R == 4) {
+    const float2 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]), s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
+    const float2 jd = make_float2(sgn * d13.y, -sgn * d13.x);           // -i * d13 (forward), +i * d13 (inverse)
+    v[0] = cadd(s02, s13); v[2] = csub(s02, s13);
+    v[1] = cadd(d02, jd);  v[3] = csub(d02, jd);
+  } else {  // R == 8: two radix-4 on even / odd inputs + twiddles W8^k
+    float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+    dft_r<4>(e, sgn); dft_r<4>(o, sgn);
+    const float h = 0.70710678118654752f;
+    const float2 w1 = make_float2(h, -sgn * h), w2 = make_float2(0.f, -sgn), w3 = make_float2(-h, -sgn * h);
+    o[1] = cmul(o[1], w1); o[2] = cmul(o[2], w2); o[3] = cmul(o[3], w3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = cadd(e[k], o[k]); v[k + 4] = csub(e[k], o[k]); }
+  }
+}
+
+// One Stockham pass of radix R over the `nseq` sequences of length N (sequence q starts at q * N in src and dst):
+// butterfly j reads src[j + t * N/R], twiddles by W_{Ns R}^{t (j mod Ns)}, and writes dst[(j / Ns) Ns R + (j mod Ns) + t Ns].
+// LAST: the sequence index is q = line * r + k1 and the store goes to the interleaved final order line * L + k1 + r * k2.
+template <int R, bool LAST>
+__device__ __forceinline__ void stockham_pass(const float2* src, float2* dst, const float2* tw, int L, int N, int Ns, int nseq,
+                                              int r, float sgn) {
+  const int per = N / R, tstep = L / (Ns * R);
+  for (int idx = threadIdx.x; idx < nseq * per; idx += blockDim.x) {
+    const int q = idx / per, j = idx - q * per;
+    const int jm = j % Ns;
+    const float2* in = src + q * N + j;
+    float2 v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+      float2 w = tw[(t * jm) * tstep];
+      w.y *= sgn;
+      v[t] = t ? cmul(in[t * per], w) : in[0];
+    }
+    dft_r<R>(v, sgn);
+    const int j0 = (j / Ns) * Ns * R + jm;
+    if (LAST) {
+      const int line = q / r, k1 = q - line * r;
+#pragma unroll
+      for (int t = 0; t < R; ++t) dst[line * L + k1 + r * (j0 + t * Ns)] = v[t];
+    } else {
+#pragma unroll
+      for (int t = 0; t < R; ++t) dst[q * N + j0 + t * Ns] = v[t];
+    }
+  }
+  __syncthreads();
+}
+
+// DFT of NCL lines of length L held in shared memory: input in buf, result in buf (natural order).  inverse: conjugate
+// twiddles.  Uses tmp as the second ping-pong buffer.
+template <int NCL>
 __device__ void fft_lines(float2* buf, float2* tmp, const float2* tw, FftGeom g, bool inverse) {
   const int L = g.L, r = g.r, N2 = g.N2;
   const float sgn = inverse ? -1.0f : 1.0f;
-  for (int idx = threadIdx.x; idx < NC * N2; idx += blockDim.x) {
+  // stage 0: r-point DFT over the stride-N2 samples + twiddle W_L^{n2 k1}: r sequences z_{k1}[n2] per line, X[k1 + r k2] = DFT_N2(z_k1)[k2]
+  for (int idx = threadIdx.x; idx < NCL * N2; idx += blockDim.x) {
     const int line = idx / N2, n2 = idx - line * N2;
     const float2* src = buf + line * L;
     float2* dst = tmp + line * L;
-    const int rev = (int)(__brev((unsigned)n2) >> (32 - g.logN2)) & (N2 - 1);
     for (int k1 = 0; k1 < r; ++k1) {
       float2 acc = make_float2(0.f, 0.f);
       for (int n1 = 0; n1 < r; ++n1) {
@@ -57,30 +117,33 @@ __device__ void fft_lines(float2* buf, float2* tmp, const float2* tw, FftGeom g,
       }
       float2 t = tw[n2 * k1];
       t.y *= sgn;
-      dst[k1 * N2 + (g.logN2 ? rev : 0)] = cmul(acc, t);
+      dst[k1 * N2 + n2] = cmul(acc, t);
     }
   }
   __syncthreads();
-  for (int s = 1; s <= g.logN2; ++s) {
-    const int half = 1 << (s - 1), m = half << 1, tstep = L / m;
-    for (int idx = threadIdx.x; idx < NC * r * (N2 / 2); idx += blockDim.x) {
-      const int sub = idx / (N2 / 2), j = idx - sub * (N2 / 2);
-      const int grp = j / half, pos = j - grp * half;
-      const int i0 = sub * N2 + grp * m + pos, i1 = i0 + half;
-      float2 w = tw[pos * tstep];
-      w.y *= sgn;
-      const float2 t = cmul(w, tmp[i1]), u = tmp[i0];
-      tmp[i0] = cadd(u, t);
-      tmp[i1] = csub(u, t);
-    }
+  // Stockham passes on the NCL * r sequences of length N2 = 2^k: radix 8 first when k is odd, radix 4 for the rest;
+  // ping-pong tmp -> buf -> tmp ...; the last pass writes the interleaved natural order.  The pass count is chosen so
+  // that the result lands in buf: k = 7: 8,4,4 (tmp->buf->tmp->buf); k = 6: 4,4,4; k = 5: 8,4 then a copy; k = 4: 4,4 + copy.
+  const int nseq = NCL * r, k = g.logN2;
+  float2* a = tmp; float2* b = buf;
+  int Ns = 1, left = k;
+  auto swap = [&]() { float2* t_ = a; a = b; b = t_; };
+  if (left & 1) {
+    if (left == 3) { stockham_pass<8, true>(a, b, tw, L, N2, Ns, nseq, r, sgn); left = 0; }
+    else { stockham_pass<8, false>(a, b, tw, L, N2, Ns, nseq, r, sgn); Ns *= 8; left -= 3; }
+    swap();
+  }
+  while (left > 0) {
+    if (left == 2) stockham_pass<4, true>(a, b, tw, L, N2, Ns, nseq, r, sgn);
+    else stockham_pass<4, false>(a, b, tw, L, N2, Ns, nseq, r, sgn);
+    Ns *= 4; left -= 2;
+    swap();
+  }
+  // after the swaps `a` holds the result
+  if (a != buf) {
+    for (int idx = threadIdx.x; idx < NCL * L; idx += blockDim.x) buf[idx] = a[idx];
     __syncthreads();
   }
-  for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
-    const int line = idx / L, k = idx - line * L;
-    const int k1 = k % r, k2 = k / r;
-    buf[line * L + k] = tmp[line * L + k1 * N2 + k2];
-  }
-  __syncthreads();
 }
 
 struct PhaseArgs {
@@ -100,10 +163,10 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_rows_fwd_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D;
-  float2* buf = sm2; float2* tmp = buf + NC * L; float2* tw = tmp + NC * L;
-  const int mat = blockIdx.y, i0 = blockIdx.x * NC;
+  float2* buf = sm2; float2* tmp = buf + NCR * L; float2* tw = tmp + NCR * L;
+  const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
   make_twiddles(tw, L);
-  for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, c = idx - line * L, i = i0 + line, j = c - a.pad;
     float v = 0.f;
     if (i < D && j >= 0 && j < D) {
@@ -114,9 +177,9 @@ phase_rows_fwd_kernel(PhaseArgs a) {
     buf[idx] = make_float2(v, 0.f);
   }
   __syncthreads();
-  fft_lines(buf, tmp, tw, a.g, false);
+  fft_lines<NCR>(buf, tmp, tw, a.g, false);
   const float sc = rsqrtf((float)L);
-  for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, v = idx - line * L, i = i0 + line;
     if (i < D) a.rw[((int64_t)mat * D + i) * L + v] = make_float2(buf[idx].x * sc, buf[idx].y * sc);
   }
@@ -129,21 +192,21 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_cols_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D, h = L / 2;
-  float2* buf = sm2; float2* tmp = buf + NC * L; float2* tw = tmp + NC * L;
-  const int mat = blockIdx.y, v0 = blockIdx.x * NC;
+  float2* buf = sm2; float2* tmp = buf + NCC * L; float2* tw = tmp + NCC * L;
+  const int mat = blockIdx.y, v0 = blockIdx.x * NCC;
   make_twiddles(tw, L);
   const float sc = rsqrtf((float)L);
   if (MODE != 2) {
-    for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
-      const int u = idx / NC, c = idx - u * NC, i = u - a.pad;
+    for (int idx = threadIdx.x; idx < NCC * L; idx += blockDim.x) {
+      const int u = idx / NCC, c = idx - u * NCC, i = u - a.pad;
       buf[c * L + u] = (i >= 0 && i < D) ? a.rw[((int64_t)mat * D + i) * L + v0 + c] : make_float2(0.f, 0.f);
     }
     __syncthreads();
-    fft_lines(buf, tmp, tw, a.g, false);
+    fft_lines<NCC>(buf, tmp, tw, a.g, false);
   }
   double acc = 0.0;
-  for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
-    const int u = idx / NC, c = idx - u * NC, v = v0 + c;
+  for (int idx = threadIdx.x; idx < NCC * L; idx += blockDim.x) {
+    const int u = idx / NCC, c = idx - u * NCC, v = v0 + c;
     const int64_t yoff = ((int64_t)mat * L + (u + h) % L) * L + (v + h) % L;
     if (MODE == 0) {
       const float2 X = buf[c * L + u];
@@ -163,9 +226,9 @@ phase_cols_kernel(PhaseArgs a) {
   }
   if (MODE == 0) return;
   __syncthreads();
-  fft_lines(buf, tmp, tw, a.g, true);
-  for (int idx = threadIdx.x; idx < NC * D; idx += blockDim.x) {
-    const int i = idx / NC, c = idx - i * NC;
+  fft_lines<NCC>(buf, tmp, tw, a.g, true);
+  for (int idx = threadIdx.x; idx < NCC * D; idx += blockDim.x) {
+    const int i = idx / NCC, c = idx - i * NCC;
     const float2 t = buf[c * L + a.pad + i];
     a.cw[((int64_t)mat * D + i) * L + v0 + c] = make_float2(t.x * sc, t.y * sc);
   }
@@ -186,17 +249,17 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_rows_inv_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D;
-  float2* buf = sm2; float2* tmp = buf + NC * L; float2* tw = tmp + NC * L;
-  const int mat = blockIdx.y, i0 = blockIdx.x * NC;
+  float2* buf = sm2; float2* tmp = buf + NCR * L; float2* tw = tmp + NCR * L;
+  const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
   make_twiddles(tw, L);
-  for (int idx = threadIdx.x; idx < NC * L; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, v = idx - line * L, i = i0 + line;
     buf[idx] = i < D ? a.cw[((int64_t)mat * D + i) * L + v] : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  fft_lines(buf, tmp, tw, a.g, true);
+  fft_lines<NCR>(buf, tmp, tw, a.g, true);
   const float sc = rsqrtf((float)L);
-  for (int idx = threadIdx.x; idx < NC * D; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < NCR * D; idx += blockDim.x) {
     const int line = idx / D, j = idx - line * D, i = i0 + line;
     if (i >= D) continue;
     const float2 t = buf[line * L + a.pad + j];
@@ -211,12 +274,12 @@ phase_rows_inv_kernel(PhaseArgs a) {
   }
 }
 
-static size_t fft_smem(int L) { return (size_t)(2 * NC + 1) * L * sizeof(float2); }
+static size_t fft_smem(int L, int nc) { return (size_t)(2 * nc + 1) * L * sizeof(float2); }
 
 struct PhaseWs { double* partials; unsigned int* tickets; float2* rw; float2* cw; };
 static size_t phase_red_bytes(const nhmc_op* op, int n_chains) {
   const int L = op->img_dim + 2 * op->pad;
-  size_t b = (size_t)n_chains * op->channels * (L / NC + 1) * sizeof(double) + (size_t)n_chains * sizeof(unsigned int);
+  size_t b = (size_t)n_chains * op->channels * (L / NCC + 1) * sizeof(double) + (size_t)n_chains * sizeof(unsigned int);
   return (b + 255) & ~(size_t)255;
 }
 size_t phase_workspace_bytes(const nhmc_op* op, int n_chains) {
@@ -228,65 +291,67 @@ static PhaseWs phase_ws(const nhmc_op* op, int n_chains, void* extra) {
   const int L = op->img_dim + 2 * op->pad;
   PhaseWs w;
   w.partials = reinterpret_cast<double*>(extra);
-  w.tickets = reinterpret_cast<unsigned int*>(w.partials + (size_t)n_chains * op->channels * (L / NC + 1));
+  w.tickets = reinterpret_cast<unsigned int*>(w.partials + (size_t)n_chains * op->channels * (L / NCC + 1));
   w.rw = reinterpret_cast<float2*>((char*)extra + phase_red_bytes(op, n_chains));
   w.cw = w.rw + (size_t)n_chains * op->channels * op->img_dim * L;
   return w;
 }
 
-static int phase_setup(const nhmc_op* op, PhaseArgs& a, size_t& smem) {
+static int phase_setup(const nhmc_op* op, PhaseArgs& a, size_t& smem_r, size_t& smem_c) {
   const int L = op->img_dim + 2 * op->pad;
   if (!fft_geom(L, a.g)) {
     set_error("phase: padded size %d is not r*2^k with odd r <= 15", L);
     return NHMC_ERR_UNSUPPORTED;
   }
   a.D = op->img_dim; a.pad = op->pad; a.channels = op->channels; a.no_clamp = op->no_clamp;
-  smem = fft_smem(L);
-  if (smem > 200 * 1024) { set_error("phase: padded size %d too large for shared memory", L); return NHMC_ERR_UNSUPPORTED; }
-  if (smem > 48 * 1024) {
-    cudaFuncSetAttribute(phase_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(phase_cols_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(phase_cols_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(phase_cols_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(phase_rows_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(phase_rows_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  smem_r = fft_smem(L, NCR); smem_c = fft_smem(L, NCC);
+  if (smem_c > 200 * 1024) { set_error("phase: padded size %d too large for shared memory", L); return NHMC_ERR_UNSUPPORTED; }
+  if (smem_r > 48 * 1024) {
+    cudaFuncSetAttribute(phase_rows_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+    cudaFuncSetAttribute(phase_rows_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+    cudaFuncSetAttribute(phase_rows_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+  }
+  if (smem_c > 48 * 1024) {
+    cudaFuncSetAttribute(phase_cols_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(phase_cols_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+    cudaFuncSetAttribute(phase_cols_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
   }
   return NHMC_OK;
 }
 
 int phase_forward(const nhmc_op* op, const float* x, float* y, int n_chains, void* extra, cudaStream_t st) {
-  PhaseArgs a{}; size_t smem;
-  if (int e = phase_setup(op, a, smem)) return e;
+  PhaseArgs a{}; size_t smem_r, smem_c;
+  if (int e = phase_setup(op, a, smem_r, smem_c)) return e;
   const PhaseWs w = phase_ws(op, n_chains, extra);
   const int mats = n_chains * op->channels, L = a.g.L;
   a.x = x; a.out = y; a.rw = w.rw; a.no_clamp = 1;   // H() itself never clamps
-  phase_rows_fwd_kernel<<<dim3((a.D + NC - 1) / NC, mats), kFftThreads, smem, st>>>(a);
-  phase_cols_kernel<0><<<dim3(L / NC, mats), kFftThreads, smem, st>>>(a);
+  phase_rows_fwd_kernel<<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
+  phase_cols_kernel<0><<<dim3(L / NCC, mats), kFftThreads, smem_c, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
 
 int phase_pinv(const nhmc_op* op, const float* y, float* out, int n_chains, void* extra, cudaStream_t st) {
-  PhaseArgs a{}; size_t smem;
-  if (int e = phase_setup(op, a, smem)) return e;
+  PhaseArgs a{}; size_t smem_r, smem_c;
+  if (int e = phase_setup(op, a, smem_r, smem_c)) return e;
   const PhaseWs w = phase_ws(op, n_chains, extra);
   const int mats = n_chains * op->channels, L = a.g.L;
   a.y = y; a.out = out; a.cw = w.cw;
-  phase_cols_kernel<2><<<dim3(L / NC, mats), kFftThreads, smem, st>>>(a);
-  phase_rows_inv_kernel<1><<<dim3((a.D + NC - 1) / NC, mats), kFftThreads, smem, st>>>(a);
+  phase_cols_kernel<2><<<dim3(L / NCC, mats), kFftThreads, smem_c, st>>>(a);
+  phase_rows_inv_kernel<1><<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
 
 int phase_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float* g, float* xc_out, double* loss,
                     int n_chains, void* workspace, cudaStream_t st) {
-  PhaseArgs a{}; size_t smem;
-  if (int e = phase_setup(op, a, smem)) return e;
+  PhaseArgs a{}; size_t smem_r, smem_c;
+  if (int e = phase_setup(op, a, smem_r, smem_c)) return e;
   const PhaseWs w = phase_ws(op, n_chains, (char*)workspace + red_ws_aligned(n_chains));
   const int mats = n_chains * op->channels, L = a.g.L;
   a.x = x_hat; a.y = y; a.out = g; a.xc_out = xc_out; a.rw = w.rw; a.cw = w.cw;
   a.loss = loss; a.partials = w.partials; a.tickets = w.tickets;
-  phase_rows_fwd_kernel<<<dim3((a.D + NC - 1) / NC, mats), kFftThreads, smem, st>>>(a);
-  phase_cols_kernel<1><<<dim3(L / NC, mats), kFftThreads, smem, st>>>(a);
-  phase_rows_inv_kernel<0><<<dim3((a.D + NC - 1) / NC, mats), kFftThreads, smem, st>>>(a);
+  phase_rows_fwd_kernel<<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
+  phase_cols_kernel<1><<<dim3(L / NCC, mats), kFftThreads, smem_c, st>>>(a);
+  phase_rows_inv_kernel<0><<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
   return NHMC_LAUNCH_CHECK();
 }
 
