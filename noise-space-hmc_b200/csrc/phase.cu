@@ -89,6 +89,11 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst, co
       const int line = q / r, k1 = q - line * r;
 #pragma unroll
       for (int t = 0; t < R; ++t) dst[line * L + k1 + r * (j0 + t * Ns)] = v[t];
+    } else if (Ns == 1 && R >= 4) {
+      // first pass: a thread's R outputs are contiguous (j0 = j R): 16-byte stores, no bank conflicts from the R-strided scatter
+      float4* d4 = reinterpret_cast<float4*>(dst + q * N + j0);
+#pragma unroll
+      for (int t = 0; t < R; t += 2) d4[t / 2] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
     } else {
 #pragma unroll
       for (int t = 0; t < R; ++t) dst[q * N + j0 + t * Ns] = v[t];
