@@ -18,8 +18,14 @@
 
 namespace nhmc {
 
-constexpr int NCR = 8;         // lines per CTA, row kernels
-constexpr int NCC = 16;        // lines per CTA, column kernels (16 columns x 8 B = one 128-byte line per image row)
+#ifndef NHMC_PHASE_NCR
+#define NHMC_PHASE_NCR 8
+#endif
+constexpr int NCR = NHMC_PHASE_NCR;   // lines per CTA, row kernels
+#ifndef NHMC_PHASE_NCC
+#define NHMC_PHASE_NCC 16
+#endif
+constexpr int NCC = NHMC_PHASE_NCC;   // lines per CTA, column kernels (16 columns x 8 B = one 128-byte line per image row)
 constexpr int kFftThreads = 256;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -32,7 +38,7 @@ static bool fft_geom(int L, FftGeom& g) {
   int n2 = 1, lg = 0;
   while (L % (n2 * 2) == 0) { n2 *= 2; ++lg; }
   g.L = L; g.N2 = n2; g.logN2 = lg; g.r = L / n2;
-  return g.r <= 15 && L >= 16 && L % NCC == 0 && lg >= 2;
+  return (g.r == 1 || g.r == 3 || g.r == 5) && L >= 16 && L % 16 == 0 && lg >= 2;
 }
 
 __device__ __forceinline__ void make_twiddles(float2* tw, int L) {
@@ -65,17 +71,20 @@ __device__ __forceinline__ void dft_r(float2 (&v)[R], float sgn) {
   }
 }
 
-// One Stockham pass of radix R over the `nseq` sequences of length N (sequence q starts at q * N in src and dst):
+// One Stockham pass of radix R over the sequences q = line * RT + k1 (length N, based at line * LS + k1 * N in src and dst):
 // butterfly j reads src[j + t * N/R], twiddles by W_{Ns R}^{t (j mod Ns)}, and writes dst[(j / Ns) Ns R + (j mod Ns) + t Ns].
-// LAST: the sequence index is q = line * r + k1 and the store goes to the interleaved final order line * L + k1 + r * k2.
-template <int R, bool LAST>
-__device__ __forceinline__ void stockham_pass(const float2* src, float2* dst, const float2* tw, int L, int N, int Ns, int nseq,
-                                              int r, float sgn) {
-  const int per = N / R, tstep = L / (Ns * R);
+// LAST: the store goes to the interleaved final order line * LS + k1 + RT * k2.
+template <int R, bool LAST, int RT>
+__device__ __forceinline__ void stockham_pass(const float2* src, float2* dst, const float2* tw, int L, int N, int Ns, int nseq, float sgn) {
+  // N, Ns and R are powers of two: shifts and masks instead of integer divisions
+  const int LS = L + 2;
+  const int per = N / R, tstep = L / (Ns * R), lper = 31 - __clz(per), lNs = 31 - __clz(Ns);
   for (int idx = threadIdx.x; idx < nseq * per; idx += blockDim.x) {
-    const int q = idx / per, j = idx - q * per;
-    const int jm = j % Ns;
-    const float2* in = src + q * N + j;
+    const int q = idx >> lper, j = idx & (per - 1);
+    const int line = q / RT, k1 = q - line * RT;
+    const int base = line * LS + k1 * N;
+    const int jm = j & (Ns - 1);
+    const float2* in = src + base + j;
     float2 v[R];
 #pragma unroll
     for (int t = 0; t < R; ++t) {
@@ -84,71 +93,94 @@ __device__ __forceinline__ void stockham_pass(const float2* src, float2* dst, co
       v[t] = t ? cmul(in[t * per], w) : in[0];
     }
     dft_r<R>(v, sgn);
-    const int j0 = (j / Ns) * Ns * R + jm;
+    const int j0 = ((j >> lNs) << lNs) * R + jm;
     if (LAST) {
-      const int line = q / r, k1 = q - line * r;
 #pragma unroll
-      for (int t = 0; t < R; ++t) dst[line * L + k1 + r * (j0 + t * Ns)] = v[t];
+      for (int t = 0; t < R; ++t) dst[line * LS + k1 + RT * (j0 + t * Ns)] = v[t];
     } else if (Ns == 1 && R >= 4) {
       // first pass: a thread's R outputs are contiguous (j0 = j R): 16-byte stores, no bank conflicts from the R-strided scatter
-      float4* d4 = reinterpret_cast<float4*>(dst + q * N + j0);
+      float4* d4 = reinterpret_cast<float4*>(dst + base + j0);
 #pragma unroll
       for (int t = 0; t < R; t += 2) d4[t / 2] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
     } else {
 #pragma unroll
-      for (int t = 0; t < R; ++t) dst[q * N + j0 + t * Ns] = v[t];
+      for (int t = 0; t < R; ++t) dst[base + j0 + t * Ns] = v[t];
     }
   }
   __syncthreads();
 }
 
-// DFT of NCL lines of length L held in shared memory: input in buf, result in buf (natural order).  inverse: conjugate
-// twiddles.  Uses tmp as the second ping-pong buffer.
-template <int NCL>
-__device__ void fft_lines(float2* buf, float2* tmp, const float2* tw, FftGeom g, bool inverse) {
-  const int L = g.L, r = g.r, N2 = g.N2;
-  const float sgn = inverse ? -1.0f : 1.0f;
-  // stage 0: r-point DFT over the stride-N2 samples + twiddle W_L^{n2 k1}: r sequences z_{k1}[n2] per line, X[k1 + r k2] = DFT_N2(z_k1)[k2]
+// Shared-memory line stride (float2 units): L + 2 keeps 16-byte alignment and spreads the lines over the banks, so that the
+// transposing accesses of the column kernels (16 lines x one element) are 2-way instead of 16-way conflicted.
+__host__ __device__ __forceinline__ int line_stride(int L) { return L + 2; }
+
+// Stage 0 of the r * 2^k decomposition, r = RT at compile time (1, 3, 5): r-point DFT over the stride-N2 samples + twiddle
+// W_L^{n2 k1}, giving r sequences z_{k1}[n2] per line with X[k1 + r k2] = DFT_N2(z_k1)[k2].  The r-th roots of unity are read
+// once per thread; index products are reduced with compile-time moduli.
+template <int NCL, int RT>
+__device__ __forceinline__ void stage0(const float2* buf, float2* tmp, const float2* tw, int L, int N2, float sgn) {
+  const int LS = line_stride(L);
+  float2 root[RT];
+#pragma unroll
+  for (int k = 0; k < RT; ++k) { root[k] = tw[k * N2]; root[k].y *= sgn; }
+  const int lN2 = 31 - __clz(N2);
   for (int idx = threadIdx.x; idx < NCL * N2; idx += blockDim.x) {
-    const int line = idx / N2, n2 = idx - line * N2;
-    const float2* src = buf + line * L;
-    float2* dst = tmp + line * L;
-    for (int k1 = 0; k1 < r; ++k1) {
-      float2 acc = make_float2(0.f, 0.f);
-      for (int n1 = 0; n1 < r; ++n1) {
-        float2 w = tw[((n1 * k1) % r) * N2];
-        w.y *= sgn;
-        acc = cadd(acc, cmul(src[N2 * n1 + n2], w));
-      }
+    const int line = idx >> lN2, n2 = idx & (N2 - 1);
+    const float2* src = buf + line * LS;
+    float2* dst = tmp + line * LS;
+    float2 x[RT];
+#pragma unroll
+    for (int n1 = 0; n1 < RT; ++n1) x[n1] = src[N2 * n1 + n2];
+#pragma unroll
+    for (int k1 = 0; k1 < RT; ++k1) {
+      float2 acc = x[0];
+#pragma unroll
+      for (int n1 = 1; n1 < RT; ++n1) acc = cadd(acc, cmul(x[n1], root[(n1 * k1) % RT]));
       float2 t = tw[n2 * k1];
       t.y *= sgn;
-      dst[k1 * N2 + n2] = cmul(acc, t);
+      dst[k1 * N2 + n2] = k1 ? cmul(acc, t) : acc;
     }
   }
   __syncthreads();
+}
+
+// DFT of NCL lines of length L (line stride line_stride(L)) held in shared memory: input in buf, result in buf (natural
+// order).  inverse: conjugate twiddles.  Uses tmp as the second ping-pong buffer.
+template <int NCL, int RT>
+__device__ __forceinline__ void fft_lines_r(float2* buf, float2* tmp, const float2* tw, FftGeom g, float sgn) {
+  const int L = g.L, N2 = g.N2;
+  stage0<NCL, RT>(buf, tmp, tw, L, N2, sgn);
   // Stockham passes on the NCL * r sequences of length N2 = 2^k: radix 8 first when k is odd, radix 4 for the rest;
-  // ping-pong tmp -> buf -> tmp ...; the last pass writes the interleaved natural order.  The pass count is chosen so
-  // that the result lands in buf: k = 7: 8,4,4 (tmp->buf->tmp->buf); k = 6: 4,4,4; k = 5: 8,4 then a copy; k = 4: 4,4 + copy.
-  const int nseq = NCL * r, k = g.logN2;
+  // ping-pong tmp -> buf -> tmp ...; the last pass writes the interleaved natural order.
+  // k = 7: 8,4,4 (tmp->buf->tmp->buf); k = 6: 4,4,4; k = 5: 8,4 then a copy; k = 4: 4,4 + copy.
+  const int nseq = NCL * RT, k = g.logN2;
   float2* a = tmp; float2* b = buf;
   int Ns = 1, left = k;
   auto swap = [&]() { float2* t_ = a; a = b; b = t_; };
   if (left & 1) {
-    if (left == 3) { stockham_pass<8, true>(a, b, tw, L, N2, Ns, nseq, r, sgn); left = 0; }
-    else { stockham_pass<8, false>(a, b, tw, L, N2, Ns, nseq, r, sgn); Ns *= 8; left -= 3; }
+    if (left == 3) { stockham_pass<8, true, RT>(a, b, tw, L, N2, Ns, nseq, sgn); left = 0; }
+    else { stockham_pass<8, false, RT>(a, b, tw, L, N2, Ns, nseq, sgn); Ns *= 8; left -= 3; }
     swap();
   }
   while (left > 0) {
-    if (left == 2) stockham_pass<4, true>(a, b, tw, L, N2, Ns, nseq, r, sgn);
-    else stockham_pass<4, false>(a, b, tw, L, N2, Ns, nseq, r, sgn);
+    if (left == 2) stockham_pass<4, true, RT>(a, b, tw, L, N2, Ns, nseq, sgn);
+    else stockham_pass<4, false, RT>(a, b, tw, L, N2, Ns, nseq, sgn);
     Ns *= 4; left -= 2;
     swap();
   }
-  // after the swaps `a` holds the result
-  if (a != buf) {
-    for (int idx = threadIdx.x; idx < NCL * L; idx += blockDim.x) buf[idx] = a[idx];
+  if (a != buf) {   // after the swaps `a` holds the result
+    const int LS = line_stride(L);
+    for (int idx = threadIdx.x; idx < NCL * LS; idx += blockDim.x) buf[idx] = a[idx];
     __syncthreads();
   }
+}
+
+template <int NCL>
+__device__ void fft_lines(float2* buf, float2* tmp, const float2* tw, FftGeom g, bool inverse) {
+  const float sgn = inverse ? -1.0f : 1.0f;
+  if (g.r == 3) fft_lines_r<NCL, 3>(buf, tmp, tw, g, sgn);
+  else if (g.r == 5) fft_lines_r<NCL, 5>(buf, tmp, tw, g, sgn);
+  else fft_lines_r<NCL, 1>(buf, tmp, tw, g, sgn);
 }
 
 struct PhaseArgs {
@@ -168,7 +200,8 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_rows_fwd_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D;
-  float2* buf = sm2; float2* tmp = buf + NCR * L; float2* tw = tmp + NCR * L;
+  const int LS = line_stride(L);
+  float2* buf = sm2; float2* tmp = buf + NCR * LS; float2* tw = tmp + NCR * LS;
   const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
   make_twiddles(tw, L);
   for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
@@ -179,14 +212,14 @@ phase_rows_fwd_kernel(PhaseArgs a) {
       if (!a.no_clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
       if (a.xc_out) a.xc_out[((int64_t)mat * D + i) * D + j] = v;
     }
-    buf[idx] = make_float2(v, 0.f);
+    buf[line * LS + c] = make_float2(v, 0.f);
   }
   __syncthreads();
   fft_lines<NCR>(buf, tmp, tw, a.g, false);
   const float sc = rsqrtf((float)L);
   for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, v = idx - line * L, i = i0 + line;
-    if (i < D) a.rw[((int64_t)mat * D + i) * L + v] = make_float2(buf[idx].x * sc, buf[idx].y * sc);
+    if (i < D) { const float2 t = buf[line * LS + v]; a.rw[((int64_t)mat * D + i) * L + v] = make_float2(t.x * sc, t.y * sc); }
   }
 }
 
@@ -197,14 +230,15 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_cols_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D, h = L / 2;
-  float2* buf = sm2; float2* tmp = buf + NCC * L; float2* tw = tmp + NCC * L;
+  const int LS = line_stride(L);
+  float2* buf = sm2; float2* tmp = buf + NCC * LS; float2* tw = tmp + NCC * LS;
   const int mat = blockIdx.y, v0 = blockIdx.x * NCC;
   make_twiddles(tw, L);
   const float sc = rsqrtf((float)L);
   if (MODE != 2) {
     for (int idx = threadIdx.x; idx < NCC * L; idx += blockDim.x) {
       const int u = idx / NCC, c = idx - u * NCC, i = u - a.pad;
-      buf[c * L + u] = (i >= 0 && i < D) ? a.rw[((int64_t)mat * D + i) * L + v0 + c] : make_float2(0.f, 0.f);
+      buf[c * LS + u] = (i >= 0 && i < D) ? a.rw[((int64_t)mat * D + i) * L + v0 + c] : make_float2(0.f, 0.f);
     }
     __syncthreads();
     fft_lines<NCC>(buf, tmp, tw, a.g, false);
@@ -214,19 +248,19 @@ phase_cols_kernel(PhaseArgs a) {
     const int u = idx / NCC, c = idx - u * NCC, v = v0 + c;
     const int64_t yoff = ((int64_t)mat * L + (u + h) % L) * L + (v + h) % L;
     if (MODE == 0) {
-      const float2 X = buf[c * L + u];
+      const float2 X = buf[c * LS + u];
       a.out[yoff] = sqrtf(X.x * X.x + X.y * X.y) * sc;
     } else if (MODE == 1) {
-      float2 X = buf[c * L + u];
+      float2 X = buf[c * LS + u];
       X.x *= sc; X.y *= sc;
       const float mag = sqrtf(X.x * X.x + X.y * X.y);
       const float res = mag - a.y[yoff];
       acc += (double)res * (double)res;
       const float f = mag > 0.f ? res / mag : 0.f;      // d|z|/dz at 0 := 0 (torch's sgn convention)
-      buf[c * L + u] = make_float2(X.x * f, X.y * f);
+      buf[c * LS + u] = make_float2(X.x * f, X.y * f);
     } else {
       const float sg = ((u + v) & 1) ? -1.0f : 1.0f;
-      buf[c * L + u] = make_float2(a.y[yoff] * sg, 0.f);
+      buf[c * LS + u] = make_float2(a.y[yoff] * sg, 0.f);
     }
   }
   if (MODE == 0) return;
@@ -234,7 +268,7 @@ phase_cols_kernel(PhaseArgs a) {
   fft_lines<NCC>(buf, tmp, tw, a.g, true);
   for (int idx = threadIdx.x; idx < NCC * D; idx += blockDim.x) {
     const int i = idx / NCC, c = idx - i * NCC;
-    const float2 t = buf[c * L + a.pad + i];
+    const float2 t = buf[c * LS + a.pad + i];
     a.cw[((int64_t)mat * D + i) * L + v0 + c] = make_float2(t.x * sc, t.y * sc);
   }
   if (MODE == 1) {
@@ -254,12 +288,13 @@ __global__ void __launch_bounds__(kFftThreads)
 phase_rows_inv_kernel(PhaseArgs a) {
   extern __shared__ float2 sm2[];
   const int L = a.g.L, D = a.D;
-  float2* buf = sm2; float2* tmp = buf + NCR * L; float2* tw = tmp + NCR * L;
+  const int LS = line_stride(L);
+  float2* buf = sm2; float2* tmp = buf + NCR * LS; float2* tw = tmp + NCR * LS;
   const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
   make_twiddles(tw, L);
   for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, v = idx - line * L, i = i0 + line;
-    buf[idx] = i < D ? a.cw[((int64_t)mat * D + i) * L + v] : make_float2(0.f, 0.f);
+    buf[line * LS + v] = i < D ? a.cw[((int64_t)mat * D + i) * L + v] : make_float2(0.f, 0.f);
   }
   __syncthreads();
   fft_lines<NCR>(buf, tmp, tw, a.g, true);
@@ -267,7 +302,7 @@ phase_rows_inv_kernel(PhaseArgs a) {
   for (int idx = threadIdx.x; idx < NCR * D; idx += blockDim.x) {
     const int line = idx / D, j = idx - line * D, i = i0 + line;
     if (i >= D) continue;
-    const float2 t = buf[line * L + a.pad + j];
+    const float2 t = buf[line * LS + a.pad + j];
     const int64_t off = ((int64_t)mat * D + i) * D + j;
     if (MODE == 0) {
       const float xh = a.x[off];
@@ -279,7 +314,7 @@ phase_rows_inv_kernel(PhaseArgs a) {
   }
 }
 
-static size_t fft_smem(int L, int nc) { return (size_t)(2 * nc + 1) * L * sizeof(float2); }
+static size_t fft_smem(int L, int nc) { return ((size_t)2 * nc * line_stride(L) + L) * sizeof(float2); }
 
 struct PhaseWs { double* partials; unsigned int* tickets; float2* rw; float2* cw; };
 static size_t phase_red_bytes(const nhmc_op* op, int n_chains) {
