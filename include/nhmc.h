@@ -181,9 +181,9 @@ typedef struct nhmc_op {
   const float* gain_pinv;     /* deblur2d: [C,D,D] 1/D_c where non-zero else 0               */
   float coef[12];             /* color: [0..2] forward weights w_c (y = sum_c w_c x_c),      */
                               /*        [3..5] adjoint weights, [6..8] pseudo-inverse weights */
-  const float* tc_tables;     /* deblur2d / sepmat, optional: the tables nhmc_op_prepare_tables wrote (tf32 hi/lo     */
-                              /* splits of U1,V1,U2,V2 and their transposes for the tensor-core GEMMs); NULL: every   */
-                              /* call rebuilds them in its workspace                                                  */
+  const float* tc_tables;     /* optional: the derived tables nhmc_op_prepare_tables wrote -- deblur2d / sepmat: tf32  */
+                              /* hi/lo splits of U1,V1,U2,V2 and their transposes for the tensor-core GEMMs; phase:     */
+                              /* the FFT twiddle table W_L^j (float2[L]).  NULL: every call rebuilds them               */
 } nhmc_op;
 
 size_t nhmc_sizeof_op(void);

@@ -31,6 +31,8 @@ int phase_forward(const nhmc_op*, const float*, float*, int, void*, cudaStream_t
 int phase_pinv(const nhmc_op*, const float*, float*, int, void*, cudaStream_t);
 int phase_loss_grad(const nhmc_op*, const float*, const float*, float*, float*, double*, int, void*, cudaStream_t);
 size_t phase_workspace_bytes(const nhmc_op*, int);
+size_t phase_tables_bytes(const nhmc_op*);
+int phase_prepare_tables(const nhmc_op*, void*, cudaStream_t);
 
 __device__ __forceinline__ float clamp1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
 __device__ __forceinline__ float inr(float v, float lo, float hi) { return (v >= lo && v <= hi) ? 1.0f : 0.0f; }
@@ -481,13 +483,16 @@ extern "C" int64_t nhmc_op_meas_size(const nhmc_op* op) {
 }
 
 extern "C" size_t nhmc_op_tables_bytes(const nhmc_op* op) {
-  if (!op || (op->kind != NHMC_OP_DEBLUR2D && op->kind != NHMC_OP_SEPMAT)) return 0;
+  if (!op) return 0;
+  if (op->kind == NHMC_OP_PHASE) return phase_tables_bytes(op);
+  if (op->kind != NHMC_OP_DEBLUR2D && op->kind != NHMC_OP_SEPMAT) return 0;
   return spectral_tables_bytes(op);
 }
 
 extern "C" int nhmc_op_prepare_tables(const nhmc_op* op, void* tables, nhmc_stream_t stream) {
   NHMC_CHECK_ARG(op && tables && aligned16(tables), "operator and a 16-byte aligned table buffer required");
   NHMC_CHECK_ARG(nhmc_op_tables_bytes(op) > 0, "this operator has no derived tables");
+  if (op->kind == NHMC_OP_PHASE) return phase_prepare_tables(op, tables, (cudaStream_t)stream);
   return spectral_prepare_tables(op, reinterpret_cast<float*>(tables), (cudaStream_t)stream);
 }
 

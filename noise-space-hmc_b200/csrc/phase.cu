@@ -10,8 +10,8 @@
 // autosort FFT of the r sub-sequences of length 2^k in radix-8 / radix-4 passes (2^7 = 8*4*4: three passes instead of the
 // seven radix-2 passes of round 1, each butterfly held in registers, no bit reversal; the last pass stores straight into
 // the interleaved output order), NC lines per CTA ping-ponging between two shared-memory buffers (fp32, twiddles from
-// sincospi once per CTA).  Rows: NC = 8 lines per CTA; columns: NC = 16, so that the strided global accesses of a column
-// block are whole 128-byte lines.  The zero padding is exploited: only the D non-zero rows are transformed in the row
+// sincospi once per CTA).  Rows: 4 lines per CTA, columns: 8 (swept: fewer lines = more resident CTAs hiding the pass barriers wins over
+// wider global segments).  The zero padding is exploited: only the D non-zero rows are transformed in the row
 // pass and only D output rows are produced by the inverse column pass.  Three kernels per loss/gradient: rows fwd ->
 // columns (fwd, |.|-residual, inverse, all in shared memory) -> rows inverse.
 #include "common.cuh"
@@ -19,13 +19,13 @@
 namespace nhmc {
 
 #ifndef NHMC_PHASE_NCR
-#define NHMC_PHASE_NCR 8
+#define NHMC_PHASE_NCR 4
 #endif
 constexpr int NCR = NHMC_PHASE_NCR;   // lines per CTA, row kernels
 #ifndef NHMC_PHASE_NCC
-#define NHMC_PHASE_NCC 16
+#define NHMC_PHASE_NCC 8
 #endif
-constexpr int NCC = NHMC_PHASE_NCC;   // lines per CTA, column kernels (16 columns x 8 B = one 128-byte line per image row)
+constexpr int NCC = NHMC_PHASE_NCC;   // lines per CTA, column kernels (measured: 8 columns / 4 rows per CTA are the fastest, profiles/r2_stream_variants.md)
 constexpr int kFftThreads = 256;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -41,7 +41,11 @@ static bool fft_geom(int L, FftGeom& g) {
   return (g.r == 1 || g.r == 3 || g.r == 5) && L >= 16 && L % 16 == 0 && lg >= 2;
 }
 
-__device__ __forceinline__ void make_twiddles(float2* tw, int L) {
+__device__ __forceinline__ void make_twiddles(float2* tw, int L, const float2* table = nullptr) {
+  if (table) {   // prepared once by nhmc_op_prepare_tables: L2-resident 8 L bytes instead of L sincospi evaluations per CTA
+    for (int j = threadIdx.x; j < L; j += blockDim.x) tw[j] = __ldg(table + j);
+    return;
+  }
   for (int j = threadIdx.x; j < L; j += blockDim.x) {
     float s, c;
     sincospif(2.0f * (float)j / (float)L, &s, &c);
@@ -192,6 +196,7 @@ struct PhaseArgs {
   float2* cw;          // [mats][D][L] column-inverse-transformed (cropped rows)
   double* loss; double* partials; unsigned int* tickets;
   int D, pad, channels, no_clamp;
+  const float2* twg;   // prepared twiddle table W_L^j (or nullptr)
   FftGeom g;
 };
 
@@ -203,7 +208,7 @@ phase_rows_fwd_kernel(PhaseArgs a) {
   const int LS = line_stride(L);
   float2* buf = sm2; float2* tmp = buf + NCR * LS; float2* tw = tmp + NCR * LS;
   const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
-  make_twiddles(tw, L);
+  make_twiddles(tw, L, a.twg);
   for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, c = idx - line * L, i = i0 + line, j = c - a.pad;
     float v = 0.f;
@@ -233,7 +238,7 @@ phase_cols_kernel(PhaseArgs a) {
   const int LS = line_stride(L);
   float2* buf = sm2; float2* tmp = buf + NCC * LS; float2* tw = tmp + NCC * LS;
   const int mat = blockIdx.y, v0 = blockIdx.x * NCC;
-  make_twiddles(tw, L);
+  make_twiddles(tw, L, a.twg);
   const float sc = rsqrtf((float)L);
   if (MODE != 2) {
     for (int idx = threadIdx.x; idx < NCC * L; idx += blockDim.x) {
@@ -291,7 +296,7 @@ phase_rows_inv_kernel(PhaseArgs a) {
   const int LS = line_stride(L);
   float2* buf = sm2; float2* tmp = buf + NCR * LS; float2* tw = tmp + NCR * LS;
   const int mat = blockIdx.y, i0 = blockIdx.x * NCR;
-  make_twiddles(tw, L);
+  make_twiddles(tw, L, a.twg);
   for (int idx = threadIdx.x; idx < NCR * L; idx += blockDim.x) {
     const int line = idx / L, v = idx - line * L, i = i0 + line;
     buf[line * LS + v] = i < D ? a.cw[((int64_t)mat * D + i) * L + v] : make_float2(0.f, 0.f);
@@ -344,6 +349,7 @@ static int phase_setup(const nhmc_op* op, PhaseArgs& a, size_t& smem_r, size_t& 
     return NHMC_ERR_UNSUPPORTED;
   }
   a.D = op->img_dim; a.pad = op->pad; a.channels = op->channels; a.no_clamp = op->no_clamp;
+  a.twg = reinterpret_cast<const float2*>(op->tc_tables);
   smem_r = fft_smem(L, NCR); smem_c = fft_smem(L, NCC);
   if (smem_c > 200 * 1024) { set_error("phase: padded size %d too large for shared memory", L); return NHMC_ERR_UNSUPPORTED; }
   if (smem_r > 48 * 1024) {
@@ -392,6 +398,20 @@ int phase_loss_grad(const nhmc_op* op, const float* x_hat, const float* y, float
   phase_rows_fwd_kernel<<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
   phase_cols_kernel<1><<<dim3(L / NCC, mats), kFftThreads, smem_c, st>>>(a);
   phase_rows_inv_kernel<0><<<dim3((a.D + NCR - 1) / NCR, mats), kFftThreads, smem_r, st>>>(a);
+  return NHMC_LAUNCH_CHECK();
+}
+
+__global__ void phase_twiddle_kernel(float2* table, int L) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < L; j += gridDim.x * blockDim.x) {
+    float sn, cs;
+    sincospif(2.0f * (float)j / (float)L, &sn, &cs);
+    table[j] = make_float2(cs, -sn);
+  }
+}
+size_t phase_tables_bytes(const nhmc_op* op) { return (size_t)(op->img_dim + 2 * op->pad) * sizeof(float2); }
+int phase_prepare_tables(const nhmc_op* op, void* tables, cudaStream_t st) {
+  const int L = op->img_dim + 2 * op->pad;
+  phase_twiddle_kernel<<<(L + 255) / 256, 256, 0, st>>>(reinterpret_cast<float2*>(tables), L);
   return NHMC_LAUNCH_CHECK();
 }
 

@@ -58,6 +58,8 @@ class Operator:
     def _prepare_tables(self):
         """Operator-owned derived tables (the tf32 hi/lo splits of the SVD factors the tensor-core GEMMs read), built once
         by the library into a buffer this object owns; without them every call rebuilds them in its workspace."""
+        if self.device.type != "cuda":
+            return                                   # host-side construction (argument checks, table extraction): nothing to build
         nb = int(lib().nhmc_op_tables_bytes(ctypes.byref(self.desc)))
         if nb:
             self._tc_tables = torch.empty((nb + 3) // 4, dtype=torch.float32, device=self.device)
@@ -411,6 +413,7 @@ class PhaseRetrievalOperator(Operator):
         super().__init__(channels, img_dim, device)
         self.pad = int((oversample / 8.0) * 256)
         self.desc.pad = self.pad
+        self._prepare_tables()           # FFT twiddle table, built once
 
     def meas_shape(self, B):
         L = self.img_dim + 2 * self.pad
