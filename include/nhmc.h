@@ -336,6 +336,18 @@ int nhmc_softmax_fwd(int dtype, const void* logits, void* probs, float scale, in
 int nhmc_softmax_bwd(int dtype, const void* probs, const void* dprobs, void* dlogits, float scale,
                      int64_t rows, int cols, nhmc_stream_t stream);
 
+/* K10b fused attention forward for passes that keep no gradient state (the latent U-Net of hmc_latent:
+ * openaimodel.py:545-575 QKVAttentionLegacy == unet_ffhq.py:408-425): out = softmax(scale * q k^T) v per (sample, head),
+ * logits and probabilities never written to memory (tcgen05: S and O in tensor memory, P through shared memory).
+ *   qk  [batch, tokens, heads, 2, head_dim]  token-major, q then k of one head adjacent
+ *   v   [batch, heads*head_dim, tokens]      channel-major
+ *   out [batch, tokens, heads*head_dim]      token-major
+ * dtype NHMC_BF16 / NHMC_F16, head_dim 32 or 64, tokens % 8 == 0; fp32 accumulation, fp32 softmax statistics.
+ * flags: NHMC_F_NO_PDL.  Anything else returns NHMC_ERR_UNSUPPORTED (callers keep the three-kernel path). */
+int nhmc_attn_fwd(int dtype, const void* qk, const void* v, void* out, int batch, int tokens, int heads,
+                  int head_dim, float scale, unsigned int flags, nhmc_stream_t stream);
+
+
 /* ------------------------------------------------------------------------------------------
  * U-Net resampling / skip-concat epilogues, channels-last [B, H, W, C] (unet_ffhq.py:153-211 as used
  * by the up/down ResBlocks :307-316; skip concat :729-731).

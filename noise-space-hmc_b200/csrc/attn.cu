@@ -1,0 +1,303 @@
+// K10b: fused attention forward  out = softmax(scale * q k^T) v  for the score-network passes that keep no gradient
+// state (the latent U-Net of hmc_latent: three forwards per leapfrog step, no VJP; QKVAttentionLegacy,
+// ldm/modules/diffusionmodules/openaimodel.py:545-575 == guided_diffusion/unet_ffhq.py:408-425).  The unfused path
+// writes the [B*heads, T, T] logits, reads and rewrites them in the softmax kernel and reads them again in the P V
+// product: 4 passes over 235 MB per block at T = 1024 with 14 heads of 32 channels.  Here they never leave the SM.
+//
+// One CTA = 128 query rows of one (sample, head); tcgen05, warp-specialised:
+//   warp 0 (one lane)  TMA producer : Q tile once; K tiles (pass 0 and pass 1) and V tiles (pass 1) through two 2-deep rings
+//   warp 1 (one lane)  MMA issuer   : S = Q K_j^T  (M128 N128, K = head dim)     -> TMEM columns [0, 128)
+//                                     O += P_j V_j (M128 N = head dim, K = 128)  -> TMEM columns [128, 128 + head dim)
+//   warps 2-5          softmax      : thread = query row (tcgen05.ld 32x32b: no shuffles).  Pass 0 takes the row maximum
+//                                     over all key tiles; pass 1 recomputes S, p = 2^(c s - c m) <= 1 with the FINAL maximum
+//                                     (so O needs no rescaling and every exponential is evaluated once), accumulates
+//                                     l = sum p, writes P as bf16 into shared memory in the 128-byte-swizzled K-major
+//                                     layout the second MMA reads; the epilogue scales O by 1 / l.
+// Q K^T is computed twice (cheap: K = 32); the exponentials -- the actual bound of this kernel, 16 per clock per SM -- once.
+// Layouts (chosen so that every MMA operand is K-major and the producing / consuming GEMMs need no transpose):
+//   qk  [B, T, heads, 2, ch]  token-major, q then k of a head adjacent (the qkv projection's own channel order)
+//   v   [B, heads*ch, T]      channel-major
+//   out [B, T, heads*ch]      token-major
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "tc5.cuh"
+
+namespace nhmc {
+using namespace tc5;
+
+namespace {
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 192;
+constexpr int AT_QBYTES = AT_BM * 128;            // 128 rows x one 128-byte swizzle row (ch = 32: upper half zero-filled by TMA)
+constexpr int AT_KBYTES = AT_BN * 128;
+constexpr int AT_PBYTES = 2 * AT_BM * 128;        // two 64-key chunks of [128 rows][128 bytes]
+
+template <int CH> struct AttnSmem {
+  static constexpr int VCHUNK = CH * 128;         // [CH rows][64 keys] bf16
+  static constexpr int VBYTES = 2 * VCHUNK;
+  static constexpr int OFF_K = AT_QBYTES, OFF_V = OFF_K + 2 * AT_KBYTES, OFF_P = OFF_V + 2 * VBYTES, OFF_BAR = OFF_P + AT_PBYTES;
+  static constexpr int TOTAL = OFF_BAR + 256 + 1024 /* alignment slack */;
+};
+
+struct AttnArgs {
+  void* out;
+  int T, heads;
+  float c;          // scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int CH, bool BF16>
+__global__ void __launch_bounds__(AT_THREADS, CH == 32 ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  using L = AttnSmem<CH>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7;
+  uint64_t *s_full = bars + 9, *s_empty = bars + 10, *p_full = bars + 11, *p_empty = bars + 12, *o_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int nkv = (a.T + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&mapQK);
+    prefetch_tensormap(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+    mbar_init(s_full, 1); mbar_init(s_empty, 128);
+    mbar_init(p_full, 128); mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, AT_QBYTES);
+      tma_load_4d(sm, &mapQK, q_full, 0, 2 * h, q0, b);
+      for (int it = 0; it < 2 * nkv; ++it) {
+        const int j = it >= nkv ? it - nkv : it;
+        const int ks = it & 1;
+        mbar_wait(k_empty + ks, ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(k_full + ks, AT_KBYTES);
+        tma_load_4d(sm + L::OFF_K + ks * AT_KBYTES, &mapQK, k_full + ks, 0, 2 * h + 1, j * AT_BN, b);
+        if (it >= nkv) {
+          const int vs = j & 1;
+          mbar_wait(v_empty + vs, ((j >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(v_full + vs, L::VBYTES);
+          unsigned char* vd = sm + L::OFF_V + vs * L::VBYTES;
+          tma_load_3d(vd, &mapV, v_full + vs, j * AT_BN, h * CH, b);
+          tma_load_3d(vd + L::VCHUNK, &mapV, v_full + vs, j * AT_BN + 64, h * CH, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, AT_BM, AT_BN);
+      constexpr uint32_t idesc_o = umma_idesc(BF16 ? 1 : 0, AT_BM, CH);
+      const uint64_t dq = umma_desc_sw128(smem_addr(sm));
+      const uint32_t p_addr = smem_addr(sm + L::OFF_P);
+      auto pv = [&](int j) {
+        const int vs = j & 1;
+        mbar_wait(v_full + vs, (j >> 1) & 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_addr(sm + L::OFF_V + vs * L::VBYTES);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t dp = umma_desc_sw128(p_addr + half * (AT_BM * 128));
+          const uint64_t dv = umma_desc_sw128(v_addr + half * L::VCHUNK);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)                          // 16 keys = 32 bytes along the swizzled row
+            umma_f16(tmem_o, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || half > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(v_empty + vs);
+        umma_commit(p_empty);
+      };
+      mbar_wait(q_full, 0);
+      for (int it = 0; it < 2 * nkv; ++it) {
+        const int ks = it & 1;
+        mbar_wait(k_full + ks, (it >> 1) & 1);
+        mbar_wait(s_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_sw128(smem_addr(sm + L::OFF_K + ks * AT_KBYTES));
+#pragma unroll
+        for (int kk = 0; kk < CH / 16; ++kk)
+          umma_f16(tmem_s, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(k_empty + ks);
+        umma_commit(s_full);
+        if (it > nkv) pv(it - nkv - 1);                           // P V of the previous key tile, behind this tile's S
+      }
+      pv(nkv - 1);
+      umma_commit(o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const bool ragged = (a.T % AT_BN) != 0;
+    int it = 0;
+    // ---- pass 0: row maximum of the raw logits ----
+    float m = -INFINITY;
+    for (int j = 0; j < nkv; ++j, ++it) {
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      const int valid = a.T - j * AT_BN;                          // key columns of this tile that exist
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_base + (uint32_t)(g * 32), r);
+        tmem_ld_wait();
+        if (ragged && j == nkv - 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (g * 32 + i < valid) m = fmaxf(m, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+    }
+    // ---- pass 1: p = 2^(c s - c m), l = sum p, P -> shared memory (swizzled K-major), O accumulates in TMEM ----
+    const float mc = m * a.c;
+    float l = 0.f;
+    unsigned char* prow = sm + L::OFF_P + row * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < nkv; ++j, ++it) {
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      const int valid = a.T - j * AT_BN;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_base + (uint32_t)(g * 32), r);
+        tmem_ld_wait();
+        float p[32];
+        if (ragged && j == nkv - 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = g * 32 + i < valid ? ex2(fmaf(__uint_as_float(r[i]), a.c, -mc)) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = ex2(fmaf(__uint_as_float(r[i]), a.c, -mc));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) l += p[i];
+        if (g == 0) mbar_wait(p_empty, (j & 1) ^ 1);              // P V of the previous tile has read the buffer
+        unsigned char* pc = prow + (g >> 1) * (AT_BM * 128);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const int chunk = (g & 1) * 4 + c4;                     // 16-byte chunk of this row's 128 bytes
+          uint4 w;
+          w.x = pack2<BF16>(p[c4 * 8], p[c4 * 8 + 1]);
+          w.y = pack2<BF16>(p[c4 * 8 + 2], p[c4 * 8 + 3]);
+          w.z = pack2<BF16>(p[c4 * 8 + 4], p[c4 * 8 + 5]);
+          w.w = pack2<BF16>(p[c4 * 8 + 6], p[c4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(pc + ((chunk ^ sw) << 4)) = w;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(s_empty);
+      fence_proxy_async();                                        // generic-proxy stores -> visible to the MMA's async reads
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> out[b, t, h*CH + c] ----
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = __fdividef(1.0f, l);
+    const int t = q0 + row;
+    const int C = a.heads * CH;
+    unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + (((int64_t)b * a.T + t) * C + (int64_t)h * CH) * 2;
+#pragma unroll
+    for (int g = 0; g < CH / 32; ++g) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), r);
+      tmem_ld_wait();
+      if (t < a.T) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint4 w;
+          w.x = pack2<BF16>(__uint_as_float(r[c4 * 8]) * inv, __uint_as_float(r[c4 * 8 + 1]) * inv);
+          w.y = pack2<BF16>(__uint_as_float(r[c4 * 8 + 2]) * inv, __uint_as_float(r[c4 * 8 + 3]) * inv);
+          w.z = pack2<BF16>(__uint_as_float(r[c4 * 8 + 4]) * inv, __uint_as_float(r[c4 * 8 + 5]) * inv);
+          w.w = pack2<BF16>(__uint_as_float(r[c4 * 8 + 6]) * inv, __uint_as_float(r[c4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + g * 64 + c4 * 16) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+template <int CH, bool BF16>
+int attn_launch(const void* qk, const void* v, void* out, int batch, int T, int heads, float scale, unsigned flags, cudaStream_t st) {
+  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap mqk, mv;
+  {
+    const uint64_t dims[4] = {(uint64_t)CH, (uint64_t)(2 * heads), (uint64_t)T, (uint64_t)batch};
+    const uint64_t strides[3] = {(uint64_t)CH * 2, (uint64_t)heads * 2 * CH * 2, (uint64_t)T * heads * 2 * CH * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)AT_BM, 1};          // CH = 32: columns 32..63 are out of bounds -> zero
+    if (int e = make_tensor_map(&mqk, dt, 4, qk, dims, strides, box)) return e;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)T, (uint64_t)(heads * CH), (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)T * 2, (uint64_t)heads * CH * T * 2};
+    const uint32_t box[3] = {64, (uint32_t)CH, 1};
+    if (int e = make_tensor_map(&mv, dt, 3, v, dims, strides, box)) return e;
+  }
+  auto kern = attn_fwd_kernel<CH, BF16>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<CH>::TOTAL);
+  if (attr != cudaSuccess) return cuda_status(attr, "attn_fwd smem attribute");
+  AttnArgs a{out, T, heads, scale * 1.4426950408889634f};
+  const dim3 grid((T + AT_BM - 1) / AT_BM, batch * heads);
+  return cuda_status(launch_pdl(!(flags & NHMC_F_NO_PDL), kern, grid, dim3(AT_THREADS), (size_t)AttnSmem<CH>::TOTAL, st, mqk, mv, a),
+                     "attn_fwd launch");
+}
+
+}  // namespace
+}  // namespace nhmc
+
+extern "C" int nhmc_attn_fwd(int dtype, const void* qk, const void* v, void* out, int batch, int tokens, int heads, int head_dim,
+                             float scale, unsigned int flags, nhmc_stream_t stream) {
+  using namespace nhmc;
+  NHMC_CHECK_ARG(qk && v && out && batch > 0 && tokens > 0 && heads > 0, "bad arguments");
+  NHMC_CHECK_ARG(aligned16(qk) && aligned16(v) && aligned16(out), "operands must be 16-byte aligned");
+  NHMC_CHECK_ARG(tokens % 8 == 0, "tokens must be a multiple of 8 (16-byte rows of v)");
+  NHMC_CHECK_ARG((int64_t)batch * heads <= 65535, "batch * heads exceeds the grid limit");
+  if ((dtype != NHMC_BF16 && dtype != NHMC_F16) || (head_dim != 32 && head_dim != 64)) {
+    set_error("nhmc_attn_fwd: bf16 / f16 with head_dim 32 or 64 only (dtype %d, head_dim %d)", dtype, head_dim);
+    return NHMC_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == NHMC_BF16)
+    return head_dim == 32 ? attn_launch<32, true>(qk, v, out, batch, tokens, heads, scale, flags, st)
+                          : attn_launch<64, true>(qk, v, out, batch, tokens, heads, scale, flags, st);
+  return head_dim == 32 ? attn_launch<32, false>(qk, v, out, batch, tokens, heads, scale, flags, st)
+                        : attn_launch<64, false>(qk, v, out, batch, tokens, heads, scale, flags, st);
+}

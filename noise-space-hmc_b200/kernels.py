@@ -383,6 +383,25 @@ def softmax_fwd(logits, probs, scale):
               "nhmc_softmax_fwd")
 
 
+def attn_fwd_supported(dtype, tokens, head_dim):
+    """Shapes the fused attention forward (nhmc_attn_fwd) takes; everything else keeps GEMM + softmax + GEMM."""
+    return dtype in (torch.bfloat16, torch.float16) and head_dim in (32, 64) and tokens % 8 == 0
+
+
+def attn_fwd(qk, v, out, heads, scale):
+    """out[b, t, h*ch + c] = sum_s softmax_s(scale * q[b,t,h,:] . k[b,s,h,:]) v[b, h*ch + c, s]
+    qk [B, T, heads, 2, ch] (= [B, T, 2C]) token-major, v [B, C, T] channel-major, out [B, T, C] token-major."""
+    for t_, n_ in ((qk, "qk"), (v, "v"), (out, "out")):
+        _req(t_, name=n_)
+    B, T, C2 = qk.shape
+    ch = C2 // (2 * heads)
+    assert v.shape == (B, C2 // 2, T) and out.shape == (B, T, C2 // 2) and qk.dtype == v.dtype == out.dtype
+    nb = (qk.numel() + v.numel() + out.numel()) * qk.element_size()
+    with _timed("attn_fwd", 1, nb):
+        check(lib().nhmc_attn_fwd(_DT[qk.dtype], _p(qk), _p(v), _p(out), B, T, heads, ch, float(scale), _flags(), _stream()),
+              "nhmc_attn_fwd")
+
+
 def softmax_bwd(probs, dprobs, dlogits, scale):
     cols = probs.shape[-1]
     rows = probs.numel() // cols

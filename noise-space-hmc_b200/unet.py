@@ -448,13 +448,34 @@ class AttentionBlock(nn.Module):
         self.qkv = nn.Conv1d(channels, channels * 3, 1)
         self.proj_out = nn.Conv1d(channels, channels, 1)
 
+    def _fused_forward(self, tok, nh):
+        """No gradient state wanted (the latent U-Net of hmc_latent, main_sampling_latent.py:640-648 under no_grad): one
+        fused kernel instead of Q K^T -> softmax -> P V; logits and probabilities never reach memory.  The projection is
+        split so that every operand of the kernel is K-major: q, k token-major [B, T, heads, 2, ch] (the qkv weight's own
+        channel order head*(3ch) + {q, k, v}*ch + c keeps q and k of a head adjacent), v channel-major [B, C, T]."""
+        B, T, C = tok.shape
+        ch = C // nh
+        w, bias = self.qkv.weight, self.qkv.bias
+        wqk_t = _derived(self, "_wqk_t", (w,), lambda: w.detach()[:, :, 0].view(nh, 3 * ch, C)[:, :2 * ch].reshape(2 * C, C).t().contiguous())
+        wv = _derived(self, "_wv", (w,), lambda: w.detach()[:, :, 0].view(nh, 3 * ch, C)[:, 2 * ch:].reshape(C, C).contiguous())
+        bqk = _derived(self, "_bqk", (bias,), lambda: bias.detach().view(nh, 3 * ch)[:, :2 * ch].reshape(1, 1, 2 * C).contiguous())
+        bv = _derived(self, "_bv", (bias,), lambda: bias.detach().view(nh, 3 * ch)[:, 2 * ch:].reshape(1, C, 1).contiguous())
+        qk = torch.baddbmm(bqk, tok, wqk_t.unsqueeze(0).expand(B, C, 2 * C))                        # [B, T, 2C]
+        v = torch.baddbmm(bv, wv.unsqueeze(0).expand(B, C, C), tok.transpose(1, 2))                  # [B, C, T]
+        a = torch.empty_like(tok)
+        kernels.attn_fwd(qk, v, a, nh, 1.0 / math.sqrt(ch))
+        return torch.bmm(a, self.proj_out.weight[:, :, 0].t().unsqueeze(0).expand(B, C, C))         # [B, T, C]
+
     def forward(self, x):
         B, C, H, W = x.shape
         T, nh = H * W, self.num_heads
         xn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
         # Every operand is a VIEW handed to a (strided-)batched GEMM, forward and backward (_AttentionCore)
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
-        h = _AttentionCore.apply(tok, self.qkv.weight[:, :, 0], self.qkv.bias, self.proj_out.weight[:, :, 0], None, nh)
+        if not (torch.is_grad_enabled() and tok.requires_grad) and kernels.attn_fwd_supported(tok.dtype, T, C // nh) and tok.is_cuda:
+            h = self._fused_forward(tok, nh)
+        else:
+            h = _AttentionCore.apply(tok, self.qkv.weight[:, :, 0], self.qkv.bias, self.proj_out.weight[:, :, 0], None, nh)
         b32 = _derived(self, "_proj_bias_f32", (self.proj_out.bias,), lambda: self.proj_out.bias.detach().float().contiguous())
         # x + proj_out(a) (unet_ffhq.py:365): residual and proj_out's bias in ONE pass; h [B, T, C] IS channels-last [B, C, H, W]
         return _BiasAdd.apply(x, h.view(B, H, W, C).permute(0, 3, 1, 2), b32)

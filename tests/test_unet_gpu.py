@@ -82,6 +82,55 @@ def test_softmax_epilogue(dtype, rows, cols):
     assert abs(float(p.float().sum(-1).mean()) - 1.0) < 5e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,T,heads,ch", [(2, 1024, 3, 32), (1, 256, 5, 32), (3, 64, 2, 32), (2, 200, 2, 32), (1, 384, 2, 64),
+                                          (2, 1024, 1, 64), (1, 72, 3, 64)])
+def test_fused_attention_forward(dtype, B, T, heads, ch):
+    """nhmc_attn_fwd (tcgen05: S / O in tensor memory, P through shared memory) against fp32 torch attention on the
+    same rounded operands (unet_ffhq.py:408-425).  T = 200 / 72 exercise the ragged last key tile and query tile."""
+    from nhmc_b200 import kernels
+    g = torch.Generator().manual_seed(7)
+    C = heads * ch
+    qk = (torch.randn(B, T, heads, 2, ch, generator=g) * 1.5).cuda().to(dtype)
+    v = torch.randn(B, C, T, generator=g).cuda().to(dtype)
+    out = torch.full((B, T, C), float("nan"), device="cuda", dtype=dtype)
+    scale = 1 / math.sqrt(ch)
+    kernels.attn_fwd(qk.view(B, T, 2 * C), v, out, heads, scale)
+    q = qk[:, :, :, 0].float().permute(0, 2, 1, 3)                       # [B, h, T, ch]
+    k = qk[:, :, :, 1].float().permute(0, 2, 1, 3)
+    vv = v.float().view(B, heads, ch, T)
+    probs = torch.softmax(torch.einsum("bhtc,bhsc->bhts", q, k) * scale, dim=-1)
+    ref = torch.einsum("bhts,bhcs->bthc", probs, vv).reshape(B, T, C)
+    assert torch.isfinite(out.float()).all()
+    tol = 2e-2 if dtype == torch.bfloat16 else 4e-3                      # P and the output are rounded to the 8 / 11-bit type
+    np.testing.assert_allclose(out.float().cpu().numpy(), ref.cpu().numpy(), atol=tol, rtol=tol)
+
+
+def test_attention_block_fused_forward_matches_autograd_path():
+    """AttentionBlock under no_grad takes the fused kernel; with a gradient wanted it takes GEMM + softmax + GEMM.  Same
+    weights, same input: the two agree to bf16 rounding."""
+    from nhmc_b200 import unet, kernels
+    torch.manual_seed(3)
+    blk = unet.AttentionBlock(128, num_head_channels=32).cuda().to(torch.bfloat16)
+    for p_ in blk.parameters():
+        p_.data.normal_(0, 0.2)
+    x = torch.randn(2, 128, 16, 16, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    with kernels.gn_scope(kernels.GnWorkspace(x.device, 2)):
+        calls = {}
+        orig = kernels.attn_fwd
+        kernels.attn_fwd = lambda *a, **k: (calls.setdefault("n", 0), calls.__setitem__("n", calls["n"] + 1), orig(*a, **k))[-1]
+        try:
+            with torch.no_grad():
+                y_fused = blk(x)
+            assert calls["n"] == 1
+            y_ref = blk(x.clone().requires_grad_(True))
+            assert calls["n"] == 1
+        finally:
+            kernels.attn_fwd = orig
+    d = (y_fused.float() - y_ref.float()).abs().max().item()
+    assert d <= 3e-2 * max(1.0, y_ref.float().abs().max().item()), d
+
+
 def _small_model(dtype):
     from nhmc_b200 import unet
     m = unet.create_model(**SMALL, dtype=dtype)

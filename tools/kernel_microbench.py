@@ -165,6 +165,34 @@ def main():
         o2 = torch.empty_like(o1)
         report("split2", [B, C, 2 * H, 2 * H], 2 * big.numel() * 2, timeit(lambda: kernels.split2(big, o1, o2), a.reps, flush), pk)
 
+    if want("attn"):
+        # the latent U-Net's three attention shapes at 8 chains (ffhq_latent: 224 * (2, 3, 4) channels, 32 per head): the fused
+        # forward against Q K^T (cuBLAS) -> softmax kernel -> P V (cuBLAS), same operands.  Bytes = q, k, v in and out once.
+        import math
+        for (B, T, nh, ch) in ((8, 1024, 14, 32), (8, 256, 21, 32), (8, 64, 28, 32)):
+            C = nh * ch
+            qk = torch.randn(B, T, 2 * C, device=dev, dtype=torch.bfloat16)
+            v = torch.randn(B, C, T, device=dev, dtype=torch.bfloat16)
+            out = torch.empty(B, T, C, device=dev, dtype=torch.bfloat16)
+            scale = 1 / math.sqrt(ch)
+            nb = (qk.numel() + v.numel() + out.numel()) * 2
+            ms = timeit(lambda: kernels.attn_fwd(qk, v, out, nh, scale), a.reps, flush)
+            report("attn_fwd_fused", [B, T, nh, ch], nb, ms, pk)
+            exps = B * nh * T * T
+            print(json.dumps({"kernel": "attn_fwd_fused", "bound": "sfu (ex2: 16 / clk / SM)", "shape": [B, T, nh, ch], "us": round(ms * 1e3, 2),
+                              "Gexp_per_s": round(exps / 1e9 / (ms / 1e3), 1), "peak_Gexp_per_s_at_1.9GHz": round(148 * 16 * 1.9, 1),
+                              "frac": round(exps / 1e9 / (ms / 1e3) / (148 * 16 * 1.9), 3)}), flush=True)
+            qkv = torch.randn(B, 3 * C, T, device=dev, dtype=torch.bfloat16)
+            q_, k_, v_ = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)
+            probs = torch.empty(B * nh, T, T, device=dev, dtype=torch.bfloat16)
+
+            def unfused():
+                logits = torch.bmm(q_.transpose(1, 2), k_)
+                kernels.softmax_fwd(logits, probs, scale)
+                return torch.bmm(v_, probs.transpose(1, 2))
+            ms = timeit(unfused, a.reps, flush)
+            report("attn_fwd_unfused(bmm+softmax+bmm)", [B, T, nh, ch], nb, ms, pk)
+
 
 if __name__ == "__main__":
     main()
