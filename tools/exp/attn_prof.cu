@@ -1,0 +1,364 @@
+// K10b: fused attention forward  out = softmax(scale * q k^T) v  for the score-network passes that keep no gradient
+// state (the latent U-Net of hmc_latent: three forwards per leapfrog step, no VJP; QKVAttentionLegacy,
+// ldm/modules/diffusionmodules/openaimodel.py:545-575 == guided_diffusion/unet_ffhq.py:408-425).  The unfused path
+// writes the [B*heads, T, T] logits, reads and rewrites them in the softmax kernel and reads them again in the P V
+// product: 4 passes over 235 MB per block at T = 1024 with 14 heads of 32 channels.  Here they never leave the SM.
+//
+// One CTA = 128 query rows of one (sample, head); tcgen05, warp-specialised:
+//   warp 0 (one lane)  TMA producer : Q tile once; K tiles (pass 0 and pass 1) and V tiles (pass 1) through a 3- and a 2-deep ring
+//   warp 1 (one lane)  MMA issuer   : S = Q K_j^T  (M128, K = head dim) -> TMEM; pass 0: whole tiles (N128) into two slots,
+//                                     pass 1: two 64-key halves (N64) with a barrier pair each
+//                                     O += P_j V_j (M128 N = head dim, K = 128)  -> TMEM columns [128, 128 + head dim)
+//   warps 2-5          softmax      : thread = query row (tcgen05.ld 32x32b: no shuffles).  Pass 0 takes the row maximum
+//                                     over all key tiles; pass 1 recomputes S, p = 2^(c s - c m) <= 1 with the FINAL maximum
+//                                     (so O needs no rescaling and every exponential is evaluated once), accumulates
+//                                     l = sum p, writes P as bf16 into shared memory in the 128-byte-swizzled K-major
+//                                     layout the second MMA reads; the epilogue scales O by 1 / l.  A TMEM slot goes back
+//                                     to the MMA issuer as soon as its values sit in registers: the next S is produced
+//                                     while the exponentials of this one run.
+// Q K^T is computed twice (cheap: K = 32); the exponentials -- the actual bound of this kernel: MUFU.EX2 issues one warp
+// instruction per 8 clocks per scheduler, 16 results per clock per SM (ncu source page, profiles/r2_attn_ncu_summary.md) -- once.
+// Layouts (chosen so that every MMA operand is K-major and the producing / consuming GEMMs need no transpose):
+//   qk  [B, T, heads, 2, ch]  token-major, q then k of a head adjacent (the qkv projection's own channel order)
+//   v   [B, heads*ch, T]      channel-major
+//   out [B, T, heads*ch]      token-major
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "tc5.cuh"
+#define PROF_T() clock64()
+__device__ long long g_attn_prof[1024][12];
+
+
+namespace nhmc {
+using namespace tc5;
+
+namespace {
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 192;
+constexpr int AT_QBYTES = AT_BM * 128;            // 128 rows x one 128-byte swizzle row (ch = 32: upper half zero-filled by TMA)
+constexpr int AT_KBYTES = AT_BN * 128;
+constexpr int AT_PBYTES = 2 * AT_BM * 128;        // two 64-key chunks of [128 rows][128 bytes]
+#ifndef NHMC_ATTN_KSTAGES
+#define NHMC_ATTN_KSTAGES 3
+#endif
+constexpr int AT_KS = NHMC_ATTN_KSTAGES;
+
+template <int CH> struct AttnSmem {
+  static constexpr int VCHUNK = CH * 128;         // [CH rows][64 keys] bf16
+  static constexpr int VBYTES = 2 * VCHUNK;
+  static constexpr int KS = CH == 32 ? AT_KS : 2;
+  static constexpr int OFF_K = AT_QBYTES, OFF_V = OFF_K + KS * AT_KBYTES, OFF_P = OFF_V + 2 * VBYTES, OFF_BAR = OFF_P + AT_PBYTES;
+  // no alignment slack: two CTAs of the ch = 32 kernel must fit one SM (2 x (112.25 KiB + 1 KiB reserved) <= 228 KiB); the
+  // dynamic shared memory window of a kernel without static shared memory starts 1024-byte aligned, checked at run time
+  static constexpr int TOTAL = OFF_BAR + 256;
+};
+
+struct AttnArgs {
+  void* out;
+  int T, heads;
+  float c;          // scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// Barrier indices.  Pass 0 double-buffers whole 128-key S tiles in TMEM columns [0,128) / [128,256); pass 1 produces S in two
+// 64-key halves (columns [0,64) / [64,128), one barrier pair each) and accumulates O in columns [128, 128 + CH).
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 11, B_S0FULL = 13, B_S0EMPTY = 15, B_S1FULL = 17, B_S1EMPTY = 19,
+       B_PFULL = 21, B_PEMPTY = 22, B_OFULL = 23, B_COUNT = 24 };
+
+template <int CH, bool BF16>
+__global__ void __launch_bounds__(AT_THREADS, CH == 32 ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  using L = AttnSmem<CH>;
+  constexpr int KS = L::KS;
+  static_assert(KS <= 4, "barrier table holds four K stages");
+  extern __shared__ __align__(1024) unsigned char sm[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_BM;
+  const int b = blockIdx.y / a.heads, h = blockIdx.y % a.heads;
+  const int nkv = (a.T + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && lane == 0) {
+    if (smem_addr(sm) & 1023u) asm volatile("trap;");             // swizzled tiles need 1024-byte aligned bases
+    prefetch_tensormap(&mapQK);
+    prefetch_tensormap(&mapV);
+    for (int i = 0; i < B_COUNT; ++i) {                            // "empty" barriers of S and "full" of P: all 128 softmax threads arrive
+      const bool by_softmax = (i >= B_S0EMPTY && i < B_S0EMPTY + 2) || (i >= B_S1EMPTY && i < B_S1EMPTY + 2) || i == B_PFULL;
+      mbar_init(bars + i, by_softmax ? 128 : 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_o = tmem + 128;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bars + B_QFULL, AT_QBYTES);
+      tma_load_4d(sm, &mapQK, bars + B_QFULL, 0, 2 * h, q0, b);
+      for (int it = 0; it < 2 * nkv; ++it) {
+        const int j = it >= nkv ? it - nkv : it;
+        const int ks = it % KS;
+        mbar_wait(bars + B_KEMPTY + ks, ((it / KS) & 1) ^ 1);
+        mbar_arrive_expect_tx(bars + B_KFULL + ks, AT_KBYTES);
+        tma_load_4d(sm + L::OFF_K + ks * AT_KBYTES, &mapQK, bars + B_KFULL + ks, 0, 2 * h + 1, j * AT_BN, b);
+        if (it >= nkv) {
+          const int vs = j & 1;
+          mbar_wait(bars + B_VEMPTY + vs, ((j >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(bars + B_VFULL + vs, L::VBYTES);
+          unsigned char* vd = sm + L::OFF_V + vs * L::VBYTES;
+          tma_load_3d(vd, &mapV, bars + B_VFULL + vs, j * AT_BN, h * CH, b);
+          tma_load_3d(vd + L::VCHUNK, &mapV, bars + B_VFULL + vs, j * AT_BN + 64, h * CH, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s0 = umma_idesc(BF16 ? 1 : 0, AT_BM, AT_BN);
+      constexpr uint32_t idesc_s1 = umma_idesc(BF16 ? 1 : 0, AT_BM, 64);
+      constexpr uint32_t idesc_o = umma_idesc(BF16 ? 1 : 0, AT_BM, CH);
+      const uint64_t dq = umma_desc_sw128(smem_addr(sm));
+      const uint32_t p_addr = smem_addr(sm + L::OFF_P);
+      auto pv = [&](int j) {
+        const int vs = j & 1;
+        mbar_wait(bars + B_VFULL + vs, (j >> 1) & 1);
+        mbar_wait(bars + B_PFULL, j & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_addr(sm + L::OFF_V + vs * L::VBYTES);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint64_t dp = umma_desc_sw128(p_addr + half * (AT_BM * 128));
+          const uint64_t dv = umma_desc_sw128(v_addr + half * L::VCHUNK);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)                          // 16 keys = 32 bytes along the swizzled row
+            umma_f16(tmem_o, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || half > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(bars + B_VEMPTY + vs);
+        umma_commit(bars + B_PEMPTY);
+      };
+      mbar_wait(bars + B_QFULL, 0);
+      // ---- pass 0: S tiles for the row maxima, two TMEM slots ----
+      for (int j = 0; j < nkv; ++j) {
+        const int ks = j % KS, slot = j & 1;
+        mbar_wait(bars + B_KFULL + ks, (j / KS) & 1);
+        mbar_wait(bars + B_S0EMPTY + slot, ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dk = umma_desc_sw128(smem_addr(sm + L::OFF_K + ks * AT_KBYTES));
+#pragma unroll
+        for (int kk = 0; kk < CH / 16; ++kk)
+          umma_f16(tmem + slot * 128, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s0, kk > 0 ? 1u : 0u);
+        umma_commit(bars + B_KEMPTY + ks);
+        umma_commit(bars + B_S0FULL + slot);
+      }
+      // every pass-0 tile has been read (the softmax warps take them in order): pass 1 may overwrite both slots
+      mbar_wait(bars + B_S0EMPTY + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);
+      // ---- pass 1: S in 64-key halves, P V of the previous tile behind them ----
+      for (int j = 0; j < nkv; ++j) {
+        const int it = nkv + j, ks = it % KS;
+        mbar_wait(bars + B_KFULL + ks, (it / KS) & 1);
+        const uint32_t k_addr = smem_addr(sm + L::OFF_K + ks * AT_KBYTES);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(bars + B_S1EMPTY + hf, (j & 1) ^ 1);
+          tc_fence_after();
+          const uint64_t dk = umma_desc_sw128(k_addr + hf * (64 * 128));
+#pragma unroll
+          for (int kk = 0; kk < CH / 16; ++kk)
+            umma_f16(tmem + hf * 64, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s1, kk > 0 ? 1u : 0u);
+          umma_commit(bars + B_S1FULL + hf);
+        }
+        umma_commit(bars + B_KEMPTY + ks);
+        if (j > 0) pv(j - 1);
+      }
+      pv(nkv - 1);
+      umma_commit(bars + B_OFULL);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const bool ragged = (a.T % AT_BN) != 0;
+    // ---- pass 0: row maximum of the raw logits.  The slot is handed back as soon as its values are in registers ----
+    long long pw0 = 0, pl0 = 0, pw1 = 0, pl1 = 0, pwp = 0, pwo = 0, tq; const long long pstart = PROF_T();
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: 2 softmax warps per scheduler, the ILP is ours to supply
+    for (int j = 0; j < nkv; ++j) {
+      const int slot = j & 1;
+      tq = PROF_T(); mbar_wait(bars + B_S0FULL + slot, (j >> 1) & 1); pw0 += PROF_T() - tq;
+      tc_fence_after();
+      const int valid = a.T - j * AT_BN;                          // key columns of this tile that exist
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r0[32], r1[32];
+        tq = PROF_T();
+        tmem_ld32(tmem + lane_base + (uint32_t)(slot * 128 + hf * 64), r0);
+        tmem_ld32(tmem + lane_base + (uint32_t)(slot * 128 + hf * 64 + 32), r1);
+        tmem_ld_wait(); pl0 += PROF_T() - tq;
+        if (hf == 1) { tc_fence_before(); mbar_arrive(bars + B_S0EMPTY + slot); }
+        if (ragged && j == nkv - 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (hf * 64 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r0[i]));
+            if (hf * 64 + 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r1[i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        }
+      }
+    }
+    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    // ---- pass 1: p = 2^(c s - c m), l = sum p, P -> shared memory (swizzled K-major), O accumulates in TMEM ----
+    const float mc = m * a.c; const long long pmid = PROF_T();
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    unsigned char* prow = sm + L::OFF_P + row * 128;
+    const int sw = row & 7;
+    for (int j = 0; j < nkv; ++j) {
+      const int valid = a.T - j * AT_BN;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r[2][32];
+        tq = PROF_T(); mbar_wait(bars + B_S1FULL + hf, j & 1); pw1 += PROF_T() - tq;
+        tc_fence_after(); tq = PROF_T();
+        tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64), r[0]);
+        tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64 + 32), r[1]);
+        tmem_ld_wait(); pl1 += PROF_T() - tq;
+        tc_fence_before();
+        mbar_arrive(bars + B_S1EMPTY + hf);                       // this half may be refilled while the exponentials run
+        unsigned char* pc = prow + hf * (AT_BM * 128);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float p[32];
+          if (ragged && j == nkv - 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = hf * 64 + g * 32 + i < valid ? ex2(fmaf(__uint_as_float(r[g][i]), a.c, -mc)) : 0.f;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p[i] = ex2(fmaf(__uint_as_float(r[g][i]), a.c, -mc));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
+          if (hf == 0 && g == 0) { tq = PROF_T(); mbar_wait(bars + B_PEMPTY, (j & 1) ^ 1); pwp += PROF_T() - tq; }   // P V of the previous tile has read the buffer
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int chunk = g * 4 + c4;                         // 16-byte chunk of this row's 128 bytes
+            uint4 w;
+            w.x = pack2<BF16>(p[c4 * 8], p[c4 * 8 + 1]);
+            w.y = pack2<BF16>(p[c4 * 8 + 2], p[c4 * 8 + 3]);
+            w.z = pack2<BF16>(p[c4 * 8 + 4], p[c4 * 8 + 5]);
+            w.w = pack2<BF16>(p[c4 * 8 + 6], p[c4 * 8 + 7]);
+            *reinterpret_cast<uint4*>(pc + ((chunk ^ sw) << 4)) = w;
+          }
+        }
+      }
+      fence_proxy_async();                                        // generic-proxy stores -> visible to the MMA's async reads
+      mbar_arrive(bars + B_PFULL);
+    }
+    // ---- epilogue: O / l -> out[b, t, h*CH + c] ----
+    const long long pend1 = PROF_T(); mbar_wait(bars + B_OFULL, 0); pwo = PROF_T() - pend1;
+    tc_fence_after();
+    const float inv = __fdividef(1.0f, (l4[0] + l4[1]) + (l4[2] + l4[3]));
+    const int t = q0 + row;
+    const int C = a.heads * CH;
+    unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + (((int64_t)b * a.T + t) * C + (int64_t)h * CH) * 2;
+#pragma unroll
+    for (int g = 0; g < CH / 32; ++g) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), r);
+      tmem_ld_wait();
+      if (t < a.T) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          uint4 w;
+          w.x = pack2<BF16>(__uint_as_float(r[c4 * 8]) * inv, __uint_as_float(r[c4 * 8 + 1]) * inv);
+          w.y = pack2<BF16>(__uint_as_float(r[c4 * 8 + 2]) * inv, __uint_as_float(r[c4 * 8 + 3]) * inv);
+          w.z = pack2<BF16>(__uint_as_float(r[c4 * 8 + 4]) * inv, __uint_as_float(r[c4 * 8 + 5]) * inv);
+          w.w = pack2<BF16>(__uint_as_float(r[c4 * 8 + 6]) * inv, __uint_as_float(r[c4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + g * 64 + c4 * 16) = w;
+        }
+      }
+    }
+    if (threadIdx.x == 64) {
+      const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+      if (cta < 1024) {
+        long long* o = g_attn_prof[cta];
+        o[0] = PROF_T() - pstart; o[1] = pmid - pstart; o[2] = pend1 - pmid; o[3] = pw0; o[4] = pl0; o[5] = pw1; o[6] = pl1; o[7] = pwp; o[8] = pwo;
+        unsigned smid; asm("mov.u32 %0, %%smid;" : "=r"(smid)); o[9] = smid; o[10] = pstart;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }
+}
+
+template <int CH, bool BF16>
+int attn_launch(const void* qk, const void* v, void* out, int batch, int T, int heads, float scale, unsigned flags, cudaStream_t st) {
+  const CUtensorMapDataType dt = BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap mqk, mv;
+  {
+    const uint64_t dims[4] = {(uint64_t)CH, (uint64_t)(2 * heads), (uint64_t)T, (uint64_t)batch};
+    const uint64_t strides[3] = {(uint64_t)CH * 2, (uint64_t)heads * 2 * CH * 2, (uint64_t)T * heads * 2 * CH * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)AT_BM, 1};          // CH = 32: columns 32..63 are out of bounds -> zero
+    if (int e = make_tensor_map(&mqk, dt, 4, qk, dims, strides, box)) return e;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)T, (uint64_t)(heads * CH), (uint64_t)batch};
+    const uint64_t strides[2] = {(uint64_t)T * 2, (uint64_t)heads * CH * T * 2};
+    const uint32_t box[3] = {64, (uint32_t)CH, 1};
+    if (int e = make_tensor_map(&mv, dt, 3, v, dims, strides, box)) return e;
+  }
+  auto kern = attn_fwd_kernel<CH, BF16>;
+  static const cudaError_t attr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<CH>::TOTAL);
+  if (attr != cudaSuccess) return cuda_status(attr, "attn_fwd smem attribute");
+  AttnArgs a{out, T, heads, scale * 1.4426950408889634f};
+  const dim3 grid((T + AT_BM - 1) / AT_BM, batch * heads);
+  return cuda_status(launch_pdl(!(flags & NHMC_F_NO_PDL), kern, grid, dim3(AT_THREADS), (size_t)AttnSmem<CH>::TOTAL, st, mqk, mv, a),
+                     "attn_fwd launch");
+}
+
+}  // namespace
+}  // namespace nhmc
+
+extern "C" int nhmc_attn_prof_dump(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, g_attn_prof, sizeof(g_attn_prof));
+}
+
+extern "C" int nhmc_attn_fwd(int dtype, const void* qk, const void* v, void* out, int batch, int tokens, int heads, int head_dim,
+                             float scale, unsigned int flags, nhmc_stream_t stream) {
+  using namespace nhmc;
+  NHMC_CHECK_ARG(qk && v && out && batch > 0 && tokens > 0 && heads > 0, "bad arguments");
+  NHMC_CHECK_ARG(aligned16(qk) && aligned16(v) && aligned16(out), "operands must be 16-byte aligned");
+  NHMC_CHECK_ARG(tokens % 8 == 0, "tokens must be a multiple of 8 (16-byte rows of v)");
+  NHMC_CHECK_ARG((int64_t)batch * heads <= 65535, "batch * heads exceeds the grid limit");
+  if ((dtype != NHMC_BF16 && dtype != NHMC_F16) || (head_dim != 32 && head_dim != 64)) {
+    set_error("nhmc_attn_fwd: bf16 / f16 with head_dim 32 or 64 only (dtype %d, head_dim %d)", dtype, head_dim);
+    return NHMC_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == NHMC_BF16)
+    return head_dim == 32 ? attn_launch<32, true>(qk, v, out, batch, tokens, heads, scale, flags, st)
+                          : attn_launch<64, true>(qk, v, out, batch, tokens, heads, scale, flags, st);
+  return head_dim == 32 ? attn_launch<32, false>(qk, v, out, batch, tokens, heads, scale, flags, st)
+                        : attn_launch<64, false>(qk, v, out, batch, tokens, heads, scale, flags, st);
+}

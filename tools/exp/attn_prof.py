@@ -1,0 +1,30 @@
+"""Per-phase cycle counts of the fused attention kernel (instrumented copy tools/exp/attn_prof.cu, built into
+tools/exp/libvar/libnhmc_attnprof.so): where a softmax warp's time goes.  NHMC_LIB_PATH=<that lib> python tools/exp/attn_prof.py"""
+import ctypes as C, math, os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import nhmc_b200
+from nhmc_b200 import kernels, _lib
+
+B, T, nh, ch = 8, 1024, 14, 32
+Cc = nh * ch
+dev = torch.device("cuda")
+qk = torch.randn(B, T, 2 * Cc, device=dev, dtype=torch.bfloat16)
+v = torch.randn(B, Cc, T, device=dev, dtype=torch.bfloat16)
+out = torch.empty(B, T, Cc, device=dev, dtype=torch.bfloat16)
+for _ in range(3):
+    kernels.attn_fwd(qk, v, out, nh, 1 / math.sqrt(ch))
+torch.cuda.synchronize()
+lib = _lib.lib()
+host = np.zeros((1024, 12), dtype=np.int64)
+lib.nhmc_attn_prof_dump.argtypes = [C.c_void_p]
+lib.nhmc_attn_prof_dump(host.ctypes.data)
+names = ["total", "pass0", "pass1", "wait_s0full", "ld_pass0", "wait_s1full", "ld_pass1", "wait_pempty", "wait_ofull", "smid", "start"]
+h = host[:896]
+t0 = h[:, 10].min()
+order = np.argsort(h[:, 10])
+print("CTAs by start time: first 4, middle 4, last 4 (cycles)")
+for idx in list(order[:4]) + list(order[444:448]) + list(order[-4:]):
+    print({n: int(h[idx, i]) if n != "start" else int(h[idx, i] - t0) for i, n in enumerate(names)})
+print("mean over CTAs:", {n: float(h[:, i].mean()) for i, n in enumerate(names[:9])})
