@@ -5,19 +5,19 @@
 // product: 4 passes over 235 MB per block at T = 1024 with 14 heads of 32 channels.  Here they never leave the SM.
 //
 // One CTA = 128 query rows of one (sample, head); tcgen05, warp-specialised:
-//   warp 0 (one lane)  TMA producer : Q tile once; K tiles (pass 0 and pass 1) and V tiles (pass 1) through a 3- and a 2-deep ring
-//   warp 1 (one lane)  MMA issuer   : S = Q K_j^T  (M128, K = head dim) -> TMEM; pass 0: whole tiles (N128) into two slots,
-//                                     pass 1: two 64-key halves (N64) with a barrier pair each
-//                                     O += P_j V_j (M128 N = head dim, K = 128)  -> TMEM columns [128, 128 + head dim)
-//   warps 2-5          softmax      : thread = query row (tcgen05.ld 32x32b: no shuffles).  Pass 0 takes the row maximum
-//                                     over all key tiles; pass 1 recomputes S, p = 2^(c s - c m) <= 1 with the FINAL maximum
-//                                     (so O needs no rescaling and every exponential is evaluated once), accumulates
-//                                     l = sum p, writes P as bf16 into shared memory in the 128-byte-swizzled K-major
-//                                     layout the second MMA reads; the epilogue scales O by 1 / l.  A TMEM slot goes back
-//                                     to the MMA issuer as soon as its values sit in registers: the next S is produced
-//                                     while the exponentials of this one run.
-// Q K^T is computed twice (cheap: K = 32); the exponentials -- the actual bound of this kernel: MUFU.EX2 issues one warp
-// instruction per 8 clocks per scheduler, 16 results per clock per SM (ncu source page, profiles/r2_attn_ncu_summary.md) -- once.
+//   warp 0 (one lane)  TMA producer : Q tile once; K tiles through a 3-deep, V tiles through a 2-deep ring
+//   warp 1 (one lane)  MMA issuer   : S = Q K_j^T in two 64-key halves (M128 N64, K = head dim) -> TMEM columns [0,64) / [64,128)
+//                                     O += P V per half (M128 N = head dim, K = 64)            -> TMEM columns [128, 128 + head dim)
+//   warps 2-5          softmax      : thread = query row (tcgen05.ld 32x32b: no shuffles).  ONE pass over the keys with a
+//                                     running maximum: p = 2^(c s - c m_used) where m_used follows the true maximum lazily --
+//                                     only when that has grown by more than 2^8 are O (tcgen05.ld -> scale -> tcgen05.st) and
+//                                     l = sum p rescaled, a warp-uniform and rare event -- so every exponential is evaluated
+//                                     once and Q K^T is computed once.  P goes as bf16 into shared memory in the
+//                                     128-byte-swizzled K-major layout the second MMA reads; the epilogue scales O by 1 / l.
+//                                     A TMEM half goes back to the MMA issuer as soon as its values sit in registers: the
+//                                     next S is produced while the exponentials of this one run.
+// The exponentials are the bound of this kernel: MUFU.EX2 issues one warp instruction per 8 clocks per scheduler, 16 results
+// per clock per SM (tools/exp/exp_mufu.cu, profiles/r2_attn_ncu_summary.md).
 // Layouts (chosen so that every MMA operand is K-major and the producing / consuming GEMMs need no transpose):
 //   qk  [B, T, heads, 2, ch]  token-major, q then k of a head adjacent (the qkv projection's own channel order)
 //   v   [B, heads*ch, T]      channel-major
@@ -71,10 +71,12 @@ template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b)
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// Barrier indices.  Pass 0 double-buffers whole 128-key S tiles in TMEM columns [0,128) / [128,256); pass 1 produces S in two
-// 64-key halves (columns [0,64) / [64,128), one barrier pair each) and accumulates O in columns [128, 128 + CH).
-enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 11, B_S0FULL = 13, B_S0EMPTY = 15, B_S1FULL = 17, B_S1EMPTY = 19,
-       B_PFULL = 21, B_PEMPTY = 22, B_OFULL = 23, B_COUNT = 24 };
+// Barrier indices.  S is produced in 64-key halves (TMEM columns [0,64) / [64,128)), each with its own full / empty pair; P has
+// one 64-key shared-memory chunk per half with a full barrier (softmax -> MMA) and a "P V done" barrier (MMA commit -> softmax);
+// O accumulates in TMEM columns [128, 128 + CH).
+enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 11, B_SFULL = 13, B_SEMPTY = 15, B_PFULL = 17, B_PVDONE = 19,
+       B_OFULL = 21, B_COUNT = 22 };
+constexpr float AT_RESCALE_LOG2 = 8.0f;   // O and l are rescaled only when a row maximum grew by more than 2^8: p <= 256 in between
 
 template <int CH, bool BF16>
 __global__ void __launch_bounds__(AT_THREADS, CH == 32 ? 2 : 1)
@@ -95,8 +97,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     if (smem_addr(sm) & 1023u) asm volatile("trap;");             // swizzled tiles need 1024-byte aligned bases
     prefetch_tensormap(&mapQK);
     prefetch_tensormap(&mapV);
-    for (int i = 0; i < B_COUNT; ++i) {                            // "empty" barriers of S and "full" of P: all 128 softmax threads arrive
-      const bool by_softmax = (i >= B_S0EMPTY && i < B_S0EMPTY + 2) || (i >= B_S1EMPTY && i < B_S1EMPTY + 2) || i == B_PFULL;
+    for (int i = 0; i < B_COUNT; ++i) {                            // S "empty" and P "full": all 128 softmax threads arrive
+      const bool by_softmax = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2);
       mbar_init(bars + i, by_softmax ? 128 : 1);
     }
     fence_barrier_init();
@@ -114,81 +116,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     if (lane == 0) {
       mbar_arrive_expect_tx(bars + B_QFULL, AT_QBYTES);
       tma_load_4d(sm, &mapQK, bars + B_QFULL, 0, 2 * h, q0, b);
-      for (int it = 0; it < 2 * nkv; ++it) {
-        const int j = it >= nkv ? it - nkv : it;
-        const int ks = it % KS;
-        mbar_wait(bars + B_KEMPTY + ks, ((it / KS) & 1) ^ 1);
+      for (int j = 0; j < nkv; ++j) {
+        const int ks = j % KS, vs = j & 1;
+        mbar_wait(bars + B_KEMPTY + ks, ((j / KS) & 1) ^ 1);
         mbar_arrive_expect_tx(bars + B_KFULL + ks, AT_KBYTES);
         tma_load_4d(sm + L::OFF_K + ks * AT_KBYTES, &mapQK, bars + B_KFULL + ks, 0, 2 * h + 1, j * AT_BN, b);
-        if (it >= nkv) {
-          const int vs = j & 1;
-          mbar_wait(bars + B_VEMPTY + vs, ((j >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(bars + B_VFULL + vs, L::VBYTES);
-          unsigned char* vd = sm + L::OFF_V + vs * L::VBYTES;
-          tma_load_3d(vd, &mapV, bars + B_VFULL + vs, j * AT_BN, h * CH, b);
-          tma_load_3d(vd + L::VCHUNK, &mapV, bars + B_VFULL + vs, j * AT_BN + 64, h * CH, b);
-        }
+        mbar_wait(bars + B_VEMPTY + vs, ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(bars + B_VFULL + vs, L::VBYTES);
+        unsigned char* vd = sm + L::OFF_V + vs * L::VBYTES;
+        tma_load_3d(vd, &mapV, bars + B_VFULL + vs, j * AT_BN, h * CH, b);
+        tma_load_3d(vd + L::VCHUNK, &mapV, bars + B_VFULL + vs, j * AT_BN + 64, h * CH, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s0 = umma_idesc(BF16 ? 1 : 0, AT_BM, AT_BN);
-      constexpr uint32_t idesc_s1 = umma_idesc(BF16 ? 1 : 0, AT_BM, 64);
+      constexpr uint32_t idesc_s = umma_idesc(BF16 ? 1 : 0, AT_BM, 64);
       constexpr uint32_t idesc_o = umma_idesc(BF16 ? 1 : 0, AT_BM, CH);
       const uint64_t dq = umma_desc_sw128(smem_addr(sm));
       const uint32_t p_addr = smem_addr(sm + L::OFF_P);
-      auto pv = [&](int j) {
+      // O += P(j, hf) V(j, hf): 64 keys = four K16 slices
+      auto pv = [&](int j, int hf) {
         const int vs = j & 1;
-        mbar_wait(bars + B_VFULL + vs, (j >> 1) & 1);
-        mbar_wait(bars + B_PFULL, j & 1);
+        if (hf == 0) mbar_wait(bars + B_VFULL + vs, (j >> 1) & 1);
+        mbar_wait(bars + B_PFULL + hf, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_addr(sm + L::OFF_V + vs * L::VBYTES);
+        const uint64_t dp = umma_desc_sw128(p_addr + hf * (AT_BM * 128));
+        const uint64_t dv = umma_desc_sw128(smem_addr(sm + L::OFF_V + vs * L::VBYTES) + hf * L::VCHUNK);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint64_t dp = umma_desc_sw128(p_addr + half * (AT_BM * 128));
-          const uint64_t dv = umma_desc_sw128(v_addr + half * L::VCHUNK);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)                          // 16 keys = 32 bytes along the swizzled row
-            umma_f16(tmem_o, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || half > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(bars + B_VEMPTY + vs);
-        umma_commit(bars + B_PEMPTY);
+        for (int kk = 0; kk < 4; ++kk)                            // 16 keys = 32 bytes along the swizzled row
+          umma_f16(tmem_o, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || hf > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(bars + B_PVDONE + hf);
+        if (hf == 1) umma_commit(bars + B_VEMPTY + vs);
       };
       mbar_wait(bars + B_QFULL, 0);
-      // ---- pass 0: S tiles for the row maxima, two TMEM slots ----
+      // issue order = the order in which the softmax warps free / fill things: S(j, lo), P V(j-1, lo), S(j, hi), P V(j-1, hi)
       for (int j = 0; j < nkv; ++j) {
-        const int ks = j % KS, slot = j & 1;
+        const int ks = j % KS;
         mbar_wait(bars + B_KFULL + ks, (j / KS) & 1);
-        mbar_wait(bars + B_S0EMPTY + slot, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint64_t dk = umma_desc_sw128(smem_addr(sm + L::OFF_K + ks * AT_KBYTES));
-#pragma unroll
-        for (int kk = 0; kk < CH / 16; ++kk)
-          umma_f16(tmem + slot * 128, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s0, kk > 0 ? 1u : 0u);
-        umma_commit(bars + B_KEMPTY + ks);
-        umma_commit(bars + B_S0FULL + slot);
-      }
-      // every pass-0 tile has been read (the softmax warps take them in order): pass 1 may overwrite both slots
-      mbar_wait(bars + B_S0EMPTY + ((nkv - 1) & 1), ((nkv - 1) >> 1) & 1);
-      // ---- pass 1: S in 64-key halves, P V of the previous tile behind them ----
-      for (int j = 0; j < nkv; ++j) {
-        const int it = nkv + j, ks = it % KS;
-        mbar_wait(bars + B_KFULL + ks, (it / KS) & 1);
         const uint32_t k_addr = smem_addr(sm + L::OFF_K + ks * AT_KBYTES);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
-          mbar_wait(bars + B_S1EMPTY + hf, (j & 1) ^ 1);
+          mbar_wait(bars + B_SEMPTY + hf, (j & 1) ^ 1);
           tc_fence_after();
           const uint64_t dk = umma_desc_sw128(k_addr + hf * (64 * 128));
 #pragma unroll
           for (int kk = 0; kk < CH / 16; ++kk)
-            umma_f16(tmem + hf * 64, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s1, kk > 0 ? 1u : 0u);
-          umma_commit(bars + B_S1FULL + hf);
+            umma_f16(tmem + hf * 64, dq + (uint64_t)(kk * 2), dk + (uint64_t)(kk * 2), idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(bars + B_SFULL + hf);
+          if (hf == 1) umma_commit(bars + B_KEMPTY + ks);
+          if (j > 0) pv(j - 1, hf);
         }
-        umma_commit(bars + B_KEMPTY + ks);
-        if (j > 0) pv(j - 1);
       }
-      pv(nkv - 1);
+      pv(nkv - 1, 0);
+      pv(nkv - 1, 1);
       umma_commit(bars + B_OFULL);
     }
   } else {
@@ -196,55 +176,69 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const bool ragged = (a.T % AT_BN) != 0;
-    // ---- pass 0: row maximum of the raw logits.  The slot is handed back as soon as its values are in registers ----
-    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains: 2 softmax warps per scheduler, the ILP is ours to supply
-    for (int j = 0; j < nkv; ++j) {
-      const int slot = j & 1;
-      mbar_wait(bars + B_S0FULL + slot, (j >> 1) & 1);
-      tc_fence_after();
-      const int valid = a.T - j * AT_BN;                          // key columns of this tile that exist
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(tmem + lane_base + (uint32_t)(slot * 128 + hf * 64), r0);
-        tmem_ld32(tmem + lane_base + (uint32_t)(slot * 128 + hf * 64 + 32), r1);
-        tmem_ld_wait();
-        if (hf == 1) { tc_fence_before(); mbar_arrive(bars + B_S0EMPTY + slot); }
-        if (ragged && j == nkv - 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (hf * 64 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r0[i]));
-            if (hf * 64 + 32 + i < valid) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(r1[i]));
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-        }
-      }
-    }
-    const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-    // ---- pass 1: p = 2^(c s - c m), l = sum p, P -> shared memory (swizzled K-major), O accumulates in TMEM ----
-    const float mc = m * a.c;
+    // One pass over the keys with a running maximum.  m_used is the maximum the stored exponentials refer to: it follows the
+    // true running maximum lazily (only when that has grown by more than 2^AT_RESCALE_LOG2), and then O (tensor memory) and l
+    // are rescaled -- a warp-uniform, rare event (the first units of a row).  Thread = row: no cross-thread state.
+    float m_used = -INFINITY;
     float l4[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned char* prow = sm + L::OFF_P + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < nkv; ++j) {
-      const int valid = a.T - j * AT_BN;
+      const int valid = a.T - j * AT_BN;                          // key columns of this tile that exist
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t r[2][32];
-        mbar_wait(bars + B_S1FULL + hf, j & 1);
+        mbar_wait(bars + B_SFULL + hf, j & 1);
         tc_fence_after();
         tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64), r[0]);
         tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64 + 32), r[1]);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(bars + B_S1EMPTY + hf);                       // this half may be refilled while the exponentials run
+        mbar_arrive(bars + B_SEMPTY + hf);                        // this half may be refilled while the exponentials run
+        const bool mask = ragged && j == nkv - 1;
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (hf * 64 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[0][i]));
+            if (hf * 64 + 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[1][i]));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(r[0][i]), __uint_as_float(r[1][i])));
+        }
+        const float m_new = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), m_used);
+        const bool first = (j == 0 && hf == 0);
+        const bool grow = (m_new - m_used) * a.c > AT_RESCALE_LOG2;       // also true from -inf (first unit)
+        if (first) {
+          m_used = m_new;                                          // nothing accumulated yet
+        } else if (__any_sync(0xffffffffu, grow)) {
+          // every P V issued so far must have landed in O: the last one is that of the previous unit
+          if (hf == 1) mbar_wait(bars + B_PVDONE + 0, j & 1); else mbar_wait(bars + B_PVDONE + 1, (j - 1) & 1);
+          tc_fence_after();
+          const float f = grow ? ex2((m_used - m_new) * a.c) : 1.0f;     // m_used = -inf -> 0 (a row whose keys so far were all masked)
+          if (grow) m_used = m_new;
+#pragma unroll
+          for (int g = 0; g < CH / 32; ++g) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(tmem_o + lane_base + (uint32_t)(g * 32), o);
+          }
+          tmem_st_wait();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) l4[i] *= f;
+        }
+        const float mc = m_used * a.c;
+        // the P V that read this chunk last (previous tile, same half) must be done before it is overwritten
+        if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);
         unsigned char* pc = prow + hf * (AT_BM * 128);
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           float p[32];
-          if (ragged && j == nkv - 1) {
+          if (mask) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) p[i] = hf * 64 + g * 32 + i < valid ? ex2(fmaf(__uint_as_float(r[g][i]), a.c, -mc)) : 0.f;
           } else {
@@ -253,7 +247,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
-          if (hf == 0 && g == 0) mbar_wait(bars + B_PEMPTY, (j & 1) ^ 1);   // P V of the previous tile has read the buffer
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
             const int chunk = g * 4 + c4;                         // 16-byte chunk of this row's 128 bytes
@@ -265,9 +258,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
             *reinterpret_cast<uint4*>(pc + ((chunk ^ sw) << 4)) = w;
           }
         }
+        tc_fence_before();                                        // orders a rescale's tcgen05.st before the MMA that follows the arrive
+        fence_proxy_async();                                      // generic-proxy stores -> visible to the MMA's async reads
+        mbar_arrive(bars + B_PFULL + hf);
       }
-      fence_proxy_async();                                        // generic-proxy stores -> visible to the MMA's async reads
-      mbar_arrive(bars + B_PFULL);
     }
     // ---- epilogue: O / l -> out[b, t, h*CH + c] ----
     mbar_wait(bars + B_OFULL, 0);

@@ -85,13 +85,20 @@ def test_softmax_epilogue(dtype, rows, cols):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("B,T,heads,ch", [(2, 1024, 3, 32), (1, 256, 5, 32), (3, 64, 2, 32), (2, 200, 2, 32), (1, 384, 2, 64),
                                           (2, 1024, 1, 64), (1, 72, 3, 64)])
-def test_fused_attention_forward(dtype, B, T, heads, ch):
+@pytest.mark.parametrize("ramp", [False, True])
+def test_fused_attention_forward(dtype, B, T, heads, ch, ramp):
     """nhmc_attn_fwd (tcgen05: S / O in tensor memory, P through shared memory) against fp32 torch attention on the
-    same rounded operands (unet_ffhq.py:408-425).  T = 200 / 72 exercise the ragged last key tile and query tile."""
+    same rounded operands (unet_ffhq.py:408-425).  T = 200 / 72 exercise the ragged last key tile and query tile; `ramp`
+    makes the keys grow along the sequence so that the row maxima keep rising by far more than the lazy-rescale threshold
+    (the accumulator in tensor memory is rescaled many times per row)."""
     from nhmc_b200 import kernels
     g = torch.Generator().manual_seed(7)
     C = heads * ch
-    qk = (torch.randn(B, T, heads, 2, ch, generator=g) * 1.5).cuda().to(dtype)
+    qk = torch.randn(B, T, heads, 2, ch, generator=g) * 1.5
+    if ramp:
+        qk[:, :, :, 1] *= torch.linspace(0.1, 8.0, T).view(1, T, 1, 1)
+        qk[:, :, :, 0] = qk[:, :, :, 0].abs()                    # q . k grows with the key index for about half the channels' signs
+    qk = qk.cuda().to(dtype)
     v = torch.randn(B, C, T, generator=g).cuda().to(dtype)
     out = torch.full((B, T, C), float("nan"), device="cuda", dtype=dtype)
     scale = 1 / math.sqrt(ch)

@@ -20,7 +20,7 @@ lib = _lib.lib()
 host = np.zeros((1024, 12), dtype=np.int64)
 lib.nhmc_attn_prof_dump.argtypes = [C.c_void_p]
 lib.nhmc_attn_prof_dump(host.ctypes.data)
-names = ["total", "pass0", "pass1", "wait_s0full", "ld_pass0", "wait_s1full", "ld_pass1", "wait_pempty", "wait_ofull", "smid", "start"]
+names = ["total", "loop", "max_calc", "wait_sfull", "tmem_ld", "wait_pvdone", "rescale", "n_rescale", "wait_ofull", "smid", "start"]
 h = host[:896]
 t0 = h[:, 10].min()
 order = np.argsort(h[:, 10])

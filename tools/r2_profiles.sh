@@ -24,7 +24,10 @@ python tools/kernel_microbench.py --only ddim --reps 1 > /dev/null 2>&1 && \
 ncu --set full --clock-control none -k regex:ddim_ -s 6 -c 2 -o /tmp/r2p_ddim python tools/kernel_microbench.py --only ddim --reps 1 > $O/r2p_ncu_ddim.log 2>&1
 python tools/kernel_microbench.py --only op --reps 1 > /dev/null 2>&1 && \
 ncu --set full --clock-control none -k regex:"loss_grad|tc_gemm|phase_" -c 30 -o /tmp/r2p_ops python tools/kernel_microbench.py --only op --reps 1 > $O/r2p_ncu_ops.log 2>&1
+python tools/kernel_microbench.py --only attn --reps 1 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:attn_fwd_kernel -c 1 -o /tmp/r2p_attn python tools/kernel_microbench.py --only attn --reps 1 > $O/r2p_ncu_attn.log 2>&1
+ncu -i /tmp/r2p_attn.ncu-rep --page source --csv > $O/r2p_attn_source.csv 2>/dev/null
 # the .ncu-rep files stay on the box (gpurun_out is capped at 64 MiB): only the raw-page CSVs travel
-for r in gn leapfrog ddim ops; do ncu -i /tmp/r2p_$r.ncu-rep --page raw --csv > $O/r2p_${r}_raw.csv 2>/dev/null; done
+for r in gn leapfrog ddim ops attn; do ncu -i /tmp/r2p_$r.ncu-rep --page raw --csv > $O/r2p_${r}_raw.csv 2>/dev/null; done
 du -sh $O
 ls -la $O | tail -30
