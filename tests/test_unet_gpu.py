@@ -100,9 +100,14 @@ def test_fused_attention_forward(dtype, B, T, heads, ch, ramp):
         qk[:, :, :, 0] = qk[:, :, :, 0].abs()                    # q . k grows with the key index for about half the channels' signs
     qk = qk.cuda().to(dtype)
     v = torch.randn(B, C, T, generator=g).cuda().to(dtype)
-    out = torch.full((B, T, C), float("nan"), device="cuda", dtype=dtype)
+    # the output sits between two guard bands: a store outside [B, T, C] (ragged query tiles) would change them
+    guard = 4096
+    buf = torch.full((guard + B * T * C + guard,), 777.0, device="cuda", dtype=dtype)
+    out = buf[guard:guard + B * T * C].view(B, T, C)
+    out.fill_(float("nan"))
     scale = 1 / math.sqrt(ch)
     kernels.attn_fwd(qk.view(B, T, 2 * C), v, out, heads, scale)
+    assert bool((buf[:guard] == 777.0).all()) and bool((buf[guard + B * T * C:] == 777.0).all())
     q = qk[:, :, :, 0].float().permute(0, 2, 1, 3)                       # [B, h, T, ch]
     k = qk[:, :, :, 1].float().permute(0, 2, 1, 3)
     vv = v.float().view(B, heads, ch, T)
