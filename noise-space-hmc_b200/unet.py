@@ -148,12 +148,15 @@ class _AttentionCore(torch.autograd.Function):
         q, k, v = qkv.view(B * nh, 3 * ch, T).split(ch, dim=1)
         da = torch.bmm(wp.t().unsqueeze(0).expand(B, C, C), dh.transpose(1, 2)).view(B * nh, ch, T)   # da[c,t] = sum_o wp[o,c] dh[t,o]
         dprobs = torch.bmm(da.transpose(1, 2), v)                                    # [B*nh, T, T], contiguous
-        dv = torch.bmm(da, probs)                                                    # dv[c,s] = sum_t da[c,t] probs[t,s]
+        # dq, dk, dv land in their slices of one [B*nh, 3ch, T] buffer (strided-batched GEMM outputs: row stride T, batch
+        # stride 3ch*T), not in three tensors that a concatenation pass then copies (224 us at the decoder's T = 4096)
+        dqkv = torch.empty_like(qkv).view(B * nh, 3 * ch, T)
+        torch.bmm(da, probs, out=dqkv[:, 2 * ch:])                                   # dv[c,s] = sum_t da[c,t] probs[t,s]
         dlogits = torch.empty_like(probs)
         kernels.softmax_bwd(probs, dprobs, dlogits, scale)
-        dq = torch.bmm(k, dlogits.transpose(1, 2))                                   # dq[c,t] = sum_s k[c,s] dlogits[t,s]
-        dk = torch.bmm(q, dlogits)                                                   # dk[c,s] = sum_t q[c,t] dlogits[t,s]
-        dqkv = torch.cat([dq, dk, dv], dim=1).view(B, C3, T)
+        torch.bmm(k, dlogits.transpose(1, 2), out=dqkv[:, :ch])                      # dq[c,t] = sum_s k[c,s] dlogits[t,s]
+        torch.bmm(q, dlogits, out=dqkv[:, ch:2 * ch])                                # dk[c,s] = sum_t q[c,t] dlogits[t,s]
+        dqkv = dqkv.view(B, C3, T)
         dtok = torch.bmm(dqkv.transpose(1, 2), wq.unsqueeze(0).expand(B, C3, C))     # [B, T, C], contiguous
         return dtok, None, None, None, None, None
 
@@ -468,13 +471,26 @@ class AttentionBlock(nn.Module):
         w, bias = self.qkv.weight, self.qkv.bias
         wqk_t = _derived(self, "_wqk_t", (w,), lambda: w.detach()[:, :, 0].view(nh, 3 * ch, C)[:, :2 * ch].reshape(2 * C, C).t().contiguous())
         wv = _derived(self, "_wv", (w,), lambda: w.detach()[:, :, 0].view(nh, 3 * ch, C)[:, 2 * ch:].reshape(C, C).contiguous())
-        bqk = _derived(self, "_bqk", (bias,), lambda: bias.detach().view(nh, 3 * ch)[:, :2 * ch].reshape(1, 1, 2 * C).contiguous())
-        bv = _derived(self, "_bv", (bias,), lambda: bias.detach().view(nh, 3 * ch)[:, 2 * ch:].reshape(1, C, 1).contiguous())
-        qk = torch.baddbmm(bqk, tok, wqk_t.unsqueeze(0).expand(B, C, 2 * C))                        # [B, T, 2C]
-        v = torch.baddbmm(bv, wv.unsqueeze(0).expand(B, C, C), tok.transpose(1, 2))                  # [B, C, T]
+        bqk = _derived(self, "_bqk", (bias,), lambda: bias.detach().view(nh, 3 * ch)[:, :2 * ch].reshape(2 * C).contiguous())
+        # no broadcast-bias copies (baddbmm materialises an expanded bias into its output first: 2 x 12 us per block at
+        # T = 1024): q|k take the bias in the GEMM epilogue (addmm with a 1-D bias), v's bias leaves the kernel altogether --
+        # softmax rows sum to one, so it adds W_p b_v to the block output, folded into proj_out's bias (_fused_out_bias)
+        qk = torch.addmm(bqk, tok.reshape(B * T, C), wqk_t).view(B, T, 2 * C)
+        v = torch.bmm(wv.unsqueeze(0).expand(B, C, C), tok.transpose(1, 2))                          # [B, C, T]
         a = torch.empty_like(tok)
         kernels.attn_fwd(qk, v, a, nh, 1.0 / math.sqrt(ch))
         return torch.bmm(a, self.proj_out.weight[:, :, 0].t().unsqueeze(0).expand(B, C, C))         # [B, T, C]
+
+    def _fused_out_bias(self, nh):
+        """proj_out.bias + W_p b_v in fp32 (see _fused_forward)."""
+        w, bias, wp, bp = self.qkv.weight, self.qkv.bias, self.proj_out.weight, self.proj_out.bias
+        C = self.channels
+        ch = C // nh
+
+        def build():
+            bv = bias.detach().float().view(nh, 3 * ch)[:, 2 * ch:].reshape(C)
+            return (bp.detach().float() + wp.detach()[:, :, 0].float() @ bv).contiguous()
+        return _derived(self, "_fused_bias_f32", (w, bias, wp, bp), build)
 
     def forward(self, x):
         B, C, H, W = x.shape
@@ -484,9 +500,10 @@ class AttentionBlock(nn.Module):
         tok = xn.permute(0, 2, 3, 1).reshape(B, T, C)                                # channels-last tokens [B, T, C]
         if not (torch.is_grad_enabled() and tok.requires_grad) and kernels.attn_fwd_supported(tok.dtype, T, C // nh) and tok.is_cuda:
             h = self._fused_forward(tok, nh)
+            b32 = self._fused_out_bias(nh)
         else:
             h = _AttentionCore.apply(tok, self.qkv.weight[:, :, 0], self.qkv.bias, self.proj_out.weight[:, :, 0], None, nh)
-        b32 = _derived(self, "_proj_bias_f32", (self.proj_out.bias,), lambda: self.proj_out.bias.detach().float().contiguous())
+            b32 = _derived(self, "_proj_bias_f32", (self.proj_out.bias,), lambda: self.proj_out.bias.detach().float().contiguous())
         # x + proj_out(a) (unet_ffhq.py:365): residual and proj_out's bias in ONE pass; h [B, T, C] IS channels-last [B, C, H, W]
         return _BiasAdd.apply(x, h.view(B, H, W, C).permute(0, 3, 1, 2), b32)
 
