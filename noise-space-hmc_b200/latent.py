@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, kernels
-from .unet import (UNetModel, _derived, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_bias, _conv_nobias, group_norm_act,
+from .unet import (UNetModel, _derived, _AttentionCore, _BiasAdd, _Norm, _ScaledSoftmax, _Upsample2, _cl, _conv_bias, _conv_nobias, group_norm_act,
                    group_norm_act_skip)
 
 VQ_GN_EPS = 1e-6          # model.py:37-38 Normalize()
@@ -119,14 +119,9 @@ class AttnBlock(nn.Module):
         self.proj_out = nn.Conv2d(channels, channels, 1)
 
     def _qkv(self):
-        c = getattr(self, "_qkv_cache", None)
-        w = self.q.weight
-        if c is None or c[0].device != w.device or c[0].dtype != w.dtype:
-            W = torch.cat([m.weight.detach()[:, :, 0, 0] for m in (self.q, self.k, self.v)], 0).contiguous()
-            b = torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)], 0).contiguous()
-            c = (W, b)
-            self._qkv_cache = c
-        return c
+        ws = tuple(m.weight for m in (self.q, self.k, self.v)) + tuple(m.bias for m in (self.q, self.k, self.v))
+        return _derived(self, "_qkv_cache", ws, lambda: (torch.cat([m.weight.detach()[:, :, 0, 0] for m in (self.q, self.k, self.v)], 0).contiguous(),
+                                                           torch.cat([m.bias.detach() for m in (self.q, self.k, self.v)], 0).contiguous()))
 
     def forward(self, x):
         B, C, H, W = x.shape
@@ -134,13 +129,12 @@ class AttnBlock(nn.Module):
         hn, x = group_norm_act_skip(x, self.norm, _lib.GN_PLAIN)
         tok = hn.permute(0, 2, 3, 1).reshape(B, T, C)                                 # channels-last: no copy
         Wqkv, bqkv = self._qkv()
-        q, k, v = F.linear(tok, Wqkv, bqkv).split(C, dim=-1)                          # one GEMM for q, k, v
-        logits = torch.matmul(q, k.transpose(1, 2))                                   # [B, T(q), T(k)]
-        probs = _ScaledSoftmax.apply(logits, float(int(C) ** (-0.5)))
-        a = torch.matmul(probs, v)                                                    # [B, T, C]
-        h = F.linear(a, self.proj_out.weight[:, :, 0, 0], self.proj_out.bias)
-        out = x.permute(0, 2, 3, 1).reshape(B, T, C) + h
-        return out.view(B, H, W, C).permute(0, 3, 1, 2)
+        # the U-Net's attention core with one head (channel order {q, k, v} * C + c, scale C^-1/2): hand-written input gradient
+        # whose GEMMs write dq, dk, dv into one buffer -- autograd's split backward concatenated them with a 224 us copy of
+        # the [8, 4096, 1536] tensor -- and the residual add + proj_out bias in one pass of bias_add_kernel
+        h = _AttentionCore.apply(tok, Wqkv, bqkv, self.proj_out.weight[:, :, 0, 0], None, 1)
+        b32 = _derived(self, "_proj_bias_f32", (self.proj_out.bias,), lambda: self.proj_out.bias.detach().float().contiguous())
+        return _BiasAdd.apply(x, h.view(B, H, W, C).permute(0, 3, 1, 2), b32)
 
 
 class _UpsampleConv(nn.Module):
