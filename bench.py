@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--deg", default="sr4", help="sr4 | sr16 | inpaint_random | inpaint_box | hdr | deblur_aniso | deblur_gauss | phase_retrieval | color")
     ap.add_argument("--chains", type=int, default=8, help="chains per GPU")
+    ap.add_argument("--cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the library convolutions (1 = autotune at warm-up)")
+    ap.add_argument("--cudnn-limit", type=int, default=-1, help="torch.backends.cudnn.benchmark_limit (-1 = torch's default of 10, 0 = all algorithms)")
     ap.add_argument("--workload", default="pixel", choices=["pixel", "latent"], help="pixel: --algo hmc (BASELINE config[1], the metric's configuration); latent: --algo hmc_latent on the ffhq_latent architecture (BASELINE config[4])")
     ap.add_argument("--lanes", type=int, default=1, help="groups of chains evaluated on their own streams (parallel branches of the captured step)")
     ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the U-Net epilogue kernels (1 = library default)")
@@ -146,7 +148,9 @@ def run_ours(args, rank, world, local_rank):
     from nhmc_b200 import _lib, kernels, sampler, schedule, unet
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    if args.cudnn_limit >= 0:
+        torch.backends.cudnn.benchmark_limit = args.cudnn_limit           # 0 = try every algorithm cuDNN offers
     kernels.set_flags(0 if args.pdl else _lib.F_NO_PDL)
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B, K, W = args.chains, args.steps, max(args.warmup, 3)
