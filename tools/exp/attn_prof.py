@@ -1,4 +1,4 @@
-"""Per-phase cycle counts of the fused attention kernel (instrumented copy tools/exp/attn_prof.cu, built into
+"""Per-phase cycle counts of the fused attention kernel (instrumented build generated from csrc/attn.cu by tools/exp/make_attn_prof.py, built into
 tools/exp/libvar/libnhmc_attnprof.so): where a softmax warp's time goes.  NHMC_LIB_PATH=<that lib> python tools/exp/attn_prof.py"""
 import ctypes as C, math, os, sys
 import numpy as np
