@@ -32,7 +32,7 @@ using namespace tc5;
 
 namespace {
 
-constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 192;
+constexpr int AT_BM = 128, AT_BN = 128, AT_THREADS = 320;   // producer warp, MMA warp, two softmax warpgroups
 constexpr int AT_QBYTES = AT_BM * 128;            // 128 rows x one 128-byte swizzle row (ch = 32: upper half zero-filled by TMA)
 constexpr int AT_KBYTES = AT_BN * 128;
 constexpr int AT_PBYTES = 2 * AT_BM * 128;        // two 64-key chunks of [128 rows][128 bytes]
@@ -75,7 +75,7 @@ template <bool BF16> __device__ __forceinline__ uint32_t pack2(float a, float b)
 // one 64-key shared-memory chunk per half with a full barrier (softmax -> MMA) and a "P V done" barrier (MMA commit -> softmax);
 // O accumulates in TMEM columns [128, 128 + CH).
 enum { B_QFULL = 0, B_KFULL = 1, B_KEMPTY = 5, B_VFULL = 9, B_VEMPTY = 11, B_SFULL = 13, B_SEMPTY = 15, B_PFULL = 17, B_PVDONE = 19,
-       B_OFULL = 21, B_COUNT = 22 };
+       B_OFULL = 21, B_MERGE = 22, B_COUNT = 23 };
 constexpr float AT_RESCALE_LOG2 = 8.0f;   // O and l are rescaled only when a row maximum grew by more than 2^8: p <= 256 in between
 
 template <int CH, bool BF16>
@@ -98,7 +98,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
     prefetch_tensormap(&mapQK);
     prefetch_tensormap(&mapV);
     for (int i = 0; i < B_COUNT; ++i) {                            // S "empty" and P "full": all 128 softmax threads arrive
-      const bool by_softmax = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2);
+      const bool by_softmax = (i >= B_SEMPTY && i < B_SEMPTY + 2) || (i >= B_PFULL && i < B_PFULL + 2) || i == B_MERGE;
       mbar_init(bars + i, by_softmax ? 128 : 1);
     }
     fence_barrier_init();
@@ -144,7 +144,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
         const uint64_t dv = umma_desc_sw128(smem_addr(sm + L::OFF_V + vs * L::VBYTES) + hf * L::VCHUNK);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)                            // 16 keys = 32 bytes along the swizzled row
-          umma_f16(tmem_o, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || hf > 0 || kk > 0) ? 1u : 0u);
+          umma_f16(tmem_o + hf * CH, dp + (uint64_t)(kk * 2), dv + (uint64_t)(kk * 2), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(bars + B_PVDONE + hf);
         if (hf == 1) umma_commit(bars + B_VEMPTY + vs);
       };
@@ -172,118 +172,141 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQK, const __grid_constant
       umma_commit(bars + B_OFULL);
     }
   } else {
+    // Two softmax warpgroups: warps 2-5 take the lower 64 keys of every tile, warps 6-9 the upper 64, each with its own running
+    // maximum, sum and accumulator (O_lo / O_hi in TMEM) -- two independent streams, merged once at the end.  Four softmax
+    // warps per scheduler (two CTAs per SM) instead of two: the FFMA -> MUFU -> FADD / pack / store chain of one warp no
+    // longer leaves the special-function pipe idle.  Thread = query row within its warpgroup.
+    const int hf = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t tmem_s = tmem + lane_base + (uint32_t)(hf * 64);
+    const uint32_t tmem_oh = tmem_o + lane_base + (uint32_t)(hf * CH);
     const bool ragged = (a.T % AT_BN) != 0;
-    // One pass over the keys with a running maximum.  m_used is the maximum the stored exponentials refer to: it follows the
-    // true running maximum lazily (only when that has grown by more than 2^AT_RESCALE_LOG2), and then O (tensor memory) and l
-    // are rescaled -- a warp-uniform, rare event (the first units of a row).  Thread = row: no cross-thread state.
+    // m_used is the maximum the stored exponentials refer to: it follows the true running maximum lazily (only when that has
+    // grown by more than 2^AT_RESCALE_LOG2), and then O (tensor memory) and l are rescaled -- a warp-uniform, rare event.
     float m_used = -INFINITY;
     float l4[4] = {0.f, 0.f, 0.f, 0.f};
-    unsigned char* prow = sm + L::OFF_P + row * 128;
+    unsigned char* pc = sm + L::OFF_P + hf * (AT_BM * 128) + row * 128;
     const int sw = row & 7;
     for (int j = 0; j < nkv; ++j) {
-      const int valid = a.T - j * AT_BN;                          // key columns of this tile that exist
+      const int valid = a.T - j * AT_BN - hf * 64;                 // keys of this half that exist (<= 0: none)
+      const bool mask = ragged && j == nkv - 1;
+      mbar_wait(bars + B_SFULL + hf, j & 1);
+      tc_fence_after();
+      // pass A over the 64 logits of the unit: the maximum (32 at a time: registers)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t r[2][32];
-        mbar_wait(bars + B_SFULL + hf, j & 1);
-        tc_fence_after();
-        tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64), r[0]);
-        tmem_ld32(tmem + lane_base + (uint32_t)(hf * 64 + 32), r[1]);
+      for (int g = 0; g < 2; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + (uint32_t)(g * 32), r);
         tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(bars + B_SEMPTY + hf);                        // this half may be refilled while the exponentials run
-        const bool mask = ragged && j == nkv - 1;
-        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (hf * 64 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[0][i]));
-            if (hf * 64 + 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[1][i]));
-          }
+          for (int i = 0; i < 32; ++i) if (g * 32 + i < valid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(__uint_as_float(r[0][i]), __uint_as_float(r[1][i])));
+          for (int i = 0; i < 32; i += 2) mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
         }
-        const float m_new = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), m_used);
-        const bool first = (j == 0 && hf == 0);
-        const bool grow = (m_new - m_used) * a.c > AT_RESCALE_LOG2;       // also true from -inf (first unit)
-        if (first) {
-          m_used = m_new;                                          // nothing accumulated yet
-        } else if (__any_sync(0xffffffffu, grow)) {
-          // every P V issued so far must have landed in O: the last one is that of the previous unit
-          if (hf == 1) mbar_wait(bars + B_PVDONE + 0, j & 1); else mbar_wait(bars + B_PVDONE + 1, (j - 1) & 1);
-          tc_fence_after();
-          const float f = grow ? ex2((m_used - m_new) * a.c) : 1.0f;     // m_used = -inf -> 0 (a row whose keys so far were all masked)
-          if (grow) m_used = m_new;
-#pragma unroll
-          for (int g = 0; g < CH / 32; ++g) {
-            uint32_t o[32];
-            tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(tmem_o + lane_base + (uint32_t)(g * 32), o);
-          }
-          tmem_st_wait();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) l4[i] *= f;
-        }
-        const float mc = m_used * a.c;
-        // the P V that read this chunk last (previous tile, same half) must be done before it is overwritten
-        if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);
-        unsigned char* pc = prow + hf * (AT_BM * 128);
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          float p[32];
-          if (mask) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = hf * 64 + g * 32 + i < valid ? ex2(fmaf(__uint_as_float(r[g][i]), a.c, -mc)) : 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) p[i] = ex2(fmaf(__uint_as_float(r[g][i]), a.c, -mc));
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int chunk = g * 4 + c4;                         // 16-byte chunk of this row's 128 bytes
-            uint4 w;
-            w.x = pack2<BF16>(p[c4 * 8], p[c4 * 8 + 1]);
-            w.y = pack2<BF16>(p[c4 * 8 + 2], p[c4 * 8 + 3]);
-            w.z = pack2<BF16>(p[c4 * 8 + 4], p[c4 * 8 + 5]);
-            w.w = pack2<BF16>(p[c4 * 8 + 6], p[c4 * 8 + 7]);
-            *reinterpret_cast<uint4*>(pc + ((chunk ^ sw) << 4)) = w;
-          }
-        }
-        tc_fence_before();                                        // orders a rescale's tcgen05.st before the MMA that follows the arrive
-        fence_proxy_async();                                      // generic-proxy stores -> visible to the MMA's async reads
-        mbar_arrive(bars + B_PFULL + hf);
       }
-    }
-    // ---- epilogue: O / l -> out[b, t, h*CH + c] ----
-    mbar_wait(bars + B_OFULL, 0);
-    tc_fence_after();
-    const float inv = __fdividef(1.0f, (l4[0] + l4[1]) + (l4[2] + l4[3]));
-    const int t = q0 + row;
-    const int C = a.heads * CH;
-    unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + (((int64_t)b * a.T + t) * C + (int64_t)h * CH) * 2;
+      const float m_new = fmaxf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), m_used);
+      const bool grow = (m_new - m_used) * a.c > AT_RESCALE_LOG2;        // also true from -inf
+      if (j == 0) {
+        m_used = m_new;                                            // nothing accumulated yet
+      } else if (__any_sync(0xffffffffu, grow)) {
+        mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);              // every P V into this accumulator has landed
+        tc_fence_after();
+        const float f = grow ? ex2((m_used - m_new) * a.c) : 1.0f; // m_used = -inf -> 0 (all keys so far were masked)
+        if (grow) m_used = m_new;
 #pragma unroll
-    for (int g = 0; g < CH / 32; ++g) {
-      uint32_t r[32];
-      tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), r);
-      tmem_ld_wait();
-      if (t < a.T) {
+        for (int g = 0; g < CH / 32; ++g) {
+          uint32_t o[32];
+          tmem_ld32(tmem_oh + (uint32_t)(g * 32), o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st32(tmem_oh + (uint32_t)(g * 32), o);
+        }
+        tmem_st_wait();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l4[i] *= f;
+      }
+      const float mc = m_used * a.c;
+      // the P V that read this chunk last (previous tile) must be done before it is overwritten
+      if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);
+      // pass B: exponentials, 32 at a time; the TMEM half goes back to the MMA issuer after the second load
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + (uint32_t)(g * 32), r);
+        tmem_ld_wait();
+        if (g == 1) { tc_fence_before(); mbar_arrive(bars + B_SEMPTY + hf); }
+        float p[32];
+        if (mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = g * 32 + i < valid ? ex2(fmaf(__uint_as_float(r[i]), a.c, -mc)) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p[i] = ex2(fmaf(__uint_as_float(r[i]), a.c, -mc));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
+          const int chunk = g * 4 + c4;                           // 16-byte chunk of this row's 128 bytes
           uint4 w;
-          w.x = pack2<BF16>(__uint_as_float(r[c4 * 8]) * inv, __uint_as_float(r[c4 * 8 + 1]) * inv);
-          w.y = pack2<BF16>(__uint_as_float(r[c4 * 8 + 2]) * inv, __uint_as_float(r[c4 * 8 + 3]) * inv);
-          w.z = pack2<BF16>(__uint_as_float(r[c4 * 8 + 4]) * inv, __uint_as_float(r[c4 * 8 + 5]) * inv);
-          w.w = pack2<BF16>(__uint_as_float(r[c4 * 8 + 6]) * inv, __uint_as_float(r[c4 * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + g * 64 + c4 * 16) = w;
+          w.x = pack2<BF16>(p[c4 * 8], p[c4 * 8 + 1]);
+          w.y = pack2<BF16>(p[c4 * 8 + 2], p[c4 * 8 + 3]);
+          w.z = pack2<BF16>(p[c4 * 8 + 4], p[c4 * 8 + 5]);
+          w.w = pack2<BF16>(p[c4 * 8 + 6], p[c4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(pc + ((chunk ^ sw) << 4)) = w;
+        }
+      }
+      tc_fence_before();                                          // orders a rescale's tcgen05.st before the MMA that follows the arrive
+      fence_proxy_async();                                        // generic-proxy stores -> visible to the MMA's async reads
+      mbar_arrive(bars + B_PFULL + hf);
+    }
+    // ---- merge the two halves and write  (O_lo f_lo + O_hi f_hi) / (l_lo f_lo + l_hi f_hi)  -> out[b, t, h*CH + c] ----
+    // The upper warpgroup hands (m, l) of its rows over through the Q tile's shared memory: every S product has been read by
+    // now (the last one by this very warpgroup), so nothing reads Q any more.
+    const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    float2* xch = reinterpret_cast<float2*>(sm);
+    if (hf == 1) {
+      xch[row] = make_float2(m_used, l);
+      __threadfence_block();
+      mbar_arrive(bars + B_MERGE);
+    } else {
+      mbar_wait(bars + B_OFULL, 0);
+      tc_fence_after();
+      mbar_wait(bars + B_MERGE, 0);
+      const float2 other = xch[row];
+      const float m_all = fmaxf(m_used, other.x);
+      const float f_lo = ex2((m_used - m_all) * a.c);
+      const float f_hi = other.x == -INFINITY ? 0.f : ex2((other.x - m_all) * a.c);
+      const float inv = __fdividef(1.0f, l * f_lo + other.y * f_hi);
+      const float s_lo = f_lo * inv, s_hi = f_hi * inv;
+      const int t = q0 + row;
+      const int C = a.heads * CH;
+      unsigned char* orow = reinterpret_cast<unsigned char*>(a.out) + (((int64_t)b * a.T + t) * C + (int64_t)h * CH) * 2;
+#pragma unroll
+      for (int g = 0; g < CH / 32; ++g) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_o + lane_base + (uint32_t)(g * 32), r0);
+        tmem_ld32(tmem_o + lane_base + (uint32_t)(CH + g * 32), r1);
+        tmem_ld_wait();
+        if (t < a.T) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r0[c4 * 8 + i]) * s_lo + __uint_as_float(r1[c4 * 8 + i]) * s_hi;
+            uint4 w;
+            w.x = pack2<BF16>(v[0], v[1]);
+            w.y = pack2<BF16>(v[2], v[3]);
+            w.z = pack2<BF16>(v[4], v[5]);
+            w.w = pack2<BF16>(v[6], v[7]);
+            *reinterpret_cast<uint4*>(orow + g * 64 + c4 * 16) = w;
+          }
         }
       }
     }
