@@ -7,15 +7,17 @@
 // One CTA = 128 query rows of one (sample, head); tcgen05, warp-specialised:
 //   warp 0 (one lane)  TMA producer : Q tile once; K tiles through a 3-deep, V tiles through a 2-deep ring
 //   warp 1 (one lane)  MMA issuer   : S = Q K_j^T in two 64-key halves (M128 N64, K = head dim) -> TMEM columns [0,64) / [64,128)
-//                                     O += P V per half (M128 N = head dim, K = 64)            -> TMEM columns [128, 128 + head dim)
-//   warps 2-5          softmax      : thread = query row (tcgen05.ld 32x32b: no shuffles).  ONE pass over the keys with a
-//                                     running maximum: p = 2^(c s - c m_used) where m_used follows the true maximum lazily --
-//                                     only when that has grown by more than 2^8 are O (tcgen05.ld -> scale -> tcgen05.st) and
-//                                     l = sum p rescaled, a warp-uniform and rare event -- so every exponential is evaluated
-//                                     once and Q K^T is computed once.  P goes as bf16 into shared memory in the
-//                                     128-byte-swizzled K-major layout the second MMA reads; the epilogue scales O by 1 / l.
-//                                     A TMEM half goes back to the MMA issuer as soon as its values sit in registers: the
-//                                     next S is produced while the exponentials of this one run.
+//                                     O_half += P V per half (M128 N = head dim, K = 64)       -> TMEM columns [128, 128 + 2 head dim)
+//   warps 2-5, 6-9     softmax      : two warpgroups, one per key half (lower / upper 64 keys of every tile), each with its
+//                                     own running maximum, sum and accumulator (O_lo / O_hi, TMEM columns [128, 128 + 2 head dim)),
+//                                     merged once in the epilogue.  Thread = query row (tcgen05.ld 32x32b: no shuffles).  ONE
+//                                     pass over the keys: p = 2^(c s - c m_used) where m_used follows the running maximum
+//                                     lazily -- only when that has grown by more than 2^8 are O (tcgen05.ld -> scale ->
+//                                     tcgen05.st) and l = sum p rescaled, a warp-uniform and rare event -- so every
+//                                     exponential is evaluated once and Q K^T is computed once.  P goes as bf16 into shared
+//                                     memory in the 128-byte-swizzled K-major layout the second MMA reads.  A TMEM half goes
+//                                     back to the MMA issuer as soon as its values have been read for the second time
+//                                     (maximum, then exponentials, 32 columns at a time: 90 registers, two CTAs per SM).
 // The exponentials are the bound of this kernel: MUFU.EX2 issues one warp instruction per 8 clocks per scheduler, 16 results
 // per clock per SM (tools/exp/exp_mufu.cu, profiles/r2_attn_ncu_summary.md).
 // Layouts (chosen so that every MMA operand is K-major and the producing / consuming GEMMs need no transpose):
