@@ -21,10 +21,11 @@ host = np.zeros((1024, 12), dtype=np.int64)
 lib.nhmc_attn_prof_dump.argtypes = [C.c_void_p]
 lib.nhmc_attn_prof_dump(host.ctypes.data)
 names = ["total", "loop", "max_calc", "wait_sfull", "tmem_ld", "wait_pvdone", "rescale", "n_rescale", "wait_ofull", "smid", "start"]
-h = host[:896]
+h = host[:512]          # lower-half warpgroup of CTAs 0..511 (rows 512.. hold the upper-half warpgroup)
 t0 = h[:, 10].min()
 order = np.argsort(h[:, 10])
 print("CTAs by start time: first 4, middle 4, last 4 (cycles)")
-for idx in list(order[:4]) + list(order[444:448]) + list(order[-4:]):
+for idx in list(order[:4]) + list(order[254:258]) + list(order[-4:]):
     print({n: int(h[idx, i]) if n != "start" else int(h[idx, i] - t0) for i, n in enumerate(names)})
-print("mean over CTAs:", {n: float(h[:, i].mean()) for i, n in enumerate(names[:9])})
+print("mean over CTAs, lower-half warpgroup:", {n: float(h[:, i].mean()) for i, n in enumerate(names[:9])})
+print("mean over CTAs, upper-half warpgroup:", {n: float(host[512:1024, i].mean()) for i, n in enumerate(names[:9])})

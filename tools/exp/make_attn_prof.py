@@ -22,21 +22,23 @@ def instrument(s, pad):
     rep("static constexpr int TOTAL = OFF_BAR + 256;", "static constexpr int TOTAL = OFF_BAR + 256 + %d;" % pad)
     rep("    float m_used = -INFINITY;",
         "    long long pws = 0, pld = 0, pwpv = 0, prs = 0, nrs = 0, pwo = 0, pmx = 0, tq; const long long pstart = PROF_T();\n    float m_used = -INFINITY;")
-    rep("        mbar_wait(bars + B_SFULL + hf, j & 1);\n        tc_fence_after();",
-        "        tq = PROF_T(); mbar_wait(bars + B_SFULL + hf, j & 1); pws += PROF_T() - tq;\n        tc_fence_after(); tq = PROF_T();")
-    rep("        tmem_ld_wait();\n        tc_fence_before();\n        mbar_arrive(bars + B_SEMPTY + hf);",
-        "        tmem_ld_wait(); pld += PROF_T() - tq; tq = PROF_T();\n        tc_fence_before();\n        mbar_arrive(bars + B_SEMPTY + hf);")
-    rep("        const bool first = (j == 0 && hf == 0);", "        pmx += PROF_T() - tq;\n        const bool first = (j == 0 && hf == 0);")
-    rep("          // every P V issued so far must have landed in O: the last one is that of the previous unit", "          tq = PROF_T(); ++nrs;")
-    rep("          for (int i = 0; i < 4; ++i) l4[i] *= f;\n        }", "          for (int i = 0; i < 4; ++i) l4[i] *= f;\n          prs += PROF_T() - tq;\n        }")
-    rep("        if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);",
-        "        tq = PROF_T(); if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1); pwpv += PROF_T() - tq;")
-    rep("    mbar_wait(bars + B_OFULL, 0);", "    const long long pend1 = PROF_T(); mbar_wait(bars + B_OFULL, 0); pwo = PROF_T() - pend1;")
-    rep("      }\n    }\n  }\n  tc_fence_before();\n  __syncthreads();\n  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }\n}",
-        "      }\n    }\n    if (threadIdx.x == 64) {\n      const int cta = blockIdx.y * gridDim.x + blockIdx.x;\n      if (cta < 1024) {\n"
-        "        long long* o = g_attn_prof[cta];\n        o[0] = PROF_T() - pstart; o[1] = pend1 - pstart; o[2] = pmx; o[3] = pws; o[4] = pld; o[5] = pwpv; o[6] = prs; o[7] = nrs; o[8] = pwo;\n"
-        "        unsigned smid; asm(\"mov.u32 %0, %%smid;\" : \"=r\"(smid)); o[9] = smid; o[10] = pstart;\n      }\n    }\n  }\n"
+    rep("      mbar_wait(bars + B_SFULL + hf, j & 1);\n      tc_fence_after();",
+        "      tq = PROF_T(); mbar_wait(bars + B_SFULL + hf, j & 1); pws += PROF_T() - tq;\n      tc_fence_after(); tq = PROF_T();")
+    rep("      const float m_new = fmaxf(", "      pmx += PROF_T() - tq;\n      const float m_new = fmaxf(")
+    rep("        mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);              // every P V into this accumulator has landed",
+        "        tq = PROF_T(); ++nrs; mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);")
+    rep("        for (int i = 0; i < 4; ++i) l4[i] *= f;\n      }", "        for (int i = 0; i < 4; ++i) l4[i] *= f;\n        prs += PROF_T() - tq;\n      }")
+    rep("      if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1);",
+        "      tq = PROF_T(); if (j > 0) mbar_wait(bars + B_PVDONE + hf, (j - 1) & 1); pwpv += PROF_T() - tq;")
+    rep("    const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);", "    const long long pend1 = PROF_T();\n    const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);")
+    rep("      mbar_wait(bars + B_OFULL, 0);", "      tq = PROF_T(); mbar_wait(bars + B_OFULL, 0); pwo = PROF_T() - tq;")
+    # thread 64 = lane 0 of warp 2 (lower-half warpgroup), thread 192 = lane 0 of warp 6 (upper half): rows cta and 512 + cta
+    rep("  tc_fence_before();\n  __syncthreads();\n  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }\n}",
         "  tc_fence_before();\n  __syncthreads();\n  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(tmem); }\n}")
+    rep("        }\n      }\n    }\n  }\n  tc_fence_before();",
+        "        }\n      }\n    }\n    if (threadIdx.x == 64 || threadIdx.x == 192) {\n      const int cta = blockIdx.y * gridDim.x + blockIdx.x;\n      if (cta < 512) {\n"
+        "        long long* o = g_attn_prof[cta + (threadIdx.x == 192 ? 512 : 0)];\n        o[0] = PROF_T() - pstart; o[1] = pend1 - pstart; o[2] = pmx; o[3] = pws; o[4] = pld; o[5] = pwpv; o[6] = prs; o[7] = nrs; o[8] = pwo;\n"
+        "        unsigned smid; asm(\"mov.u32 %0, %%smid;\" : \"=r\"(smid)); o[9] = smid; o[10] = pstart;\n      }\n    }\n  }\n  tc_fence_before();")
     rep('extern "C" int nhmc_attn_fwd',
         'extern "C" int nhmc_attn_prof_dump(long long* host) {\n  return (int)cudaMemcpyFromSymbol(host, g_attn_prof, sizeof(g_attn_prof));\n}\n\nextern "C" int nhmc_attn_fwd')
     return s
