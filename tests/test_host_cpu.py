@@ -46,6 +46,13 @@ def test_argument_errors_are_reported_not_crashed():
     d.kind, d.pad = _lib.OP_PHASE, 64
     assert l.nhmc_op_meas_size(ctypes.byref(d)) == 3 * 384 * 384
     assert l.nhmc_ddim_mask_bytes(196608) == 196608 // 8
+    # fused attention: argument and support checks happen before anything touches a device
+    assert l.nhmc_attn_fwd(1, None, None, None, 1, 64, 1, 32, 1.0, 0, None) == 1
+    buf = ctypes.create_string_buffer(64)
+    a = ctypes.addressof(buf) + (-ctypes.addressof(buf)) % 16
+    assert l.nhmc_attn_fwd(1, a, a, a, 1, 60, 1, 32, 1.0, 0, None) == 1 and b"multiple of 8" in l.nhmc_last_error()
+    assert l.nhmc_attn_fwd(0, a, a, a, 1, 64, 1, 32, 1.0, 0, None) == 3 and b"head_dim" in l.nhmc_last_error()      # fp32: unsupported
+    assert l.nhmc_attn_fwd(1, a, a, a, 1, 64, 1, 48, 1.0, 0, None) == 3
 
 
 def test_schedule_tables_match_golden(golden):
@@ -105,6 +112,12 @@ def test_product_fails_loudly_without_cuda():
                           num_head_channels=16, use_scale_shift_norm=True, resblock_updown=True, dtype=torch.float32)
     with pytest.raises(nhmc_b200.NhmcError):
         m(torch.zeros(1, 3, 64, 64), torch.zeros(1))
+    from nhmc_b200 import kernels
+    assert kernels.attn_fwd_supported(torch.bfloat16, 1024, 32) and not kernels.attn_fwd_supported(torch.float32, 1024, 32)
+    assert not kernels.attn_fwd_supported(torch.bfloat16, 1023, 32) and not kernels.attn_fwd_supported(torch.bfloat16, 256, 16)
+    with pytest.raises(nhmc_b200.NhmcError):
+        kernels.attn_fwd(torch.zeros(1, 64, 64, dtype=torch.bfloat16), torch.zeros(1, 32, 64, dtype=torch.bfloat16),
+                         torch.zeros(1, 64, 32, dtype=torch.bfloat16), 1, 0.1)
 
 
 def test_product_does_not_import_the_oracle():
